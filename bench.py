@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the one hot path: mini-batch forward / backprop / momentum update.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c1|c4] [--precision tf32|fp32]
+
+One "step" = one mini-batch step (forward, output delta, delta backprop, weight gradients, momentum update) over one
+batch of synthetic input.  N = 1 runs BASELINE.json config C3 (784-4096-4096-10, batch 8192); N > 1 runs the same
+per-GPU batch on every rank (weak scaling) with the weight gradients all-reduced by NCCL inside the engine.
+Rank 0 prints ONE JSON line.  `--impl reference` times the UNMODIFIED reference (its cuBLAS build, oracle/_ref) on the
+same config instead.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import importlib.util
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def _load_b2nn():
+    spec = importlib.util.spec_from_file_location("b2nn_binding", os.path.join(ROOT, "cublas-ml_b200", "b2nn.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["b2nn_binding"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+WORKLOADS = {
+    # name: (layers, per-GPU batch, description)
+    "c3": ([784, 4096, 4096, 10], 8192, "C3 synthetic wide MLP 784-4096-4096-10, batch 8192 per GPU"),
+    "c1": ([784, 50, 10], 4200, "C1 MNIST-shaped classifier 784-50-10, batch 4200 (main.cpp:126-157), synthetic pixels"),
+    "c4": ([784] + [8192] * 8 + [10], 8192, "C4 synthetic deep MLP 8x8192 hidden, batch 8192 per GPU"),
+}
+
+
+def step_flops(layers, B):
+    """Algorithmic FLOPs of one step: forward + weight gradient = 2 * sum 2B(l_j+1)l_{j+1};
+    delta backprop = sum_{j>=1} 2B l_j l_{j+1}."""
+    fwd = sum(2.0 * B * (layers[j] + 1) * layers[j + 1] for j in range(len(layers) - 1))
+    bwd = sum(2.0 * B * layers[j] * layers[j + 1] for j in range(1, len(layers) - 1))
+    return 2 * fwd + bwd
+
+
+def num_params(layers):
+    return sum((layers[j] + 1) * layers[j + 1] for j in range(len(layers) - 1))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, device_index: int, uuid: str | None):
+        super().__init__(daemon=True)
+        self.stop_flag = threading.Event()
+        self.sm, self.reasons, self.power = [], set(), []
+        self.sm_max = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+                except Exception:
+                    h = None
+            self.h = h or pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.05)
+
+    def summary(self):
+        if not self.ok or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "note": "NVML unavailable or no samples"}
+        return {"sm_mhz": int(statistics.median(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "power_w_max": round(max(self.power), 1) if self.power else None}
+
+
+def synth_batches(layers, B, nb, seed, rank):
+    """nb batches of B samples, unit-major like the reference's column-major host layout: X (n+1, m) with the ones
+    column FIRST, Y (K, m) one-hot; labels = argmax of a fixed random teacher so the loss can fall."""
+    import torch
+    n, K = layers[0], layers[-1]
+    m = B * nb
+    g = torch.Generator().manual_seed(seed * 1000 + rank)
+    x = torch.empty(n + 1, m, dtype=torch.float32)
+    x[0].fill_(1.0)
+    x[1:].normal_(generator=g)
+    teacher = torch.randn(K, n, generator=torch.Generator().manual_seed(2))
+    lab = (teacher @ x[1:]).argmax(0)
+    y = torch.zeros(K, m, dtype=torch.float32)
+    y[lab, torch.arange(m)] = 1.0
+    return x, y, lab
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return d, "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def dist_setup(n_gpus):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(v, world):
+    if world == 1:
+        return v
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_ours(args):
+    import torch
+    b2nn = _load_b2nn()
+    rank, world, local = dist_setup(args.gpus)
+    layers, B, desc_text = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    K, W = args.steps, max(args.warmup, 3)
+    prec = b2nn.PREC_TF32 if args.precision == "tf32" else b2nn.PREC_FP32
+
+    net = b2nn.Net(local)
+    net.set_layers(layers, b2nn.INIT_2, 42)
+    if world > 1:
+        import torch.distributed as dist
+        uid = [b2nn.Net.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        net.comm_init(rank, world, uid[0])
+
+    nb = K
+    iters = 1
+    if K > 64:
+        nb = max(d for d in range(1, 65) if K % d == 0)
+        iters = K // nb
+    x, y, _lab = synth_batches(layers, B, nb, seed=1, rank=rank)
+    m = B * nb
+    net.set_train_data(x.numpy().reshape(-1), y.numpy().reshape(-1), m)
+
+    def desc(iters_, display_=1 << 30):
+        return b2nn.make_desc(momentum=0.9, rate=0.01, iters=iters_, display=display_, batch_num=nb, classify=True,
+                              act=b2nn.ACT_TANH, out=b2nn.OUT_SOFTMAX, cost=b2nn.COST_CROSSENTROPY, precision=prec,
+                              skip_final_cost=True)
+
+    # ---- warm-up (>= 3 steps), untimed -----------------------------------------------------------------------------
+    wd = b2nn.make_desc(momentum=0.9, rate=0.01, iters=1, display=1 << 30, batch_num=nb, classify=True, act=b2nn.ACT_TANH,
+                        out=b2nn.OUT_SOFTMAX, cost=b2nn.COST_CROSSENTROPY, precision=prec, skip_final_cost=True)
+    done = 0
+    while done < W:
+        net.train(wd)
+        done += nb
+
+    # ---- timed region: exactly K steps, device-timed on the engine's stream (CUDA events inside b2nn_train) --------
+    dev_uuid = None
+    try:
+        dev_uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        pass
+    sampler = ClockSampler(local, dev_uuid)
+    barrier(world)
+    sampler.start()
+    out = net.train(desc(iters))
+    barrier(world)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    assert out.steps == K, (out.steps, K)
+    secs = max_over_ranks(out.loop_seconds, world)
+    value = (B * world * K) / secs
+
+    # ---- roofline leg: same K steps with per-launch CUDA events on the engine stream ---------------------------------
+    net.profile_enable(True)
+    net.train(desc(iters))
+    prof = net.profile_read()
+    net.profile_enable(False)
+    pk, pk_src = peaks()
+    gemm_ms = sum(prof[k]["ms"] for k in ("forward", "backprop", "wgrad"))
+    gemm_fl = sum(prof[k]["flops"] for k in ("forward", "backprop", "wgrad"))
+    gemm_launches = sum(prof[k]["launches"] for k in ("forward", "backprop", "wgrad"))
+    total_ms = sum(v["ms"] for v in prof.values())
+    upd = prof["update"]
+    if args.precision == "tf32":
+        # MEASURED_PEAKS.json holds dense bf16; kind::tf32 runs at half the bf16 rate on the same tensor pipe.
+        peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0)) / 2.0
+        peak_note = f"0.5 x bf16_tflops_sustained ({pk_src}): tf32 is half-rate on the tcgen05 pipe"
+    else:
+        peak = 75.0
+        peak_note = "fp32 FFMA planning value (BASELINE.md); not measured"
+    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::tf32) x3 contractions" if args.precision == "tf32" else "gemm_simt_kernel",
+        "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+        "traffic": None, "peak_source": peak_note,
+        "launches": gemm_launches, "avg_launch_ms": round(gemm_ms / max(gemm_launches, 1), 4),
+        "share_of_step": round(gemm_ms / total_ms, 4) if total_ms > 0 else None,
+        "by_kind": {k: {"ms_per_step": round(v["ms"] / K, 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 and v["flops"] > 0 else None,
+                        "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 and v["bytes"] > 0 else None,
+                        "launches": v["launches"], "tc_launches": v["tc_launches"]} for k, v in prof.items()},
+        "update_hbm": {"achieved_gbs": round(upd["bytes"] / (upd["ms"] * 1e-3) / 1e9, 1) if upd["ms"] > 0 else None,
+                       "peak_gbs": pk.get("hbm_gbs"), "frac": round(upd["bytes"] / (upd["ms"] * 1e-3) / 1e9 / pk.get("hbm_gbs", 6650.0), 4) if upd["ms"] > 0 else None,
+                       "bytes_per_param": 20},
+        "algorithmic_flops_per_step": step_flops(layers, B),
+    }
+
+    # ---- end-to-end leg: host buffers through the C ABI, H2D of every batch and the loss read back inside the region
+    n1, Kout = layers[0] + 1, layers[-1]
+    n_host = min(nb, 4)
+    xh = [torch.empty(n1 * B, dtype=torch.float32).pin_memory() for _ in range(n_host)]
+    yh = [torch.empty(Kout * B, dtype=torch.float32).pin_memory() for _ in range(n_host)]
+    for i in range(n_host):
+        xh[i].copy_(x[:, i * B:(i + 1) * B].reshape(-1))
+        yh[i].copy_(y[:, i * B:(i + 1) * B].reshape(-1))
+    sd = b2nn.make_desc(momentum=0.9, rate=0.01, iters=1, display=1, batch_num=1, classify=True, act=b2nn.ACT_TANH,
+                        out=b2nn.OUT_SOFTMAX, cost=b2nn.COST_CROSSENTROPY, precision=prec, skip_final_cost=True)
+    for i in range(3):
+        net.train_step_host(sd, ctypes.c_void_p(xh[i % n_host].data_ptr()), ctypes.c_void_p(yh[i % n_host].data_ptr()), B, B * world)
+    barrier(world)
+    t0 = time.perf_counter()
+    J = 0.0
+    for i in range(K):
+        J = net.train_step_host(sd, ctypes.c_void_p(xh[i % n_host].data_ptr()), ctypes.c_void_p(yh[i % n_host].data_ptr()), B, B * world)
+    barrier(world)
+    e2e_secs = max_over_ranks(time.perf_counter() - t0, world)
+    e2e = {"value": round(B * world * K / e2e_secs, 1), "unit": "samples/s",
+           "h2d_bytes_per_step": int((layers[0] + Kout) * B * 4), "d2h_bytes_per_step": 8,
+           "ms_per_step": round(e2e_secs / K * 1e3, 4), "last_loss": round(J, 6),
+           "api": "b2nn_train_step_host (pinned host batch in, loss out, every step)"}
+
+    line = None
+    if rank == 0:
+        # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload ---------------------
+        cpu = cpu_baseline(layers, min(B, 2048 if args.workload != "c1" else B))
+        line = {
+            "metric": "train_samples_per_sec", "value": round(value, 1), "unit": "samples/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": round(secs / K * 1e3, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": desc_text, "layers": layers, "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"dp{world}", "precision_mode": args.precision,
+                       "hidden": "tanh", "output": "softmax", "cost": "cross-entropy", "momentum": 0.9,
+                       "l2": "every step reads a different batch; per-step working set (weights+velocity+gradients+activations) exceeds the 126 MB L2"},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(out.kernel_launches),
+            "gpu_launches_tcgen05": int(out.gemm_tc_launches),
+            "tflops": round(step_flops(layers, B) * K * world / secs / 1e12, 2),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    net.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return line
+
+
+def cpu_baseline(layers, sample_B):
+    """The oracle port (oracle/mlp_oracle.cpp, fp32 + OpenMP) timed on this box's host cores: ONE step at batch
+    `sample_B` of the same network — a bounded sample, reported as samples/s."""
+    try:
+        from oracle import oracle as O
+        n, K = layers[0], layers[-1]
+        rng = np.random.default_rng(1)
+        x = rng.standard_normal((sample_B, n)).astype(np.float32)
+        lab = rng.integers(0, K, sample_B)
+        x_cm, y_cm = O.with_bias_colmajor(x), O.one_hot_colmajor(lab, K)
+        th0 = O.init_weights(layers, 2, 42)
+        r = O.train(layers, x_cm, y_cm, sample_B, batch_num=1, iters=1, display=1 << 30, momentum=0.9, rate=0.01,
+                    hidden_act=O.TANH, classify=True, out_act=O.OUT_SOFTMAX, cost=O.COST_CROSSENTROPY, theta0=th0,
+                    precision="f32")
+        return {"value": round(sample_B / r.seconds, 1), "unit": "samples/s", "cores": int(O.lib().oracle_num_threads()),
+                "kind": "port", "sample": f"1 step at batch {sample_B} of the same network (loop time only)",
+                "seconds": round(r.seconds, 3)}
+    except Exception as ex:  # noqa: BLE001
+        return {"value": None, "unit": "samples/s", "cores": None, "kind": "port", "sample": f"failed: {ex}"}
+
+
+def run_reference(args):
+    """The UNMODIFIED reference (cuBLAS Sgemm + its own element-wise kernels) on the same config and GPU.  The class
+    only reports the time of a whole train*Momentum call (setup + loop + final cost, cublasNN.cpp:586-639), so the
+    per-step time is the difference of two calls that differ only in the number of epochs."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    from oracle import oracle as O
+    layers, B, desc_text = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    K, W = args.steps, max(args.warmup, 3)
+    if not O.ref_available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libcublasml_ref.so was not built (needs /root/reference)"}))
+        return None
+    nb = 4 if K % 4 == 0 else (2 if K % 2 == 0 else 1)
+    it_timed = K // nb
+    it_warm = max(1, (W + nb - 1) // nb)
+    x, y, lab = synth_batches(layers, B, nb, seed=1, rank=0)
+    x_rows = np.ascontiguousarray(x[1:].numpy().T)
+    y_rows = lab.numpy().astype(np.float32).reshape(-1, 1)
+    kw = dict(batch_num=nb, display=1 << 30, momentum=0.9, rate=0.01, hidden_act=O.TANH, classify=True,
+              out_act=O.OUT_SOFTMAX, cost=O.COST_CROSSENTROPY, init_kind=2, seed=42)
+    env_note = "NVIDIA_TF32_OVERRIDE=" + os.environ.get("NVIDIA_TF32_OVERRIDE", "unset")
+    O.ref_train(layers, x_rows, y_rows, iters=it_warm, **kw)                       # warm-up call (also warms cuBLAS)
+    t_short = O.ref_train(layers, x_rows, y_rows, iters=it_warm, **kw).seconds
+    t_long = O.ref_train(layers, x_rows, y_rows, iters=it_warm + it_timed, **kw).seconds
+    secs = max(t_long - t_short, 1e-9)
+    value = B * K / secs
+    line = {"impl": "reference", "metric": "train_samples_per_sec", "value": round(value, 1), "unit": "samples/s",
+            "n_gpus": 1, "steps": K, "warmup": it_warm * nb, "ms_per_step": round(secs / K * 1e3, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32" if os.environ.get("NVIDIA_TF32_OVERRIDE", "0") != "1" else "tf32(cuBLAS override)",
+            "data": "synthetic",
+            "config": {"workload": desc_text, "layers": layers, "batch_per_gpu": B, "global_batch": B,
+                       "parallelism": "dp1 (the reference is single-GPU)", "math": env_note,
+                       "timing": "difference of two trainClassifyMomentum calls (epochs E and E+K/nb): setup and final cost cancel"},
+            "tflops": round(step_flops(layers, B) * K / secs / 1e12, 2),
+            "cpu_baseline": {"value": round(value, 1), "unit": "samples/s", "cores": 0, "kind": "reference",
+                             "sample": "unmodified reference built from /root/reference (oracle/_ref), its cuBLAS path on cuda:0; the reference has no CPU path"},
+            "e2e": {"value": round(value, 1), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,231 @@
+// elementwise.cu — the bandwidth-bound kernels around the contractions: output layer (+ cost, argmax, error count),
+// momentum update, layout conversion at the ABI edge, weight-init rescale.
+#include "engine.h"
+#include "epilogue.cuh"
+#include "../../include/b2nn.h"
+
+namespace b2 {
+namespace {
+
+constexpr int OUT_THREADS = 128;
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += sh[i];
+    __syncthreads();
+    return t;   // valid in thread 0
+}
+
+// One thread per sample, like kernelSoftmax (activations.cu:68-88): lanes walk consecutive rows so every access
+// z[k*ld + i] is coalesced.  Fuses what the reference does in up to five launches:
+//   output activation (activations.cu:9-12, 68-88), delta = h - y (kernels.cu:46-51),
+//   per-element cost + Sasum/Sdot (costfunctions.cu:14-26, cublasNN.cpp:552-554, 613-614),
+//   argmax (kernels.cu:74-86, with the out-of-bounds store fixed) and error count (kernels.cu:88-93).
+// Softmax is max-shifted: identical to the reference whenever the reference does not overflow.
+// cost_sum / err_sum are double accumulators.
+__global__ void __launch_bounds__(OUT_THREADS) output_layer_kernel(OutputArgs a, double* cost_sum, double* err_sum) {
+    __shared__ double sh[OUT_THREADS / 32];
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    double cost = 0.0, err = 0.0;
+    if (i < a.rows) {
+        const int K = a.K;
+        float zmax = -INFINITY, total = 0.f;
+        if (a.out_kind == B2NN_OUT_SOFTMAX) {
+            for (int k = 0; k < K; ++k) zmax = fmaxf(zmax, a.z[int64_t(k) * a.ldz + i]);
+            for (int k = 0; k < K; ++k) total += expf(a.z[int64_t(k) * a.ldz + i] - zmax);
+        }
+        float best_h = 0.f, best_y = 0.f; int arg_h = 0, arg_y = 0;
+        for (int k = 0; k < K; ++k) {
+            const float zv = a.z[int64_t(k) * a.ldz + i];
+            float h;
+            if (a.out_kind == B2NN_OUT_SOFTMAX) h = expf(zv - zmax) / total;
+            else if (a.out_kind == B2NN_OUT_SIGMOID) h = sigmoid_f(zv);
+            else h = zv;
+            if (a.h) a.h[int64_t(k) * a.ldh + i] = h;
+            if (h > best_h) { best_h = h; arg_h = k; }
+            if (a.y) {
+                const float yv = a.y[int64_t(k) * a.ldy + i];
+                if (yv > best_y) { best_y = yv; arg_y = k; }
+                const float d = h - yv;
+                if (a.delta) a.delta[int64_t(k) * a.ldd + i] = d;
+                if (cost_sum) {
+                    float c = 0.f;
+                    if (a.cost_kind == B2NN_COST_SQUARED) c = d * d;
+                    else {
+                        if (yv != 0.f) c += -yv * logf(h);
+                        if (a.cost_kind == B2NN_COST_NEGLNMAX && yv != 1.f) c += -(1.f - yv) * logf(1.f - h);
+                        c = fabsf(c);
+                    }
+                    cost += double(c);
+                }
+            }
+        }
+        if (a.pred) a.pred[i] = float(arg_h);
+        if (err_sum) {
+            if (a.y_labels) err = (float(arg_h) != a.y_labels[i]) ? 1.0 : 0.0;
+            else if (a.y)   err = (arg_h != arg_y) ? 1.0 : 0.0;
+        }
+    }
+    if (cost_sum) { const double t = block_sum(cost, sh); if (threadIdx.x == 0 && t != 0.0) atomicAdd(cost_sum, t); }
+    if (err_sum)  { const double t = block_sum(err, sh);  if (threadIdx.x == 0 && t != 0.0) atomicAdd(err_sum, t); }
+}
+
+// v <- mu*v + alpha*g ; theta <- theta + v.  20 bytes per weight (read v, g, theta; write v, theta) against the
+// reference's two cublasSgeam passes at 24 bytes per weight (cublasNN.cpp:558-566, 619-627).  The gradient is already
+// in theta's layout, so the Sgeam transpose disappears.  128-bit accesses, grid-stride, one pass.
+__global__ void __launch_bounds__(256) momentum_update_kernel(float4* __restrict__ theta, float4* __restrict__ vel,
+                                                              const float4* __restrict__ grad, int64_t n4, float mu,
+                                                              float alpha) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = vel[i];
+        const float4 g = __ldcs(grad + i);
+        float4 t = theta[i];
+        v.x = fmaf(mu, v.x, alpha * g.x); v.y = fmaf(mu, v.y, alpha * g.y);
+        v.z = fmaf(mu, v.z, alpha * g.z); v.w = fmaf(mu, v.w, alpha * g.w);
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        vel[i] = v;
+        theta[i] = t;
+    }
+}
+__global__ void momentum_update_tail_kernel(float* theta, float* vel, const float* grad, int64_t from, int64_t count,
+                                            float mu, float alpha) {
+    const int64_t i = from + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < count) {
+        const float v = fmaf(mu, vel[i], alpha * grad[i]);
+        vel[i] = v;
+        theta[i] += v;
+    }
+}
+
+__global__ void theta_ref_to_internal_kernel(const float* __restrict__ ref, float* __restrict__ w, int in, int out,
+                                             int64_t ldw) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t per = int64_t(in) + 1;
+    if (idx >= per * out) return;
+    const int64_t o = idx / per, r = idx % per;          // r: reference row (0 = bias)
+    const int64_t c = (r == 0) ? in : r - 1;             // internal column (bias last)
+    w[o * ldw + c] = ref[idx];
+}
+__global__ void theta_internal_to_ref_kernel(const float* __restrict__ w, float* __restrict__ ref, int in, int out,
+                                             int64_t ldw) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t per = int64_t(in) + 1;
+    if (idx >= per * out) return;
+    const int64_t o = idx / per, r = idx % per;
+    const int64_t c = (r == 0) ? in : r - 1;
+    ref[idx] = w[o * ldw + c];
+}
+
+__global__ void stage_x_kernel(const float* __restrict__ x_ref, int64_t ld_ref, float* __restrict__ x_int,
+                               int64_t ld_int, int64_t rows, int n) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;                             // internal feature row; f == n is the ones row
+    if (i >= rows) return;
+    x_int[int64_t(f) * ld_int + i] = (f == n) ? 1.0f : x_ref[int64_t(f + 1) * ld_ref + i];
+}
+
+// vecVecElementMultiplyGPU (kernels.cu:53-58); only the custom-activation path still needs it un-fused.
+__global__ void multiply_kernel(const float* a, const float* b, float* out, int64_t n) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] * b[i];
+}
+
+__global__ void fill_kernel(float* p, float v, int64_t count) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) p[i] = v;
+}
+
+// theta = u*2*eps - eps (randinitweights.cu:13-31).  nvcc emits FADD (u+u) + FFMA for the reference expression, and
+// IEEE sqrt / division; the same operations are spelled out here so theta_0 is bit-identical.
+__global__ void init_scale_kernel(float* theta, int in, int out, int64_t count, int kind) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float eps = (kind == B2NN_INIT_1) ? __fdiv_rn(1.0f, __fsqrt_rn(float(in)))
+                                            : __fdiv_rn(__fsqrt_rn(6.0f), __fsqrt_rn(float(in + out)));
+    theta[i] = __fmaf_rn(__fadd_rn(theta[i], theta[i]), eps, -eps);
+}
+
+// classToBin (cublasNN.cpp:135-146) on the device, integer indexing (Q10).
+__global__ void labels_to_onehot_kernel(const float* __restrict__ labels, float* __restrict__ y, int64_t ldy,
+                                        int64_t rows, int K) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const int c = int(labels[i]);
+    for (int k = 0; k < K; ++k) y[int64_t(k) * ldy + i] = (k == c) ? 1.0f : 0.0f;
+}
+
+inline unsigned blocks_for(int64_t n, int threads) { return unsigned((n + threads - 1) / threads); }
+
+}  // namespace
+
+cudaError_t output_layer_launch(const OutputArgs& a, cudaStream_t stream) {
+    if (a.rows <= 0) return cudaSuccess;
+    output_layer_kernel<<<blocks_for(a.rows, OUT_THREADS), OUT_THREADS, 0, stream>>>(
+        a, a.cost_sum, a.err_sum);
+    return cudaGetLastError();
+}
+
+cudaError_t momentum_update_launch(float* theta, float* vel, const float* grad, int64_t count, float mu, float alpha,
+                                   cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(theta) | reinterpret_cast<uintptr_t>(vel) |
+                           reinterpret_cast<uintptr_t>(grad)) & 15) == 0;
+    const int64_t n4 = aligned ? count / 4 : 0;
+    if (n4 > 0) {
+        // 148 SMs x 8 resident blocks of 256 threads; grid-stride covers the rest.
+        const int64_t want = (n4 + 255) / 256;
+        const unsigned grid = unsigned(want < 148 * 8 ? want : 148 * 8);
+        momentum_update_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<float4*>(theta), reinterpret_cast<float4*>(vel),
+                                                        reinterpret_cast<const float4*>(grad), n4, mu, alpha);
+    }
+    const int64_t done = n4 * 4;
+    if (done < count)
+        momentum_update_tail_kernel<<<blocks_for(count - done, 256), 256, 0, stream>>>(theta, vel, grad, done, count, mu,
+                                                                                      alpha);
+    return cudaGetLastError();
+}
+
+cudaError_t theta_ref_to_internal_launch(const float* ref, float* w, int in, int out, int64_t ldw, cudaStream_t s) {
+    const int64_t n = (int64_t(in) + 1) * out;
+    theta_ref_to_internal_kernel<<<blocks_for(n, 256), 256, 0, s>>>(ref, w, in, out, ldw);
+    return cudaGetLastError();
+}
+cudaError_t theta_internal_to_ref_launch(const float* w, float* ref, int in, int out, int64_t ldw, cudaStream_t s) {
+    const int64_t n = (int64_t(in) + 1) * out;
+    theta_internal_to_ref_kernel<<<blocks_for(n, 256), 256, 0, s>>>(w, ref, in, out, ldw);
+    return cudaGetLastError();
+}
+cudaError_t stage_x_launch(const float* x_ref, int64_t ld_ref, float* x_int, int64_t ld_int, int64_t rows, int n,
+                           cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    dim3 grid(blocks_for(rows, 256), unsigned(n + 1));
+    stage_x_kernel<<<grid, 256, 0, s>>>(x_ref, ld_ref, x_int, ld_int, rows, n);
+    return cudaGetLastError();
+}
+cudaError_t fill_launch(float* p, float v, int64_t count, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    const int64_t want = (count + 255) / 256;
+    fill_kernel<<<unsigned(want < 148 * 8 ? want : 148 * 8), 256, 0, s>>>(p, v, count);
+    return cudaGetLastError();
+}
+cudaError_t multiply_launch(const float* a, const float* b, float* out, int64_t count, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    multiply_kernel<<<blocks_for(count, 256), 256, 0, s>>>(a, b, out, count);
+    return cudaGetLastError();
+}
+cudaError_t init_scale_launch(float* theta, int in, int out, int64_t count, int kind, cudaStream_t s) {
+    init_scale_kernel<<<blocks_for(count, 256), 256, 0, s>>>(theta, in, out, count, kind);
+    return cudaGetLastError();
+}
+cudaError_t labels_to_onehot_launch(const float* labels, float* y, int64_t ldy, int64_t rows, int K, cudaStream_t s) {
+    labels_to_onehot_kernel<<<blocks_for(rows, 256), 256, 0, s>>>(labels, y, ldy, rows, K);
+    return cudaGetLastError();
+}
+
+}  // namespace b2

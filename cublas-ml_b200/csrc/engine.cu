@@ -1,0 +1,1066 @@
+// engine.cu — context, arenas, the train loop and the C ABI of include/b2nn.h.
+//
+// Engine layout ("unit-major"): every matrix is stored [unit][sample] or [out][in] with the LAST index contiguous.
+//   X_int   (l_0+1) rows of ldx floats : feature rows 0..l_0-1, ones row at index l_0   (reference: ones COLUMN first)
+//   a_j     (l_{j+1}+1) rows of ld     : f(z_j) rows, ones row last, written once at allocation
+//   delta_j l_{j+1} rows of ld
+//   W_j     l_{j+1} rows of ldw_j = roundup4(l_j+1) floats : input weights, bias weight at column l_j
+//   V, G    same arena layout as W (velocity, weight gradient) — the reference's Delta is the transpose (F3); here the
+//           gradient is produced directly in W's layout so the update is a pure streaming pass.
+// Putting the bias unit LAST keeps every bias-free sub-matrix (W without bias column, a without ones row) at the
+// 16-byte aligned allocation base, which TMA requires; the reference's "+mBatch" pointer bump (cublasNN.cpp:676) has
+// no aligned equivalent with the bias first.
+#include "engine.h"
+#include "../../include/b2nn.h"
+
+#include <curand.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+namespace b2 {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct LayerInfo {
+    int in = 0, out = 0;       // l_j, l_{j+1} (bias not counted)
+    int64_t ldw = 0;           // roundup4(in + 1)
+    int64_t w_off = 0;         // offset (floats) inside the internal arenas W / V / G
+    int64_t ref_off = 0;       // thetaPos[j] of the reference arena (cublasNN.cpp:293-301)
+    int64_t ref_size = 0;      // thetaSize[j]
+};
+
+// One contraction of the step, bound to a backend at plan time.
+struct GemmOp {
+    GemmDesc g;
+    bool tc = false;
+    bool zero_first = false;   // split-K accumulates atomically into a zeroed gradient block
+    bool a_is_x = false;       // A is the staged training matrix: the batch start shifts its sample coordinate
+    TcPlan plan;
+};
+
+// Everything one (forward, backward) pass over `rows` samples needs; cached per distinct batch size.
+struct StepPlan {
+    int64_t rows = 0;
+    std::vector<GemmOp> fwd;     // L-1 entries
+    std::vector<GemmOp> wgrad;   // L-1 entries
+    std::vector<GemmOp> bwd;     // entry j computes delta_{j-1} from delta_j (index 0 unused)
+};
+
+struct Workspace {
+    int64_t cap = 0, ld = 0;
+    std::vector<float*> a;       // hidden activations (L-2 buffers)
+    std::vector<float*> delta;   // L-1 buffers
+    std::vector<float*> z;       // only for custom activations (L-2 buffers)
+    float* z_last = nullptr;     // K rows
+    float* scratch = nullptr;    // custom path: act'(z) / product
+    void release() {
+        for (float* p : a) cudaFree(p);
+        for (float* p : delta) cudaFree(p);
+        for (float* p : z) cudaFree(p);
+        cudaFree(z_last); cudaFree(scratch);
+        a.clear(); delta.clear(); z.clear(); z_last = nullptr; scratch = nullptr; cap = ld = 0;
+    }
+};
+
+// ---- NCCL, loaded lazily so the library has no link-time dependency on it ------------------------------------------
+struct Id128 { char bytes[128]; };   // ncclUniqueId, passed by value
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+std::string g_nccl_err;
+
+void load_nccl() {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) { g_nccl_err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return; }
+    auto sym = [&](const char* s) { return dlsym(g_nccl.handle, s); };
+    g_nccl.GetUniqueId = reinterpret_cast<int (*)(void*)>(sym("ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<int (*)(void**, int, Id128, int)>(sym("ncclCommInitRank"));
+    g_nccl.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(sym("ncclAllReduce"));
+    g_nccl.CommDestroy = reinterpret_cast<int (*)(void*)>(sym("ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(sym("ncclGetErrorString"));
+    g_nccl.GroupStart = reinterpret_cast<int (*)()>(sym("ncclGroupStart"));
+    g_nccl.GroupEnd = reinterpret_cast<int (*)()>(sym("ncclGroupEnd"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) g_nccl_err = "NCCL symbols missing";
+}
+constexpr int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_INT64 = 4, NCCL_SUM = 0;
+
+}  // namespace
+}  // namespace b2
+
+using namespace b2;
+
+struct b2nn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    curandGenerator_t gen = nullptr;
+
+    std::vector<int> layers;
+    std::vector<LayerInfo> L;
+    int64_t total_ref = 0, total_int = 0;
+    float *W = nullptr, *V = nullptr, *G = nullptr;
+
+    // training set, engine layout
+    float* X = nullptr; int64_t ldx = 0;
+    float* Y = nullptr; int64_t ldy = 0;
+    int64_t m = 0; int n = 0, K = 0;
+
+    // host-step staging (b2nn_train_step_host)
+    float* Xs = nullptr; float* Ys = nullptr; int64_t lds = 0, caps = 0;
+
+    Workspace ws;
+    std::map<int64_t, StepPlan> plans;   // keyed by rows; valid for (ws, X, precision) they were built with
+    int plans_prec = -1;
+    const float* plans_x = nullptr;
+    int64_t plans_ldx = 0, plans_xtotal = 0;
+    int plans_act = -1;
+
+    double* d_acc = nullptr;             // device accumulators: [0] cost, [1] errors, [2..] display slots
+    int acc_slots = 0;
+    double* h_acc = nullptr;             // pinned mirror
+    std::vector<cudaEvent_t> log_events;
+
+    // data parallel
+    void* comm = nullptr; int rank = 0, nranks = 1;
+    std::vector<cudaEvent_t> grad_ready, grad_reduced;
+
+    int64_t launches = 0, tc_launches = 0;
+
+    // optional per-launch CUDA-event timing (b2nn_profile_*): kind 0 forward, 1 delta backprop, 2 weight gradient,
+    // 3 output layer, 4 momentum update
+    bool profile = false;
+    struct ProfRec { int kind; bool tc; double flops; double bytes; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> prof_pool;
+};
+
+namespace {
+
+int check_device(int device, std::string& why) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        why = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return B2NN_ERR_NO_DEVICE;
+    }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= n) { why = "device index out of range"; return B2NN_ERR_ARG; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { why = "cudaGetDeviceProperties failed"; return B2NN_ERR_CUDA; }
+    if (prop.major != 10) {
+        why = "device is compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor) +
+              "; this library only contains sm_100a code";
+        return B2NN_ERR_NO_DEVICE;
+    }
+    return B2NN_OK;
+}
+
+int resolve_precision(int prec) {
+    if (prec == B2NN_PREC_FP32 || prec == B2NN_PREC_TF32) return prec;
+    const char* e = std::getenv("B2NN_PRECISION");
+    if (e && (std::strcmp(e, "fp32") == 0 || std::strcmp(e, "FP32") == 0)) return B2NN_PREC_FP32;
+    return B2NN_PREC_TF32;
+}
+
+int epi_forward(int act_kind) { return act_kind == B2NN_ACT_SIGMOID ? EPI_SIGMOID : act_kind == B2NN_ACT_TANH ? EPI_TANH : EPI_STORE; }
+int epi_backward(int act_kind) { return act_kind == B2NN_ACT_SIGMOID ? EPI_DSIGMOID : act_kind == B2NN_ACT_TANH ? EPI_DTANH : EPI_STORE; }
+
+int ensure_acc(b2nn_ctx* c, int slots) {
+    if (slots <= c->acc_slots) return B2NN_OK;
+    if (c->d_acc) cudaFree(c->d_acc);
+    if (c->h_acc) cudaFreeHost(c->h_acc);
+    c->d_acc = nullptr; c->h_acc = nullptr; c->acc_slots = 0;
+    B2_CUDA(cudaMalloc(&c->d_acc, sizeof(double) * slots));
+    B2_CUDA(cudaMallocHost(&c->h_acc, sizeof(double) * slots));
+    c->acc_slots = slots;
+    return B2NN_OK;
+}
+
+int ensure_workspace(b2nn_ctx* c, int64_t rows, bool custom) {
+    Workspace& w = c->ws;
+    const int nl = int(c->layers.size());
+    const bool need_z = custom && w.z.empty();
+    if (rows <= w.cap && !need_z) return B2NN_OK;
+    if (rows > w.cap) {
+        w.release();
+        c->plans.clear();
+        w.cap = rows;
+        w.ld = round_up(rows, 32);
+        w.a.assign(nl - 2, nullptr);
+        w.delta.assign(nl - 1, nullptr);
+        for (int j = 0; j < nl - 2; ++j) {
+            const int64_t units = c->layers[j + 1];
+            B2_CUDA(cudaMalloc(&w.a[j], sizeof(float) * (units + 1) * w.ld));
+            B2_CUDA(cudaMemsetAsync(w.a[j], 0, sizeof(float) * units * w.ld, c->stream));
+            B2_CUDA(fill_launch(w.a[j] + units * w.ld, 1.0f, w.ld, c->stream));      // addBiasMatGPU, once (kernels.cu:67-72)
+        }
+        for (int j = 0; j < nl - 1; ++j) {
+            B2_CUDA(cudaMalloc(&w.delta[j], sizeof(float) * int64_t(c->layers[j + 1]) * w.ld));
+            B2_CUDA(cudaMemsetAsync(w.delta[j], 0, sizeof(float) * int64_t(c->layers[j + 1]) * w.ld, c->stream));
+        }
+        B2_CUDA(cudaMalloc(&w.z_last, sizeof(float) * int64_t(c->layers[nl - 1]) * w.ld));
+    }
+    if (custom && w.z.empty()) {
+        w.z.assign(nl - 2, nullptr);
+        int64_t zmax = 0;
+        for (int j = 0; j < nl - 2; ++j) {
+            const int64_t cnt = int64_t(c->layers[j + 1]) * w.ld;
+            B2_CUDA(cudaMalloc(&w.z[j], sizeof(float) * cnt));
+            zmax = std::max(zmax, cnt);
+        }
+        B2_CUDA(cudaMalloc(&w.scratch, sizeof(float) * zmax));
+    }
+    return B2NN_OK;
+}
+
+// Decide the backend of one contraction and, for tcgen05, build its tensor maps.
+void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
+    GemmDesc& g = op.g;
+    op.tc = false; op.zero_first = false; g.split_k = 1;
+    const double work = double(g.M) * double(g.N) * double(g.K);
+    if (allow_split) {
+        // Weight gradient: K = batch rows is long while M x N can be a handful of tiles (50 x 785, 10 x 4097).  Split K so
+        // the grid covers the 148 SMs; partial sums meet in a zeroed gradient block via red.global.add.f32.
+        const int tile_m = (prec == B2NN_PREC_TF32) ? 128 : 64;
+        const int tile_n = (prec == B2NN_PREC_TF32) ? (g.N > 128 ? 256 : g.N > 64 ? 128 : g.N > 32 ? 64 : g.N > 16 ? 32 : 16) : 64;
+        const int64_t tiles = int64_t((g.M + tile_m - 1) / tile_m) * ((g.N + tile_n - 1) / tile_n);
+        const int kblk = (g.K + 31) / 32;
+        if (tiles < 74 && kblk >= 16) {
+            int s = int(std::min<int64_t>(kblk / 8, (296 + tiles - 1) / tiles));
+            if (s > 1) { g.split_k = s; op.zero_first = true; }
+        }
+    }
+    if (prec == B2NN_PREC_TF32 && work >= double(1 << 20) && g.M >= 32) {
+        std::string err;
+        if (tc_plan_build(op.plan, g, err)) op.tc = true;
+    }
+    if (!op.tc && g.split_k > 1) {
+        // FFMA tiles are 64 x 64: re-derive the split for that grid
+        const int64_t tiles = int64_t((g.M + 63) / 64) * ((g.N + 63) / 64);
+        const int kblk = (g.K + 15) / 16;
+        int s = (tiles < 148 && kblk >= 16) ? int(std::min<int64_t>(kblk / 8, (296 + tiles - 1) / tiles)) : 1;
+        g.split_k = std::max(1, s);
+        op.zero_first = g.split_k > 1;
+    }
+}
+
+// x_total: number of sample columns of X that hold data.  The tensor maps over X span all of them so one plan serves
+// every batch of the same size; the batch start only moves the TMA coordinates (run_gemm).
+StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64_t x_total, int prec, int act_kind) {
+    if (c->plans_prec != prec || c->plans_x != X || c->plans_ldx != ldx || c->plans_act != act_kind ||
+        c->plans_xtotal != x_total) {
+        c->plans.clear();
+        c->plans_prec = prec; c->plans_x = X; c->plans_ldx = ldx; c->plans_act = act_kind; c->plans_xtotal = x_total;
+    }
+    auto it = c->plans.find(rows);
+    if (it != c->plans.end()) return it->second;
+    StepPlan& sp = c->plans[rows];
+    sp.rows = rows;
+    const int nl = int(c->layers.size());
+    const int nw = nl - 1;
+    Workspace& w = c->ws;
+    const bool custom = act_kind == B2NN_ACT_CUSTOM;
+    sp.fwd.resize(nw); sp.wgrad.resize(nw); sp.bwd.resize(nw);
+    for (int j = 0; j < nw; ++j) {
+        const LayerInfo& li = c->L[j];
+        // forward  z_j = [a_{j-1}, 1] W_j^T     (cublasNN.cpp:645-646, 653-654, 658-659)
+        GemmOp& f = sp.fwd[j];
+        f.g = GemmDesc();
+        if (j == 0) { f.g.A = X; f.g.lda = ldx; f.a_is_x = true; f.g.a_mn_end = x_total; } else { f.g.A = w.a[j - 1]; f.g.lda = w.ld; }
+        f.g.a_major = 1;
+        f.g.B = c->W + li.w_off; f.g.ldb = li.ldw; f.g.b_major = 0;
+        f.g.M = int(rows); f.g.N = li.out; f.g.K = li.in + 1;
+        if (j < nw - 1) {
+            f.g.D = custom ? w.z[j] : w.a[j]; f.g.ldd = w.ld; f.g.epi = custom ? EPI_STORE : epi_forward(act_kind);
+        } else {
+            f.g.D = w.z_last; f.g.ldd = w.ld; f.g.epi = EPI_STORE;
+        }
+        bind_backend(c, f, prec, false);
+
+        // weight gradient  G_j = delta_j^T [a_{j-1}, 1]  in W_j's layout   (cublasNN.cpp:680-684)
+        GemmOp& g = sp.wgrad[j];
+        g.g = GemmDesc();
+        // Past the batch end X holds the next batch's samples, not zeros; the products vanish anyway because delta_j's
+        // tensor map ends exactly at `rows` and TMA zero-fills it beyond.
+        if (j == 0) { g.g.A = X; g.g.lda = ldx; g.a_is_x = true; g.g.a_k_end = x_total; } else { g.g.A = w.a[j - 1]; g.g.lda = w.ld; }
+        g.g.a_major = 0;
+        g.g.B = w.delta[j]; g.g.ldb = w.ld; g.g.b_major = 0;
+        g.g.D = c->G + li.w_off; g.g.ldd = li.ldw;
+        g.g.M = li.in + 1; g.g.N = li.out; g.g.K = int(rows);
+        g.g.epi = EPI_STORE;
+        bind_backend(c, g, prec, true);
+
+        // delta backprop  delta_{j-1} = (delta_j W_j)[:, no bias] .* f'(z_{j-1})   (cublasNN.cpp:673-676)
+        if (j > 0) {
+            GemmOp& b = sp.bwd[j];
+            b.g = GemmDesc();
+            b.g.A = w.delta[j]; b.g.lda = w.ld; b.g.a_major = 1;
+            b.g.B = c->W + li.w_off; b.g.ldb = li.ldw; b.g.b_major = 1;
+            b.g.M = int(rows); b.g.N = li.in; b.g.K = li.out;
+            if (custom) { b.g.D = w.scratch; b.g.ldd = w.ld; b.g.epi = EPI_STORE; }
+            else { b.g.D = w.delta[j - 1]; b.g.ldd = w.ld; b.g.epi = epi_backward(act_kind); b.g.aux = w.a[j - 1]; b.g.ldaux = w.ld; }
+            bind_backend(c, b, prec, false);
+        }
+    }
+    return sp;
+}
+
+cudaEvent_t prof_event(b2nn_ctx* c) {
+    if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {
+    b2nn_ctx* c; bool on;
+    ProfScope(b2nn_ctx* ctx, int kind, bool tc, double flops, double bytes) : c(ctx), on(ctx->profile) {
+        if (!on) return;
+        b2nn_ctx::ProfRec r{kind, tc, flops, bytes, prof_event(c), prof_event(c)};
+        cudaEventRecord(r.e0, c->stream);
+        c->prof.push_back(r);
+    }
+    ~ProfScope() { if (on) cudaEventRecord(c->prof.back().e1, c->stream); }
+};
+
+int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind) {
+    ProfScope scope(c, kind, op.tc, 2.0 * double(op.g.M) * double(op.g.N) * double(op.g.K), 0.0);
+    if (op.zero_first)
+        B2_CUDA(cudaMemsetAsync(op.g.D, 0, sizeof(float) * size_t(op.g.ldd) * op.g.N, c->stream));
+    if (op.tc) {
+        if (op.a_is_x && x_start != 0) {
+            TcPlan shifted = op.plan;   // tensor maps span the whole training matrix; only the coordinates move
+            if (op.g.a_major) shifted.g.a_mn0 += x_start; else shifted.g.a_k0 += x_start;
+            B2_CUDA(tc_plan_launch(shifted, c->stream));
+        } else {
+            B2_CUDA(tc_plan_launch(op.plan, c->stream));
+        }
+        ++c->tc_launches;
+    } else {
+        GemmDesc g = op.g;
+        if (op.a_is_x) { if (g.a_major) g.a_mn0 += x_start; else g.a_k0 += x_start; }
+        B2_CUDA(gemm_simt_launch(g, c->stream));
+    }
+    ++c->launches;
+    return B2NN_OK;
+}
+
+// forwardPropagate (cublasNN.cpp:642-661) over rows [x_start, x_start+rows) of X; leaves z_{L-2} in ws.z_last.
+int forward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_desc* d) {
+    const int nw = int(sp.fwd.size());
+    const bool custom = d->act_kind == B2NN_ACT_CUSTOM;
+    for (int j = 0; j < nw; ++j) {
+        int rc = run_gemm(c, sp.fwd[j], x_start, 0);
+        if (rc) return rc;
+        if (custom && j < nw - 1) {
+            // User activation: a host function that launches on the legacy default stream (cublasNN.cpp:648, 655).  The
+            // engine stream is a blocking stream, so legacy-stream work is ordered after and before it implicitly.
+            const int64_t cnt = int64_t(c->layers[j + 1]) * c->ws.ld;
+            if (cnt > INT32_MAX) { set_error("custom activation: element count exceeds int"); return B2NN_ERR_ARG; }
+            d->act_fn(c->ws.z[j], c->ws.a[j], int(cnt));
+        }
+    }
+    return B2NN_OK;
+}
+
+// backwardPropagate (cublasNN.cpp:663-685), re-ordered so G_j is produced right after delta_j: with data parallelism
+// its all-reduce then overlaps the backprop of the earlier layers.
+int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_desc* d) {
+    const int nw = int(sp.fwd.size());
+    const bool custom = d->act_kind == B2NN_ACT_CUSTOM;
+    for (int j = nw - 1; j >= 0; --j) {
+        int rc = run_gemm(c, sp.wgrad[j], x_start, 2);
+        if (rc) return rc;
+        if (c->comm && !c->grad_ready.empty()) B2_CUDA(cudaEventRecord(c->grad_ready[j], c->stream));
+        if (j > 0) {
+            rc = run_gemm(c, sp.bwd[j], 0, 1);
+            if (rc) return rc;
+            if (custom) {
+                const int64_t cnt = int64_t(c->layers[j]) * c->ws.ld;
+                if (cnt > INT32_MAX) { set_error("custom activation: element count exceeds int"); return B2NN_ERR_ARG; }
+                // sigGrad = f'(z_{j-1}) by the user's function, then delta = product .* sigGrad (cublasNN.cpp:673, 676)
+                float* tmp = c->ws.delta[j - 1];
+                d->act_grad_fn(c->ws.z[j - 1], tmp, int(cnt));
+                B2_CUDA(multiply_launch(c->ws.scratch, tmp, tmp, cnt, c->stream));
+                ++c->launches;
+            }
+        }
+    }
+    return B2NN_OK;
+}
+
+int output_and_delta(b2nn_ctx* c, const b2nn_train_desc* d, const float* Y, int64_t ldy, int64_t rows, double* cost_slot) {
+    const int nl = int(c->layers.size());
+    Workspace& w = c->ws;
+    const int K = c->layers[nl - 1];
+    const int out_kind = d->classify ? d->out_kind : B2NN_OUT_LINEAR;
+    const int cost_kind = d->classify ? d->cost_kind : B2NN_COST_SQUARED;
+    if (out_kind == B2NN_OUT_CUSTOM || (cost_kind == B2NN_COST_CUSTOM && cost_slot)) {
+        set_error("custom output activation / cost function pointers are not supported by the fused output kernel yet");
+        return B2NN_ERR_ARG;
+    }
+    OutputArgs a{};
+    a.z = w.z_last; a.ldz = w.ld;
+    a.y = Y; a.ldy = ldy;
+    a.h = nullptr; a.ldh = 0;
+    a.delta = w.delta[nl - 2]; a.ldd = w.ld;
+    a.cost_sum = cost_slot; a.pred = nullptr; a.err_sum = nullptr; a.y_labels = nullptr;
+    a.rows = rows; a.K = K; a.out_kind = out_kind; a.cost_kind = cost_kind;
+    {
+        ProfScope scope(c, 3, false, 0.0, 12.0 * double(rows) * K);
+        B2_CUDA(output_layer_launch(a, c->stream));
+    }
+    ++c->launches;
+    return B2NN_OK;
+}
+
+// One mini-batch step on device-resident data: forward, output, backward, momentum update.
+int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, int64_t ldx, int64_t x_total, const float* Y,
+               int64_t ldy, int64_t x_start, int64_t rows, int64_t global_rows, double* cost_slot) {
+    StepPlan& sp = get_plan(c, rows, X, ldx, x_total, prec, d->act_kind);
+    int rc = forward_pass(c, sp, x_start, d);
+    if (rc) return rc;
+    rc = output_and_delta(c, d, Y + x_start, ldy, rows, cost_slot);
+    if (rc) return rc;
+    rc = backward_pass(c, sp, x_start, d);
+    if (rc) return rc;
+    const float alpha = -d->rate / float(global_rows);      // cublasNN.cpp:544, 601
+    const int nw = int(c->L.size());
+    if (c->comm) {
+        // gradient all-reduce per layer on the communication stream, issued in the order the gradients were produced
+        for (int j = nw - 1; j >= 0; --j) {
+            const LayerInfo& li = c->L[j];
+            B2_CUDA(cudaStreamWaitEvent(c->comm_stream, c->grad_ready[j], 0));
+            float* gptr = c->G + li.w_off;
+            int r = g_nccl.AllReduce(gptr, gptr, size_t(li.ldw) * li.out, NCCL_FLOAT32, NCCL_SUM, c->comm, c->comm_stream);
+            if (r != 0) { set_error(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?")); return B2NN_ERR_CUDA; }
+            B2_CUDA(cudaEventRecord(c->grad_reduced[j], c->comm_stream));
+        }
+        for (int j = nw - 1; j >= 0; --j) {
+            const LayerInfo& li = c->L[j];
+            B2_CUDA(cudaStreamWaitEvent(c->stream, c->grad_reduced[j], 0));
+            {
+                ProfScope scope(c, 4, false, 0.0, 20.0 * double(li.ldw) * li.out);
+                B2_CUDA(momentum_update_launch(c->W + li.w_off, c->V + li.w_off, c->G + li.w_off, li.ldw * li.out,
+                                               d->momentum, alpha, c->stream));
+            }
+            ++c->launches;
+        }
+    } else {
+        // all layers in one pass: W, V, G share one arena layout (cublasNN.cpp:558-566 is 2 launches per layer)
+        {
+            ProfScope scope(c, 4, false, 0.0, 20.0 * double(c->total_int));
+            B2_CUDA(momentum_update_launch(c->W, c->V, c->G, c->total_int, d->momentum, alpha, c->stream));
+        }
+        ++c->launches;
+    }
+    return B2NN_OK;
+}
+
+// calcFinalCost / validate (cublasNN.cpp:687-881) over device-resident rows, chunked through the workspace.
+int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, int64_t ldx, const float* Y, int64_t ldy,
+                    const float* labels, int64_t rows, float* pred_out, float* probs_out, int64_t ldp, double* cost,
+                    double* errors) {
+    const int nl = int(c->layers.size());
+    const int K = c->layers[nl - 1];
+    int rc = ensure_acc(c, 2);
+    if (rc) return rc;
+    B2_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 2, c->stream));
+    const int64_t chunk_cap = std::max<int64_t>(c->ws.cap, std::min<int64_t>(rows, 1 << 16));
+    rc = ensure_workspace(c, chunk_cap, d->act_kind == B2NN_ACT_CUSTOM);
+    if (rc) return rc;
+    const int out_kind = d->classify ? d->out_kind : B2NN_OUT_LINEAR;
+    const int cost_kind = d->classify ? d->cost_kind : B2NN_COST_SQUARED;
+    if (out_kind == B2NN_OUT_CUSTOM || cost_kind == B2NN_COST_CUSTOM) {
+        set_error("custom output activation / cost function pointers are not supported by the fused output kernel yet");
+        return B2NN_ERR_ARG;
+    }
+    for (int64_t s = 0; s < rows; s += c->ws.cap) {
+        const int64_t r = std::min<int64_t>(c->ws.cap, rows - s);
+        StepPlan& sp = get_plan(c, r, X, ldx, rows, prec, d->act_kind);
+        rc = forward_pass(c, sp, s, d);
+        if (rc) return rc;
+        OutputArgs a{};
+        a.z = c->ws.z_last; a.ldz = c->ws.ld;
+        a.y = Y ? Y + s : nullptr; a.ldy = ldy;
+        a.h = probs_out ? probs_out + s : nullptr; a.ldh = ldp;
+        a.delta = nullptr; a.ldd = 0;
+        a.cost_sum = (Y && cost) ? c->d_acc : nullptr;
+        a.pred = pred_out ? pred_out + s : nullptr;
+        a.err_sum = (d->classify && errors && (Y || labels)) ? c->d_acc + 1 : nullptr;
+        a.y_labels = labels ? labels + s : nullptr;
+        a.rows = r; a.K = K; a.out_kind = out_kind; a.cost_kind = cost_kind;
+        B2_CUDA(output_layer_launch(a, c->stream));
+        ++c->launches;
+    }
+    B2_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    if (cost) *cost = d->classify ? c->h_acc[0] / double(rows) : c->h_acc[0] / (2.0 * double(rows));   // :735, :741
+    if (errors) *errors = c->h_acc[1];
+    return B2NN_OK;
+}
+
+// Stage a reference-layout host matrix (rows x (n+1) col-major, ones column FIRST, ld = ld_host) into engine layout.
+int stage_x_from_host(b2nn_ctx* c, const float* x_host, int64_t ld_host, int64_t row0, int64_t rows, int n, float* x_dev,
+                      int64_t ld_dev, bool fill_ones) {
+    // feature f of the engine matrix is column f+1 of the reference matrix: one strided 2-D copy, no temp buffer
+    B2_CUDA(cudaMemcpy2DAsync(x_dev, sizeof(float) * ld_dev, x_host + ld_host + row0, sizeof(float) * ld_host,
+                              sizeof(float) * rows, size_t(n), cudaMemcpyHostToDevice, c->stream));
+    if (fill_ones) B2_CUDA(fill_launch(x_dev + int64_t(n) * ld_dev, 1.0f, ld_dev, c->stream));
+    return B2NN_OK;
+}
+
+int validate_desc(const b2nn_ctx* c, const b2nn_train_desc* d) {
+    if (!c || !d) { set_error("null context or descriptor"); return B2NN_ERR_ARG; }
+    if (c->layers.size() < 3) { set_error("set_layers must be called first with >= 3 layers (cublasNN.cpp:657 needs a hidden layer)"); return B2NN_ERR_ARG; }
+    if (d->act_kind < 0 || d->act_kind > B2NN_ACT_CUSTOM) { set_error("bad act_kind"); return B2NN_ERR_ARG; }
+    if (d->act_kind == B2NN_ACT_CUSTOM && (!d->act_fn || !d->act_grad_fn)) { set_error("custom activation needs act_fn and act_grad_fn"); return B2NN_ERR_ARG; }
+    if (d->classify && (d->out_kind < 0 || d->out_kind > B2NN_OUT_CUSTOM)) { set_error("bad out_kind"); return B2NN_ERR_ARG; }
+    return B2NN_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+const char* b2nn_last_error(void) { return g_last_error.c_str(); }
+const char* b2nn_version(void) { return "b2nn 0.1 (sm_100a)"; }
+
+int b2nn_device_ok(void) {
+    std::string why;
+    return check_device(-1, why) == B2NN_OK ? 1 : 0;
+}
+
+int b2nn_create(b2nn_ctx** out, int device) {
+    if (!out) { set_error("null out pointer"); return B2NN_ERR_ARG; }
+    *out = nullptr;
+    std::string why;
+    int rc = check_device(device, why);
+    if (rc) { set_error(why); return rc; }
+    if (device < 0) cudaGetDevice(&device);
+    B2_CUDA(cudaSetDevice(device));
+    std::unique_ptr<b2nn_ctx> c(new b2nn_ctx);
+    c->device = device;
+    B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamDefault));          // blocking: orders with user ops on stream 0
+    B2_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    if (curandCreateGenerator(&c->gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS) {   // cublasNN.cpp:26
+        set_error("curandCreateGenerator failed"); return B2NN_ERR_CUDA;
+    }
+    curandSetStream(c->gen, c->stream);
+    *out = c.release();
+    return B2NN_OK;
+}
+
+void b2nn_destroy(b2nn_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    c->ws.release();
+    cudaFree(c->W); cudaFree(c->V); cudaFree(c->G);
+    cudaFree(c->X); cudaFree(c->Y); cudaFree(c->Xs); cudaFree(c->Ys);
+    cudaFree(c->d_acc);
+    if (c->h_acc) cudaFreeHost(c->h_acc);
+    for (auto e : c->log_events) cudaEventDestroy(e);
+    for (auto& r : c->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto e : c->prof_pool) cudaEventDestroy(e);
+    for (auto e : c->grad_ready) cudaEventDestroy(e);
+    for (auto e : c->grad_reduced) cudaEventDestroy(e);
+    if (c->gen) curandDestroyGenerator(c->gen);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    delete c;
+}
+
+int b2nn_set_layers(b2nn_ctx* c, const int* layers, int n_layers, int init_kind, b2nn_init_fn custom_init, uint64_t seed,
+                    int seed_is_clock) {
+    if (!c || !layers) { set_error("null argument"); return B2NN_ERR_ARG; }
+    if (n_layers < 3) { set_error("need at least one hidden layer (cublasNN.cpp:657)"); return B2NN_ERR_ARG; }
+    for (int i = 0; i < n_layers; ++i) if (layers[i] < 1) { set_error("layer width must be >= 1"); return B2NN_ERR_ARG; }
+    if (init_kind != B2NN_INIT_1 && init_kind != B2NN_INIT_2 && !(init_kind == B2NN_INIT_CUSTOM && custom_init)) {
+        set_error("bad init_kind"); return B2NN_ERR_ARG;
+    }
+    B2_CUDA(cudaSetDevice(c->device));
+    c->layers.assign(layers, layers + n_layers);
+    c->L.assign(n_layers - 1, LayerInfo());
+    c->total_ref = 0; c->total_int = 0;
+    for (int j = 0; j < n_layers - 1; ++j) {
+        LayerInfo& li = c->L[j];
+        li.in = layers[j]; li.out = layers[j + 1];
+        li.ldw = round_up(int64_t(li.in) + 1, 4);
+        li.ref_off = c->total_ref; li.ref_size = (int64_t(li.in) + 1) * li.out;
+        li.w_off = c->total_int;
+        c->total_ref += li.ref_size;
+        c->total_int += li.ldw * li.out;      // multiple of 4 floats: every layer block starts 16-byte aligned
+    }
+    cudaFree(c->W); cudaFree(c->V); cudaFree(c->G);
+    c->W = c->V = c->G = nullptr;
+    c->plans.clear(); c->ws.release();
+    if (cudaMalloc(&c->W, sizeof(float) * c->total_int) != cudaSuccess ||
+        cudaMalloc(&c->V, sizeof(float) * c->total_int) != cudaSuccess ||
+        cudaMalloc(&c->G, sizeof(float) * c->total_int) != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("cudaMalloc Failed");     // reference text, cublasNN.cpp:309
+        return B2NN_ERR_ALLOC;
+    }
+    B2_CUDA(cudaMemsetAsync(c->W, 0, sizeof(float) * c->total_int, c->stream));
+    B2_CUDA(cudaMemsetAsync(c->V, 0, sizeof(float) * c->total_int, c->stream));
+    B2_CUDA(cudaMemsetAsync(c->G, 0, sizeof(float) * c->total_int, c->stream));
+
+    // One uniform draw over the whole reference-layout arena, then the per-layer rescale (cublasNN.cpp:314-326).
+    float* ref = nullptr;
+    B2_CUDA(cudaMalloc(&ref, sizeof(float) * c->total_ref));
+    const unsigned long long s = seed_is_clock ? (unsigned long long)clock() : (unsigned long long)seed;   // :27
+    curandSetPseudoRandomGeneratorSeed(c->gen, s);
+    curandSetGeneratorOffset(c->gen, 0ULL);
+    if (curandGenerateUniform(c->gen, ref, size_t(c->total_ref)) != CURAND_STATUS_SUCCESS) {
+        cudaFree(ref); set_error("curandGenerateUniform failed"); return B2NN_ERR_CUDA;
+    }
+    for (int j = 0; j < n_layers - 1; ++j) {
+        const LayerInfo& li = c->L[j];
+        if (init_kind == B2NN_INIT_CUSTOM) {
+            if (li.ref_size > INT32_MAX) { cudaFree(ref); set_error("custom init: layer too large for int count"); return B2NN_ERR_ARG; }
+            custom_init(ref + li.ref_off, li.in + 1, li.out, int(li.ref_size));       // legacy stream, ordered by the blocking engine stream
+        } else {
+            B2_CUDA(init_scale_launch(ref + li.ref_off, li.in + 1, li.out, li.ref_size, init_kind, c->stream));
+        }
+    }
+    if (init_kind == B2NN_INIT_CUSTOM) B2_CUDA(cudaDeviceSynchronize());
+    for (int j = 0; j < n_layers - 1; ++j) {
+        const LayerInfo& li = c->L[j];
+        B2_CUDA(theta_ref_to_internal_launch(ref + li.ref_off, c->W + li.w_off, li.in, li.out, li.ldw, c->stream));
+    }
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(ref);
+    return B2NN_OK;
+}
+
+int64_t b2nn_num_weights(const b2nn_ctx* c) { return c ? c->total_ref : 0; }
+
+int b2nn_get_weights(b2nn_ctx* c, float* host, int64_t count) {
+    if (!c || !host || count != c->total_ref || !c->W) { set_error("get_weights: bad arguments"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    float* ref = nullptr;
+    B2_CUDA(cudaMalloc(&ref, sizeof(float) * c->total_ref));
+    for (const LayerInfo& li : c->L)
+        B2_CUDA(theta_internal_to_ref_launch(c->W + li.w_off, ref + li.ref_off, li.in, li.out, li.ldw, c->stream));
+    B2_CUDA(cudaMemcpyAsync(host, ref, sizeof(float) * c->total_ref, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(ref);
+    return B2NN_OK;
+}
+
+int b2nn_set_weights(b2nn_ctx* c, const float* host, int64_t count) {
+    if (!c || !host || count != c->total_ref || !c->W) { set_error("set_weights: bad arguments"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    float* ref = nullptr;
+    B2_CUDA(cudaMalloc(&ref, sizeof(float) * c->total_ref));
+    B2_CUDA(cudaMemcpyAsync(ref, host, sizeof(float) * c->total_ref, cudaMemcpyHostToDevice, c->stream));
+    for (const LayerInfo& li : c->L)
+        B2_CUDA(theta_ref_to_internal_launch(ref + li.ref_off, c->W + li.w_off, li.in, li.out, li.ldw, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(ref);
+    return B2NN_OK;
+}
+
+int b2nn_set_train_data(b2nn_ctx* c, const float* x, const float* y, int64_t m, int n_plus_1, int k) {
+    if (!c || !x || !y || m < 1) { set_error("set_train_data: bad arguments"); return B2NN_ERR_ARG; }
+    if (c->layers.empty()) { set_error("set_layers must precede set_train_data (main.cpp:125)"); return B2NN_ERR_ARG; }
+    if (n_plus_1 != c->layers[0] + 1 || k != c->layers.back()) { set_error("data shape does not match the layers"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    cudaFree(c->X); cudaFree(c->Y); c->X = c->Y = nullptr;
+    c->plans.clear();
+    c->m = m; c->n = n_plus_1 - 1; c->K = k;
+    c->ldx = round_up(m, 32); c->ldy = c->ldx;
+    if (cudaMalloc(&c->X, sizeof(float) * c->ldx * n_plus_1) != cudaSuccess ||
+        cudaMalloc(&c->Y, sizeof(float) * c->ldy * k) != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("cudaMalloc Failed");      // cublasNN.cpp:366
+        return B2NN_ERR_ALLOC;
+    }
+    B2_CUDA(cudaMemsetAsync(c->X, 0, sizeof(float) * c->ldx * n_plus_1, c->stream));
+    B2_CUDA(cudaMemsetAsync(c->Y, 0, sizeof(float) * c->ldy * k, c->stream));
+    int rc = stage_x_from_host(c, x, m, 0, m, c->n, c->X, c->ldx, true);
+    if (rc) return rc;
+    B2_CUDA(cudaMemcpy2DAsync(c->Y, sizeof(float) * c->ldy, y, sizeof(float) * m, sizeof(float) * m, size_t(k),
+                              cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2NN_OK;
+}
+
+int b2nn_reset_velocity(b2nn_ctx* c) {
+    if (!c || !c->V) { set_error("reset_velocity: no network"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    B2_CUDA(cudaMemsetAsync(c->V, 0, sizeof(float) * c->total_int, c->stream));
+    return B2NN_OK;
+}
+
+int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log_user, b2nn_train_result* result) {
+    auto t_call0 = std::chrono::steady_clock::now();                    // cublasNN.cpp:529, 586
+    int rc = validate_desc(c, d);
+    if (rc) return rc;
+    if (!c->X || !c->Y) { set_error("set_train_data must precede train (copyDataGPU, main.cpp:87)"); return B2NN_ERR_ARG; }
+    if (d->batch_num < 1 || int64_t(d->batch_num) > c->m) { set_error("batch_num must be in [1, m]"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    const int prec = resolve_precision(d->precision);
+    const int display = d->display > 0 ? d->display : 1;               // Q5
+    const int nb = d->batch_num;
+    const int64_t bs = c->m / nb;                                      // cublasNN.cpp:401
+    const int64_t last_rows = c->m - int64_t(nb - 1) * bs;             // last batch absorbs the remainder (:429)
+
+    B2_CUDA(cudaMemsetAsync(c->V, 0, sizeof(float) * c->total_int, c->stream));   // :533-534, :590-591
+    rc = ensure_workspace(c, last_rows, d->act_kind == B2NN_ACT_CUSTOM);
+    if (rc) return rc;
+    const int n_disp = d->iters / display;
+    rc = ensure_acc(c, 2 + std::max(n_disp, 1));
+    if (rc) return rc;
+    B2_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * c->acc_slots, c->stream));
+    while (int(c->log_events.size()) < 32) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->log_events.push_back(e); }
+
+    // data parallel: the update uses the GLOBAL batch size (sum over ranks of this batch's rows)
+    std::vector<int64_t> global_rows(nb);
+    for (int b = 0; b < nb; ++b) global_rows[b] = (b == nb - 1) ? last_rows : bs;
+    if (c->comm) {
+        int64_t* tmp = nullptr;
+        B2_CUDA(cudaMalloc(&tmp, sizeof(int64_t) * nb));
+        B2_CUDA(cudaMemcpyAsync(tmp, global_rows.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice, c->stream));
+        int r = g_nccl.AllReduce(tmp, tmp, size_t(nb), NCCL_INT64, NCCL_SUM, c->comm, c->stream);
+        if (r != 0) { cudaFree(tmp); set_error("ncclAllReduce(batch rows) failed"); return B2NN_ERR_CUDA; }
+        B2_CUDA(cudaMemcpyAsync(global_rows.data(), tmp, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(tmp);
+    }
+
+    if (c->comm) {
+        while (c->grad_ready.size() < c->L.size()) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->grad_ready.push_back(e); }
+        while (c->grad_reduced.size() < c->L.size()) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->grad_reduced.push_back(e); }
+    }
+    const int64_t launches0 = c->launches, tc0 = c->tc_launches;
+    cudaEvent_t ev0, ev1;
+    B2_CUDA(cudaEventCreate(&ev0)); B2_CUDA(cudaEventCreate(&ev1));
+    B2_CUDA(cudaEventRecord(ev0, c->stream));
+
+    int issued = 0, reported = 0;
+    std::vector<int> slot_iter;
+    auto flush_logs = [&](bool block) -> int {
+        while (reported < issued) {
+            cudaEvent_t e = c->log_events[reported % c->log_events.size()];
+            cudaError_t q = block ? cudaEventSynchronize(e) : cudaEventQuery(e);
+            if (q == cudaErrorNotReady) { (void)cudaGetLastError(); break; }
+            if (q != cudaSuccess) { set_error(std::string("log event: ") + cudaGetErrorString(q)); return B2NN_ERR_CUDA; }
+            const int64_t rows0 = global_rows[0];
+            double J = c->h_acc[2 + reported];
+            J = d->classify ? J / double(rows0) : J / (2.0 * double(rows0));       // :554, :615
+            if (log) log(log_user, slot_iter[reported], float(J));
+            ++reported;
+        }
+        return B2NN_OK;
+    };
+
+    for (int it = 0; it < d->iters; ++it) {                                         // :540-568, :597-629
+        for (int b = 0; b < nb; ++b) {
+            const int64_t rows = (b == nb - 1) ? last_rows : bs;
+            const bool show = ((it + 1) % display == 0) && b == 0 && issued < n_disp;   // :550, :610
+            double* slot = show ? c->d_acc + 2 + issued : nullptr;
+            rc = train_step(c, d, prec, c->X, c->ldx, c->m, c->Y, c->ldy, int64_t(b) * bs, rows, global_rows[b], slot);
+            if (rc) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
+            if (show) {
+                if (issued - reported >= int(c->log_events.size())) { rc = flush_logs(true); if (rc) return rc; }
+                if (c->comm) {
+                    // the printed cost is the global batch-0 cost: sum the per-rank partial sums
+                    int r = g_nccl.AllReduce(slot, slot, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+                    if (r != 0) { set_error("ncclAllReduce(cost) failed"); return B2NN_ERR_CUDA; }
+                }
+                B2_CUDA(cudaMemcpyAsync(c->h_acc + 2 + issued, slot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                B2_CUDA(cudaEventRecord(c->log_events[issued % c->log_events.size()], c->stream));
+                slot_iter.push_back(it);
+                ++issued;
+            }
+        }
+        rc = flush_logs(false);
+        if (rc) return rc;
+    }
+    B2_CUDA(cudaEventRecord(ev1, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    rc = flush_logs(true);
+    if (rc) return rc;
+    float ms = 0.f;
+    B2_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    const int64_t loop_launches = c->launches - launches0, loop_tc = c->tc_launches - tc0;
+
+    double final_cost = 0.0, errors = 0.0;
+    if (!d->skip_final_cost) {                                                       // :574, :635
+        rc = evaluate_device(c, d, prec, c->X, c->ldx, c->Y, c->ldy, nullptr, c->m, nullptr, nullptr, 0, &final_cost,
+                             &errors);
+        if (rc) return rc;
+        if (c->comm) {
+            // data-parallel: rank-local sums -> global cost / error count
+            double loc[3] = {d->classify ? final_cost * double(c->m) : final_cost * 2.0 * double(c->m), errors, double(c->m)};
+            double* t = nullptr;
+            B2_CUDA(cudaMalloc(&t, sizeof(double) * 3));
+            B2_CUDA(cudaMemcpyAsync(t, loc, sizeof(loc), cudaMemcpyHostToDevice, c->stream));
+            int r = g_nccl.AllReduce(t, t, 3, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+            if (r != 0) { cudaFree(t); set_error("ncclAllReduce(final cost) failed"); return B2NN_ERR_CUDA; }
+            B2_CUDA(cudaMemcpyAsync(loc, t, sizeof(loc), cudaMemcpyDeviceToHost, c->stream));
+            B2_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(t);
+            final_cost = d->classify ? loc[0] / loc[2] : loc[0] / (2.0 * loc[2]);
+            errors = loc[1];
+        }
+    }
+    auto t_call1 = std::chrono::steady_clock::now();
+    if (result) {
+        result->call_seconds = std::chrono::duration<double>(t_call1 - t_call0).count();
+        result->loop_seconds = double(ms) * 1e-3;
+        result->final_cost = final_cost;
+        result->error_count = errors;
+        result->steps = int64_t(d->iters) * nb;
+        result->kernel_launches = loop_launches;
+        result->gemm_tc_launches = loop_tc;
+    }
+    return B2NN_OK;
+}
+
+int b2nn_train_step_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const float* y, int64_t rows,
+                         int64_t global_rows, float* J_out) {
+    int rc = validate_desc(c, d);
+    if (rc) return rc;
+    if (!x || !y || rows < 1) { set_error("train_step_host: bad arguments"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    const int prec = resolve_precision(d->precision);
+    const int n = c->layers[0], K = c->layers.back();
+    if (rows > c->caps) {
+        cudaFree(c->Xs); cudaFree(c->Ys); c->Xs = c->Ys = nullptr;
+        c->caps = rows; c->lds = round_up(rows, 32);
+        B2_CUDA(cudaMalloc(&c->Xs, sizeof(float) * c->lds * (n + 1)));
+        B2_CUDA(cudaMalloc(&c->Ys, sizeof(float) * c->lds * K));
+        B2_CUDA(cudaMemsetAsync(c->Xs, 0, sizeof(float) * c->lds * (n + 1), c->stream));
+        B2_CUDA(cudaMemsetAsync(c->Ys, 0, sizeof(float) * c->lds * K, c->stream));
+        B2_CUDA(fill_launch(c->Xs + int64_t(n) * c->lds, 1.0f, c->lds, c->stream));
+    }
+    rc = ensure_workspace(c, rows, d->act_kind == B2NN_ACT_CUSTOM);
+    if (rc) return rc;
+    rc = ensure_acc(c, 3);
+    if (rc) return rc;
+    // H2D of this step's inputs (skipping the reference's ones column: the engine keeps its own ones row)
+    rc = stage_x_from_host(c, x, rows, 0, rows, n, c->Xs, c->lds, false);
+    if (rc) return rc;
+    B2_CUDA(cudaMemcpy2DAsync(c->Ys, sizeof(float) * c->lds, y, sizeof(float) * rows, sizeof(float) * rows, size_t(K),
+                              cudaMemcpyHostToDevice, c->stream));
+    double* slot = J_out ? c->d_acc + 2 : nullptr;
+    if (slot) B2_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), c->stream));
+    const int64_t g = global_rows > 0 ? global_rows : rows;
+    rc = train_step(c, d, prec, c->Xs, c->lds, rows, c->Ys, c->lds, 0, rows, g, slot);
+    if (rc) return rc;
+    if (slot) {
+        if (c->comm) {
+            int r = g_nccl.AllReduce(slot, slot, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+            if (r != 0) { set_error("ncclAllReduce(cost) failed"); return B2NN_ERR_CUDA; }
+        }
+        B2_CUDA(cudaMemcpyAsync(c->h_acc + 2, slot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+        const double J = c->h_acc[2];
+        *J_out = float(d->classify ? J / double(g) : J / (2.0 * double(g)));
+    }
+    return B2NN_OK;
+}
+
+int b2nn_evaluate(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const float* y, int64_t rows, int y_is_labels,
+                  double* cost_out, double* errors_out) {
+    int rc = validate_desc(c, d);
+    if (rc) return rc;
+    if (!x || !y || rows < 1) { set_error("evaluate: bad arguments"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    const int prec = resolve_precision(d->precision);
+    const int n = c->layers[0], K = c->layers.back();
+    const int64_t ld = round_up(rows, 32);
+    float *xd = nullptr, *yd = nullptr, *lab = nullptr;
+    B2_CUDA(cudaMalloc(&xd, sizeof(float) * ld * (n + 1)));
+    B2_CUDA(cudaMalloc(&yd, sizeof(float) * ld * K));
+    B2_CUDA(cudaMemsetAsync(xd, 0, sizeof(float) * ld * (n + 1), c->stream));
+    rc = stage_x_from_host(c, x, rows, 0, rows, n, xd, ld, true);
+    if (!rc) {
+        if (y_is_labels && d->classify) {
+            // validate(): labels -> one-hot for the cost, raw labels for the error count (cublasNN.cpp:788-790, 859)
+            rc = cudaMalloc(&lab, sizeof(float) * rows) == cudaSuccess ? 0 : B2NN_ERR_ALLOC;
+            if (!rc) rc = cudaMemcpyAsync(lab, y, sizeof(float) * rows, cudaMemcpyHostToDevice, c->stream) == cudaSuccess ? 0 : B2NN_ERR_CUDA;
+            if (!rc) rc = labels_to_onehot_launch(lab, yd, ld, rows, K, c->stream) == cudaSuccess ? 0 : B2NN_ERR_CUDA;
+        } else {
+            rc = cudaMemcpy2DAsync(yd, sizeof(float) * ld, y, sizeof(float) * rows, sizeof(float) * rows, size_t(K),
+                                   cudaMemcpyHostToDevice, c->stream) == cudaSuccess ? 0 : B2NN_ERR_CUDA;
+        }
+    }
+    if (!rc) rc = evaluate_device(c, d, prec, xd, ld, yd, ld, lab, rows, nullptr, nullptr, 0, cost_out, errors_out);
+    cudaStreamSynchronize(c->stream);
+    c->plans.clear();      // plans reference xd
+    cudaFree(xd); cudaFree(yd); cudaFree(lab);
+    return rc;
+}
+
+int b2nn_predict(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, int64_t rows, float* out, float* probs) {
+    int rc = validate_desc(c, d);
+    if (rc) return rc;
+    if (!x || !out || rows < 1) { set_error("predict: bad arguments"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    const int prec = resolve_precision(d->precision);
+    const int n = c->layers[0], K = c->layers.back();
+    const int64_t ld = round_up(rows, 32);
+    float *xd = nullptr, *pd = nullptr, *hd = nullptr;
+    B2_CUDA(cudaMalloc(&xd, sizeof(float) * ld * (n + 1)));
+    B2_CUDA(cudaMalloc(&pd, sizeof(float) * ld));
+    B2_CUDA(cudaMalloc(&hd, sizeof(float) * ld * K));
+    B2_CUDA(cudaMemsetAsync(xd, 0, sizeof(float) * ld * (n + 1), c->stream));
+    rc = stage_x_from_host(c, x, rows, 0, rows, n, xd, ld, true);
+    if (!rc) rc = evaluate_device(c, d, prec, xd, ld, nullptr, 0, nullptr, rows, d->classify ? pd : nullptr, hd, ld, nullptr, nullptr);
+    if (!rc) {
+        cudaError_t e;
+        if (d->classify) e = cudaMemcpyAsync(out, pd, sizeof(float) * rows, cudaMemcpyDeviceToHost, c->stream);
+        else e = cudaMemcpy2DAsync(out, sizeof(float) * rows, hd, sizeof(float) * ld, sizeof(float) * rows, size_t(K),
+                                   cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && probs)
+            e = cudaMemcpy2DAsync(probs, sizeof(float) * rows, hd, sizeof(float) * ld, sizeof(float) * rows, size_t(K),
+                                  cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) { set_error(std::string("predict copy back: ") + cudaGetErrorString(e)); rc = B2NN_ERR_CUDA; }
+    }
+    cudaStreamSynchronize(c->stream);
+    c->plans.clear();
+    cudaFree(xd); cudaFree(pd); cudaFree(hd);
+    return rc;
+}
+
+int b2nn_predict_device(b2nn_ctx* c, const b2nn_train_desc* d, const float* x_dev, int64_t rows, int64_t ld, float* out_dev) {
+    int rc = validate_desc(c, d);
+    if (rc) return rc;
+    if (!x_dev || !out_dev || rows < 1 || ld < rows) { set_error("predict_device: bad arguments"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    const int prec = resolve_precision(d->precision);
+    // x_dev is already in ENGINE layout: (l_0+1) rows of ld floats, ones row last.
+    if (d->classify) return evaluate_device(c, d, prec, x_dev, ld, nullptr, 0, nullptr, rows, out_dev, nullptr, 0, nullptr, nullptr);
+    return evaluate_device(c, d, prec, x_dev, ld, nullptr, 0, nullptr, rows, nullptr, out_dev, ld, nullptr, nullptr);
+}
+
+int b2nn_gemm(b2nn_ctx* c, int backend, const float* A, int64_t lda, int a_major, const float* B, int64_t ldb, int b_major,
+              float* D, int64_t ldd, int M, int N, int K, int epi, const float* aux, int64_t ldaux) {
+    if (!c || !A || !B || !D) { set_error("gemm: null argument"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    GemmDesc g;
+    g.A = A; g.lda = lda; g.a_major = a_major; g.B = B; g.ldb = ldb; g.b_major = b_major;
+    g.D = D; g.ldd = ldd; g.M = M; g.N = N; g.K = K; g.epi = epi; g.aux = aux; g.ldaux = ldaux;
+    if (backend == 1) {
+        TcPlan plan;
+        std::string err;
+        if (!tc_plan_build(plan, g, err)) { set_error("tcgen05 plan: " + err); return B2NN_ERR_ARG; }
+        B2_CUDA(tc_plan_launch(plan, c->stream));
+        ++c->tc_launches;
+    } else {
+        B2_CUDA(gemm_simt_launch(g, c->stream));
+    }
+    ++c->launches;
+    return B2NN_OK;
+}
+
+int b2nn_momentum_update(b2nn_ctx* c, float* theta, float* vel, const float* grad, int64_t count, float mu, float alpha) {
+    if (!c || !theta || !vel || !grad) { set_error("momentum_update: null argument"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    B2_CUDA(momentum_update_launch(theta, vel, grad, count, mu, alpha, c->stream));
+    ++c->launches;
+    return B2NN_OK;
+}
+
+void* b2nn_stream(b2nn_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int b2nn_profile_enable(b2nn_ctx* c, int on) {
+    if (!c) { set_error("null ctx"); return B2NN_ERR_ARG; }
+    c->profile = on != 0;
+    return B2NN_OK;
+}
+
+int b2nn_profile_read(b2nn_ctx* c, double* ms, double* flops, double* bytes, int64_t* launches, int64_t* tc_launches) {
+    if (!c || !ms || !flops || !bytes || !launches || !tc_launches) { set_error("profile_read: null argument"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < B2NN_PROFILE_KINDS; ++k) { ms[k] = 0; flops[k] = 0; bytes[k] = 0; launches[k] = 0; tc_launches[k] = 0; }
+    for (auto& r : c->prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess && r.kind >= 0 && r.kind < B2NN_PROFILE_KINDS) {
+            ms[r.kind] += t; flops[r.kind] += r.flops; bytes[r.kind] += r.bytes; ++launches[r.kind];
+            if (r.tc) ++tc_launches[r.kind];
+        }
+        c->prof_pool.push_back(r.e0); c->prof_pool.push_back(r.e1);
+    }
+    (void)cudaGetLastError();
+    c->prof.clear();
+    return B2NN_OK;
+}
+
+int b2nn_comm_unique_id(void* id128) {
+    if (!id128) { set_error("null id"); return B2NN_ERR_ARG; }
+    std::call_once(g_nccl_once, load_nccl);
+    if (!g_nccl_err.empty()) { set_error(g_nccl_err); return B2NN_ERR_CUDA; }
+    int r = g_nccl.GetUniqueId(id128);
+    if (r != 0) { set_error("ncclGetUniqueId failed"); return B2NN_ERR_CUDA; }
+    return B2NN_OK;
+}
+
+int b2nn_comm_init(b2nn_ctx* c, int rank, int nranks, const void* id128) {
+    if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { set_error("comm_init: bad arguments"); return B2NN_ERR_ARG; }
+    if (nranks == 1) return B2NN_OK;
+    std::call_once(g_nccl_once, load_nccl);
+    if (!g_nccl_err.empty()) { set_error(g_nccl_err); return B2NN_ERR_CUDA; }
+    B2_CUDA(cudaSetDevice(c->device));
+    Id128 id;
+    std::memcpy(id.bytes, id128, 128);
+    void* comm = nullptr;
+    int r = g_nccl.CommInitRank(&comm, nranks, id, rank);
+    if (r != 0) { set_error(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?")); return B2NN_ERR_CUDA; }
+    c->comm = comm; c->rank = rank; c->nranks = nranks;
+    const size_t nw = c->L.size() ? c->L.size() : 16;
+    while (c->grad_ready.size() < nw) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->grad_ready.push_back(e); }
+    while (c->grad_reduced.size() < nw) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->grad_reduced.push_back(e); }
+    return B2NN_OK;
+}
+
+int b2nn_comm_barrier(b2nn_ctx* c) {
+    if (!c) { set_error("null ctx"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    if (c->comm) {
+        int rc = ensure_acc(c, 3);
+        if (rc) return rc;
+        int r = g_nccl.AllReduce(c->d_acc, c->d_acc, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+        if (r != 0) { set_error("ncclAllReduce(barrier) failed"); return B2NN_ERR_CUDA; }
+    }
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2NN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// engine.h — internal declarations shared by the CUDA translation units of libb2nn.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace b2 {
+
+// Epilogues fused into the contraction kernels.
+enum Epi : int {
+    EPI_STORE = 0,     // D = acc
+    EPI_SIGMOID = 1,   // D = 1/(1+exp(-acc))                 (forward, activations.cu:34-39 fused)
+    EPI_TANH = 2,      // D = tanh(acc)                       (forward, activations.cu:51-56 fused)
+    EPI_DSIGMOID = 3,  // D = acc * a(1-a), a = aux           (delta backprop, activations.cu:41-49 + kernels.cu:53-58 fused)
+    EPI_DTANH = 4      // D = acc * (1-a^2), a = aux          (delta backprop, activations.cu:58-66 + kernels.cu:53-58 fused)
+};
+
+// D(m,n) = sum_k A(m,k) * B(n,k);  D stored "m contiguous": D[n*ldd + m].
+// An operand is K-major when k is its contiguous index (X[mn*ld + k]) and MN-major otherwise (X[k*ld + mn]).
+// (mn0, k0) is the origin of the operand inside its allocation: TMA needs the 16-byte aligned allocation base and
+// addresses the sub-matrix by coordinates, the FFMA kernel just offsets the pointer.
+struct GemmDesc {
+    const float* A = nullptr; int64_t lda = 0; int a_major = 0; int64_t a_mn0 = 0, a_k0 = 0;
+    const float* B = nullptr; int64_t ldb = 0; int b_major = 0; int64_t b_mn0 = 0, b_k0 = 0;
+    float* D = nullptr; int64_t ldd = 0;
+    int M = 0, N = 0, K = 0;
+    int epi = EPI_STORE;
+    const float* aux = nullptr; int64_t ldaux = 0;
+    int split_k = 1;          // > 1: partial sums are added atomically into a pre-zeroed D (EPI_STORE only)
+    // Extent of A's allocation along each index when it is larger than origin + size (0 = origin + size).  Lets one
+    // tensor map over the whole training matrix serve every batch.
+    int64_t a_mn_end = 0, a_k_end = 0;
+};
+
+// fp32 FFMA backend (gemm_simt.cu)
+cudaError_t gemm_simt_launch(const GemmDesc& g, cudaStream_t stream);
+
+// tcgen05 / TMA backend (gemm_tc.cu).  The plan owns the two tensor maps; building it is host-only work.
+struct TcPlan {
+    alignas(64) CUtensorMap map_a;
+    alignas(64) CUtensorMap map_b;
+    GemmDesc g;
+    int block_n = 0;          // tile N: 16, 32, 64, 128 or 256
+    int stages = 0;
+    int k_blocks = 0;         // per split
+    int k_blocks_total = 0;
+    unsigned grid_x = 0, grid_y = 0, grid_z = 0;
+    size_t smem_bytes = 0;
+    bool valid = false;
+};
+// Returns false (and sets err) when the operands violate a TMA constraint (alignment, stride) so the caller can
+// route the contraction to the FFMA kernel instead.
+bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err);
+cudaError_t tc_plan_launch(const TcPlan& plan, cudaStream_t stream);
+bool tc_runtime_ok(std::string& err);   // driver entry point for cuTensorMapEncodeTiled available?
+
+// element-wise / bandwidth-bound kernels (elementwise.cu)
+struct OutputArgs {
+    const float* z; int64_t ldz;      // rows x K, unit-major: z[k*ldz + i]
+    const float* y; int64_t ldy;      // targets, same layout
+    float* h;       int64_t ldh;      // activated output (may be null)
+    float* delta;   int64_t ldd;      // h - y (may be null)
+    double* cost_sum;                 // += sum of per-element cost, double accumulator (may be null)
+    float* pred;                      // argmax class per row as float (may be null)
+    double* err_sum;                  // += #(argmax h != argmax y), double accumulator (may be null)
+    const float* y_labels;            // optional class ids per row (validate path) used for the error count
+    int64_t rows; int K; int out_kind; int cost_kind;
+};
+cudaError_t output_layer_launch(const OutputArgs& a, cudaStream_t stream);
+cudaError_t momentum_update_launch(float* theta, float* vel, const float* grad, int64_t count, float mu, float alpha,
+                                   cudaStream_t stream);
+// reference arena (Theta_j (in+1) x out col-major, bias row 0)  <->  internal (out rows of ldw floats, bias at col in)
+cudaError_t theta_ref_to_internal_launch(const float* ref, float* w, int in, int out, int64_t ldw, cudaStream_t s);
+cudaError_t theta_internal_to_ref_launch(const float* w, float* ref, int in, int out, int64_t ldw, cudaStream_t s);
+// reference X (m x (n+1) col-major, ones column first) -> internal ((n+1) rows of ld floats, ones row LAST)
+cudaError_t stage_x_launch(const float* x_ref, int64_t ld_ref, float* x_int, int64_t ld_int, int64_t rows, int n,
+                           cudaStream_t s);
+cudaError_t fill_launch(float* p, float v, int64_t count, cudaStream_t s);
+cudaError_t multiply_launch(const float* a, const float* b, float* out, int64_t count, cudaStream_t s);  // out may alias b
+cudaError_t init_scale_launch(float* theta, int in, int out, int64_t count, int kind, cudaStream_t s);
+cudaError_t labels_to_onehot_launch(const float* labels, float* y, int64_t ldy, int64_t rows, int K, cudaStream_t s);
+
+void set_error(const std::string& msg);
+
+}  // namespace b2
+
+#define B2_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            b2::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" +  \
+                          std::to_string(__LINE__) + ")");                                              \
+            return B2NN_ERR_CUDA;                                                                       \
+        }                                                                                               \
+    } while (0)

@@ -1,0 +1,317 @@
+// gemm_tc.cu — tcgen05 / TMEM / TMA contraction for sm_100a, TF32 inputs with FP32 accumulation.
+//
+//   D(m,n) = sum_k A(m,k) B(n,k),   D stored m-contiguous (D[n*ldd + m]).
+//
+// One kernel template covers the three contractions of the train step; they differ only in which operand index is
+// contiguous in memory (engine layout: every matrix is "unit-major", i.e. [unit][sample] or [out][in]):
+//   forward   z = a W^T    : A = a_{j-1}  MN-major ([k = unit][m = sample]),  B = W_j      K-major ([n = out][k = in])
+//   backprop  d = dn W     : A = delta    MN-major ([k = out ][m = sample]),  B = W_{j+1}  MN-major ([k = out][n = in])
+//   wgrad     G = d^T a    : A = a_{j-1}  K-major  ([m = in  ][k = sample]),  B = delta_j  K-major  ([n = out][k = sample])
+// replacing the three cublasSgemm op combinations of the reference (cublasNN.cpp:645-659 NN, :674-675 NT, :680-684 TN).
+//
+// CTA = 6 warps, one 128 x BN output tile, K streamed in blocks of 32 floats (= one 128-byte swizzle row):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d into a STAGES-deep shared-memory ring, mbarrier complete_tx
+//   warp 1      TMEM allocator + MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::tf32 (128 x BN x 8),
+//               tcgen05.commit releases ring slots and finally signals the epilogue
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers, fused activation / derivative, coalesced
+//               stores (lane = sample index, so each warp store is one 128-byte line)
+// Tails in every dimension are handled by TMA zero fill on the load side and predication on the store side.
+// Shared-memory tiles use the 128-byte swizzle; the UMMA shared-memory descriptors are built per K step:
+//   K-major  tile: rows of 128 B, 8-row groups 1024 B apart (SBO); K step of 8 floats = +32 B on the start address
+//   MN-major tile: 32-float x 32-k boxes of 4096 B; atoms along M/N are 4096 B apart (LBO), 8-k groups 1024 B (SBO);
+//                  K step of 8 = +1024 B on the start address
+#include "engine.h"
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace b2 {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // floats per K block = 128 bytes
+constexpr int UMMA_K = 8;              // tf32: 32 bytes per instruction
+constexpr int NUM_THREADS = 192;
+constexpr int A_TILE_BYTES = BM * BK * 4;
+constexpr int ATOM_BYTES = 32 * BK * 4;   // one MN-major box: 32 (mn) x 32 (k) floats
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+__host__ __device__ constexpr int b_tile_bytes(int bn, bool b_mn) {
+    return b_mn ? ((bn + 31) / 32) * ATOM_BYTES : bn * BK * 4;
+}
+
+struct TcArgs {
+    float* D; int64_t ldd;
+    const float* aux; int64_t ldaux;
+    int M, N;
+    int k_blocks;          // K blocks handled by one CTA (per split)
+    int k_blocks_total;
+    int a_mn0, a_k0, b_mn0, b_k0;
+    int epi;
+    int atomic;            // split-K: accumulate with red.global.add
+    int stages;
+    uint32_t mn_lbo, mn_sbo;   // MN-major descriptor strides in bytes (4096 / 1024; overridable for bring-up)
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcArgs p) {
+    constexpr int B_TILE = b_tile_bytes(BN, B_MN);
+    constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t IDESC = umma_idesc_tf32(BM, BN, A_MN, B_MN);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stages = p.stages;
+    uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + size_t(stages) * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + stages;
+    uint64_t* tmem_full = empty_bar + stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kb_begin = blockIdx.z * p.k_blocks;
+    int nkb = p.k_blocks_total - kb_begin;
+    if (nkb > p.k_blocks) nkb = p.k_blocks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % stages;
+                const uint32_t ph = (kb / stages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
+                uint8_t* sb = sa + A_TILE_BYTES;
+                const int kc = (kb_begin + kb) * BK;
+                if (A_MN) {
+#pragma unroll
+                    for (int i = 0; i < BM / 32; ++i)
+                        tma_load_2d(sa + i * ATOM_BYTES, &map_a, &full_bar[s], p.a_mn0 + m0 + i * 32, p.a_k0 + kc);
+                } else {
+                    tma_load_2d(sa, &map_a, &full_bar[s], p.a_k0 + kc, p.a_mn0 + m0);
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int i = 0; i < (BN + 31) / 32; ++i)
+                        tma_load_2d(sb + i * ATOM_BYTES, &map_b, &full_bar[s], p.b_mn0 + n0 + i * 32, p.b_k0 + kc);
+                } else {
+                    tma_load_2d(sb, &map_b, &full_bar[s], p.b_k0 + kc, p.b_mn0 + n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % stages;
+            const uint32_t ph = (kb / stages) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + size_t(s) * STAGE_BYTES);
+                const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                    const uint64_t da = A_MN ? umma_smem_desc(sa + kk * 1024, p.mn_lbo, p.mn_sbo)
+                                             : umma_smem_desc(sa + kk * UMMA_K * 4, 16, 1024);
+                    const uint64_t db = B_MN ? umma_smem_desc(sb + kk * 1024, p.mn_lbo, p.mn_sbo)
+                                             : umma_smem_desc(sb + kk * UMMA_K * 4, 16, 1024);
+                    umma_tf32(tmem_base, da, db, IDESC, (kb | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);                 // slot reusable once these MMAs have read it
+                if (kb == nkb - 1) umma_commit(tmem_full);  // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- epilogue ----------------
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int m = m0 + q * 32 + lane;
+        const bool m_ok = m < p.M;
+        const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+        constexpr int CH = BN < 32 ? 16 : 32;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += CH) {
+            if (n0 + c0 >= p.N) break;                // warp-uniform
+            uint32_t r[CH];
+            if constexpr (CH == 32) tmem_ld_32x32(lane_addr + c0, r); else tmem_ld_32x16(lane_addr + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int n = n0 + c0 + j;
+                if (n < p.N && m_ok) {
+                    float v = __uint_as_float(r[j]);
+                    if (p.epi != EPI_STORE) {
+                        const float a = (p.epi >= EPI_DSIGMOID) ? __ldg(p.aux + int64_t(n) * p.ldaux + m) : 0.f;
+                        v = apply_epilogue(p.epi, v, a);
+                    }
+                    float* dst = p.D + int64_t(n) * p.ldd + m;
+                    if (p.atomic) atomicAdd(dst, v); else *dst = v;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_encode_once;
+std::string g_encode_err;
+
+void load_encode() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+        g_encode_err = std::string("cuTensorMapEncodeTiled unavailable: ") + cudaGetErrorString(e);
+        (void)cudaGetLastError();
+        return;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+// Tensor map over the allocation that holds the operand.  The tensor extent ends where the sub-matrix ends, so
+// TMA's out-of-bounds zero fill supplies the K tail (wgrad: nothing past the batch is summed) and the M/N tails.
+bool encode_operand(CUtensorMap* map, const float* base, int64_t ld, bool mn_major, int64_t mn_end, int64_t k_end,
+                    int box_rows, std::string& err) {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) { err = "operand base not 16-byte aligned"; return false; }
+    if ((ld & 3) != 0) { err = "leading dimension not a multiple of 4 floats"; return false; }
+    const int64_t inner = mn_major ? mn_end : k_end;
+    const int64_t outer = mn_major ? k_end : mn_end;
+    if (inner <= 0 || outer <= 0 || inner > ld) { err = "operand extent inconsistent with leading dimension"; return false; }
+    if (inner >= (int64_t(1) << 32) || outer >= (int64_t(1) << 32)) { err = "operand extent exceeds TMA limits"; return false; }
+    cuuint64_t gdim[2] = {cuuint64_t(inner), cuuint64_t(outer)};
+    cuuint64_t gstride[1] = {cuuint64_t(ld) * 4};
+    cuuint32_t box[2] = {32u, cuuint32_t(mn_major ? 32 : box_rows)};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed, CUresult " + std::to_string(int(r)); return false; }
+    return true;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+cudaError_t launch_one(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid(pl.grid_x, pl.grid_y, pl.grid_z);
+    kern<<<grid, NUM_THREADS, pl.smem_bytes, stream>>>(pl.map_a, pl.map_b, a);
+    return cudaGetLastError();
+}
+
+template <int BN>
+cudaError_t launch_bn(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
+    const bool am = pl.g.a_major != 0, bm = pl.g.b_major != 0;
+    if (am && bm) return launch_one<BN, true, true>(pl, a, stream);
+    if (am && !bm) return launch_one<BN, true, false>(pl, a, stream);
+    if (!am && bm) return launch_one<BN, false, true>(pl, a, stream);
+    return launch_one<BN, false, false>(pl, a, stream);
+}
+
+}  // namespace
+
+bool tc_runtime_ok(std::string& err) {
+    std::call_once(g_encode_once, load_encode);
+    if (!g_encode) { err = g_encode_err; return false; }
+    return true;
+}
+
+bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
+    plan.valid = false;
+    if (!tc_runtime_ok(err)) return false;
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) { err = "empty contraction"; return false; }
+    if (g.a_mn0 + g.M >= (int64_t(1) << 31) || g.a_k0 + g.K >= (int64_t(1) << 31) ||
+        g.b_mn0 + g.N >= (int64_t(1) << 31) || g.b_k0 + g.K >= (int64_t(1) << 31)) { err = "coordinates exceed int32"; return false; }
+    if (g.epi >= EPI_DSIGMOID && !g.aux) { err = "derivative epilogue without aux"; return false; }
+
+    int bn;
+    if (g.N > 128) bn = 256; else if (g.N > 64) bn = 128; else if (g.N > 32) bn = 64; else if (g.N > 16) bn = 32; else bn = 16;
+    if (g.b_major && bn < 32) bn = 32;     // an MN-major box is 32 floats wide
+    plan.block_n = bn;
+    plan.g = g;
+
+    const int stage_bytes = A_TILE_BYTES + b_tile_bytes(bn, g.b_major != 0);
+    int stages = (SMEM_LIMIT - 1024 - 256) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) { err = "tile does not fit shared memory"; return false; }
+    plan.stages = stages;
+    plan.smem_bytes = size_t(stages) * stage_bytes + 1024 + 256;
+
+    plan.k_blocks_total = (g.K + BK - 1) / BK;
+    int splits = (g.split_k > 1 && g.epi == EPI_STORE) ? g.split_k : 1;
+    if (splits > plan.k_blocks_total) splits = plan.k_blocks_total;
+    plan.k_blocks = (plan.k_blocks_total + splits - 1) / splits;
+    splits = (plan.k_blocks_total + plan.k_blocks - 1) / plan.k_blocks;
+    plan.grid_x = unsigned((g.M + BM - 1) / BM);
+    plan.grid_y = unsigned((g.N + bn - 1) / bn);
+    plan.grid_z = unsigned(splits);
+    if (plan.grid_y > 65535u || plan.grid_z > 65535u) { err = "grid too large"; return false; }
+
+    const int64_t a_mn_end = g.a_mn_end > 0 ? g.a_mn_end : g.a_mn0 + g.M;
+    const int64_t a_k_end = g.a_k_end > 0 ? g.a_k_end : g.a_k0 + g.K;
+    if (!encode_operand(&plan.map_a, g.A, g.lda, g.a_major != 0, a_mn_end, a_k_end, BM, err)) return false;
+    if (!encode_operand(&plan.map_b, g.B, g.ldb, g.b_major != 0, g.b_mn0 + g.N, g.b_k0 + g.K, bn, err)) return false;
+    plan.valid = true;
+    return true;
+}
+
+cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream) {
+    if (!pl.valid) return cudaErrorInvalidValue;
+    TcArgs a;
+    a.D = pl.g.D; a.ldd = pl.g.ldd; a.aux = pl.g.aux; a.ldaux = pl.g.ldaux;
+    a.M = pl.g.M; a.N = pl.g.N;
+    a.k_blocks = pl.k_blocks; a.k_blocks_total = pl.k_blocks_total;
+    a.a_mn0 = int(pl.g.a_mn0); a.a_k0 = int(pl.g.a_k0); a.b_mn0 = int(pl.g.b_mn0); a.b_k0 = int(pl.g.b_k0);
+    a.epi = pl.g.epi; a.atomic = pl.grid_z > 1 ? 1 : 0; a.stages = pl.stages;
+    a.mn_lbo = ATOM_BYTES; a.mn_sbo = 1024;
+    if (const char* e = std::getenv("B2NN_TC_MN_LBO")) a.mn_lbo = uint32_t(std::atoi(e));   // bring-up knobs
+    if (const char* e = std::getenv("B2NN_TC_MN_SBO")) a.mn_sbo = uint32_t(std::atoi(e));
+    switch (pl.block_n) {
+        case 16:  return launch_bn<16>(pl, a, stream);
+        case 32:  return launch_bn<32>(pl, a, stream);
+        case 64:  return launch_bn<64>(pl, a, stream);
+        case 128: return launch_bn<128>(pl, a, stream);
+        case 256: return launch_bn<256>(pl, a, stream);
+        default:  return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace b2

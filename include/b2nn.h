@@ -1,0 +1,181 @@
+/* b2nn.h — C ABI of the B200-native MLP training engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of HenryJia/CUBLAS-ML: the mini-batch forward / delta-backprop /
+ * momentum-update loop of class cublasNN (reference cublasNN.cpp:526-685) plus the setup and evaluation calls that
+ * bracket it.  The reference has no FFI layer; its boundary is the C++ class in cublasNN.h.  The source-compatible
+ * façade in include/cublasNN.h is a thin C++ wrapper over exactly these entry points; any other host language binds
+ * them the same way (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, non-zero on failure; b2nn_last_error() explains.
+ *   - matrices crossing the ABI use the REFERENCE host layout: column-major, sample index fastest
+ *     (IDX2C(i,j,ld) = j*ld+i, cublasNN.h:17).  X carries the leading ones column written by addBias
+ *     (cublasNN.cpp:330-346).  Weights cross in the reference arena layout: Theta_j is (l_j+1) x l_{j+1} column-major,
+ *     row 0 = bias weights, layers concatenated (cublasNN.cpp:293-301).
+ *   - there is NO CPU fallback: every compute entry point fails with B2NN_ERR_NO_DEVICE when no sm_100 GPU is usable.
+ */
+#ifndef B2NN_H
+#define B2NN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2nn_ctx b2nn_ctx;
+
+enum {
+    B2NN_OK = 0,
+    B2NN_ERR_ARG = 1,        /* bad argument / call order (reference: undefined behaviour) */
+    B2NN_ERR_NO_DEVICE = 2,  /* no CUDA device, or not compute capability 10.x */
+    B2NN_ERR_CUDA = 3,       /* a CUDA / cuRAND / NCCL call failed */
+    B2NN_ERR_ALLOC = 4       /* reference prints "cudaMalloc Failed" (cublasNN.cpp:307-311) */
+};
+
+/* Hidden activation pair = (activationHidden, activationDerivative) of train*Momentum (cublasNN.h:45-50). */
+enum { B2NN_ACT_SIGMOID = 0 /* sigmoidGPU + sigmoidGradGPU, activations.cu:34-49 */,
+       B2NN_ACT_TANH = 1    /* tanhGPU + sechSqGPU,        activations.cu:51-66 */,
+       B2NN_ACT_CUSTOM = 2  /* user function pointers, generic unfused path       */ };
+/* Output activation (activationOutput, cublasNN.h:49). */
+enum { B2NN_OUT_SIGMOID = 0 /* sigmoidOutputGPU, activations.cu:9-12 */,
+       B2NN_OUT_SOFTMAX = 1 /* softmaxGPU, activations.cu:68-88      */,
+       B2NN_OUT_LINEAR = 2  /* trainFuncApproxMomentum: raw z (cublasNN.cpp:548) */,
+       B2NN_OUT_CUSTOM = 3 };
+/* Reported cost (costFunction, cublasNN.h:50).  Never influences gradients (cublasNN.cpp:666-667). */
+enum { B2NN_COST_NEGLNMAX = 0     /* negLnMaxCostGPU, costfunctions.cu:14-19     */,
+       B2NN_COST_CROSSENTROPY = 1 /* crossEntropyCostGPU, costfunctions.cu:21-26 */,
+       B2NN_COST_SQUARED = 2      /* cublasSdot(delta,delta)/(2 mB), cublasNN.cpp:552-554 */,
+       B2NN_COST_CUSTOM = 3 };
+/* Weight initialisers (randinitweights.cu:13-31). */
+enum { B2NN_INIT_1 = 1 /* eps = 1/sqrt(in)          */, B2NN_INIT_2 = 2 /* eps = sqrt(6)/sqrt(in+out) */,
+       B2NN_INIT_CUSTOM = 3 };
+/* Arithmetic of the three contractions (forward, delta backprop, weight gradient). */
+enum { B2NN_PREC_FP32 = 0 /* fp32 FFMA, matches cublasSgemm default math up to summation order          */,
+       B2NN_PREC_TF32 = 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM; small layers stay on fp32 FFMA   */,
+       B2NN_PREC_AUTO = 2 /* B2NN_PRECISION env var ("fp32" | "tf32"), default tf32                         */ };
+
+/* Function-pointer shapes of the reference's pluggable device ops (cublasNN.h:33, 45-50).  All pointers are DEVICE
+ * pointers; the functions are HOST functions that enqueue work on the legacy default stream. */
+typedef void (*b2nn_act_fn)(const float* in, float* out, int count);
+typedef void (*b2nn_out_fn)(const float* in, float* out, int rows, int cols);
+typedef void (*b2nn_cost_fn)(float* h, float* y, float* J, int count);
+typedef void (*b2nn_init_fn)(float* theta, int in, int out, int count);
+
+/* "Iteration: <iter>\tCost: <J>" events (cublasNN.cpp:555, 616); the façade prints them. */
+typedef void (*b2nn_log_cb)(void* user, int iter, float J);
+
+typedef struct b2nn_train_desc {
+    float momentum;            /* mu  (cublasNN.cpp:560, 621) */
+    float rate;                /* alpha = -rate / mB (cublasNN.cpp:544, 601); mB = GLOBAL batch rows when data-parallel */
+    int   iters;               /* epochs (setIters) */
+    int   display;             /* print period in epochs (setDisplay); <= 0 means 1 (reference: UB, cublasNN.h:118) */
+    int   batch_num;           /* NUMBER of batches, not batch size (cublasNN.cpp:401) */
+    int   classify;            /* 1: trainClassifyMomentum, 0: trainFuncApproxMomentum */
+    int   act_kind;            /* B2NN_ACT_*  */
+    int   out_kind;            /* B2NN_OUT_*  (ignored when classify == 0) */
+    int   cost_kind;           /* B2NN_COST_* (ignored when classify == 0) */
+    int   precision;           /* B2NN_PREC_* */
+    int   skip_final_cost;     /* 1: do not run calcFinalCost at the end (benchmarks time the loop only) */
+    int   reserved0;
+    b2nn_act_fn  act_fn;       /* used when act_kind  == B2NN_ACT_CUSTOM */
+    b2nn_act_fn  act_grad_fn;
+    b2nn_out_fn  out_fn;       /* used when out_kind  == B2NN_OUT_CUSTOM */
+    b2nn_cost_fn cost_fn;      /* used when cost_kind == B2NN_COST_CUSTOM */
+} b2nn_train_desc;
+
+typedef struct b2nn_train_result {
+    double call_seconds;       /* what train*Momentum returns: setup + loop + final cost (cublasNN.cpp:529-578) */
+    double loop_seconds;       /* CUDA-event time of the epoch loop only */
+    double final_cost;         /* "Final Cost" (cublasNN.cpp:745) */
+    double error_count;        /* "Total errors" (cublasNN.cpp:760), classification only */
+    int64_t steps;             /* iters * batch_num */
+    int64_t kernel_launches;   /* kernels of this library launched inside the loop */
+    int64_t gemm_tc_launches;  /* of those, tcgen05 GEMMs */
+} b2nn_train_result;
+
+/* ---- lifetime ---------------------------------------------------------------------------------------------- */
+/* replaces cublasNN::cublasNN / ~cublasNN (cublasNN.cpp:12-60).  device < 0 => current device. */
+int  b2nn_create(b2nn_ctx** out, int device);
+void b2nn_destroy(b2nn_ctx* ctx);
+const char* b2nn_last_error(void);
+/* 1 when a usable sm_100 device is present.  Never throws; no side effects beyond CUDA runtime init. */
+int  b2nn_device_ok(void);
+const char* b2nn_version(void);
+
+/* ---- network construction ---------------------------------------------------------------------------------- */
+/* replaces cublasNN::setLayers (cublasNN.cpp:270-328): one cuRAND XORWOW uniform call over the whole arena, then the
+ * per-layer rescale.  seed_is_clock != 0 reproduces the reference's clock() seed (cublasNN.cpp:27). */
+int b2nn_set_layers(b2nn_ctx* ctx, const int* layers, int n_layers, int init_kind, b2nn_init_fn custom_init,
+                    uint64_t seed, int seed_is_clock);
+int64_t b2nn_num_weights(const b2nn_ctx* ctx);
+/* Not in the reference (weights are private, cublasNN.h:135): needed for parity tests and checkpoints. */
+int b2nn_get_weights(b2nn_ctx* ctx, float* host_theta, int64_t count);
+int b2nn_set_weights(b2nn_ctx* ctx, const float* host_theta, int64_t count);
+
+/* ---- data --------------------------------------------------------------------------------------------------- */
+/* replaces cublasNN::copyDataGPU + splitData (cublasNN.cpp:348-358, 498-524).  x: m x n_plus_1 (ones column first),
+ * y: m x k, both column-major HOST buffers; the engine keeps its own device copy. */
+int b2nn_set_train_data(b2nn_ctx* ctx, const float* x, const float* y, int64_t m, int n_plus_1, int k);
+
+/* ---- the hot path ------------------------------------------------------------------------------------------- */
+/* replaces trainFuncApproxMomentum / trainClassifyMomentum (cublasNN.cpp:526-640). */
+int b2nn_train(b2nn_ctx* ctx, const b2nn_train_desc* desc, b2nn_log_cb log, void* log_user,
+               b2nn_train_result* result);
+
+/* One mini-batch step from HOST buffers (the end-to-end path: H2D of the batch, forward, backward, update, J back).
+ * x: rows x n_plus_1, y: rows x k column-major (ld = rows).  Velocity persists across calls until
+ * b2nn_reset_velocity.  global_rows: batch rows summed over all data-parallel ranks (0 => rows). */
+int b2nn_train_step_host(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x, const float* y, int64_t rows,
+                         int64_t global_rows, float* J_out);
+int b2nn_reset_velocity(b2nn_ctx* ctx);
+
+/* ---- evaluation / inference --------------------------------------------------------------------------------- */
+/* replaces calcFinalCost / validate (cublasNN.cpp:687-881) on caller data.  y_is_labels: y is rows x 1 class ids
+ * (validate, cublasNN.cpp:788-790) instead of rows x k one-hot. */
+int b2nn_evaluate(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x, const float* y, int64_t rows,
+                  int y_is_labels, double* cost_out, double* errors_out);
+/* replaces predict (cublasNN.cpp:906-977).  out: rows x 1 class ids when classify, rows x k column-major otherwise.
+ * probs (optional): rows x k column-major activations of the last layer. */
+int b2nn_predict(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x, int64_t rows, float* out, float* probs);
+/* Same forward with x ALREADY on the device (config 5's data-resident inference sweep). */
+int b2nn_predict_device(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x_dev, int64_t rows, int64_t ld,
+                        float* out_dev);
+
+/* ---- built-in recognition ----------------------------------------------------------------------------------- */
+/* Maps the address of a built-in op (tanhGPU, softmaxGPU, ...) to its B2NN_* enum, or -1 for user code.
+ * family: 0 hidden activation, 1 its derivative, 2 output activation, 3 cost, 4 init. */
+int b2nn_builtin_kind(const void* fn, int family);
+
+/* ---- data parallel (new; the reference is single-GPU) --------------------------------------------------------- */
+/* One process per GPU.  Rank 0 calls b2nn_comm_unique_id, the host plumbing (torch.distributed, MPI, ...) broadcasts
+ * the 128 bytes, every rank calls b2nn_comm_init.  Afterwards b2nn_train all-reduces the weight gradients with NCCL
+ * over NVLink, overlapped with the backprop of earlier layers; each rank's train data is its slice of every batch. */
+int b2nn_comm_unique_id(void* id128);
+int b2nn_comm_init(b2nn_ctx* ctx, int rank, int nranks, const void* id128);
+int b2nn_comm_barrier(b2nn_ctx* ctx);
+
+/* ---- introspection ------------------------------------------------------------------------------------------ */
+/* Raw GEMM entry used by the kernel unit tests and the roofline benchmark: D(m,n) = sum_k A(m,k) B(n,k), D stored
+ * at D[n*ldd + m].  a_major / b_major: 0 = K contiguous (A[m*lda+k]), 1 = M/N contiguous (A[k*lda+m]).
+ * epi: 0 store, 1 sigmoid, 2 tanh, 3 multiply by sigmoid'(aux), 4 multiply by tanh'(aux) with aux = activation values
+ * laid out like D.  All pointers are device pointers.  backend: 0 fp32 FFMA, 1 tcgen05 tf32. */
+int b2nn_gemm(b2nn_ctx* ctx, int backend, const float* A, int64_t lda, int a_major, const float* B, int64_t ldb,
+              int b_major, float* D, int64_t ldd, int M, int N, int K, int epi, const float* aux, int64_t ldaux);
+/* Momentum update kernel alone: v = mu*v + alpha*g ; theta = theta + v over count elements (device pointers). */
+int b2nn_momentum_update(b2nn_ctx* ctx, float* theta, float* vel, const float* grad, int64_t count, float mu,
+                         float alpha);
+void* b2nn_stream(b2nn_ctx* ctx);   /* cudaStream_t the engine launches on */
+/* Per-launch CUDA-event timing on the engine's stream (what bench.py's roofline leg reads).  Kinds: 0 forward
+ * contraction, 1 delta backprop, 2 weight gradient, 3 output layer, 4 momentum update.  Arrays have
+ * B2NN_PROFILE_KINDS entries; read() synchronises, sums the events recorded since the last read and clears them. */
+#define B2NN_PROFILE_KINDS 5
+int b2nn_profile_enable(b2nn_ctx* ctx, int on);
+int b2nn_profile_read(b2nn_ctx* ctx, double* ms, double* flops, double* bytes, int64_t* launches,
+                      int64_t* tc_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2NN_H */

@@ -1,0 +1,253 @@
+"""Parity tests proper: the CUDA engine, called through the C ABI, against
+  (1) the CPU oracle on the same seeded inputs,
+  (2) the UNMODIFIED reference (oracle/_ref, cuBLAS path) run live on the same GPU when its library travelled,
+  (3) the committed golden vectors of that reference,
+and, at BASELINE.json's full C3 size, against an fp64 restatement of one step (size-independent properties)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+# Stated tolerances (max-norm relative to max|theta|, relative on J):
+#   fp32 mode: contraction in fp32 FFMA — same arithmetic class as cublasSgemm default math; only summation order and
+#              the libm ulps of expf/tanhf/logf differ.
+#   tf32 mode: inputs of the large contractions rounded to 10 mantissa bits (tcgen05 kind::tf32), fp32 accumulate.
+TOL = {"fp32": dict(theta=2e-4, J=2e-4), "tf32": dict(theta=1e-2, J=1e-2)}
+
+
+def _desc(b2nn, c, prec, **over):
+    kw = dict(momentum=c.momentum, rate=c.rate, iters=c.iters, display=c.display, batch_num=c.batch_num,
+              classify=c.classify, act=b2nn.ACT_SIGMOID if c.hidden_act == cases.SIGMOID else b2nn.ACT_TANH,
+              out=(b2nn.OUT_SIGMOID if c.out_act == cases.OUT_SIGMOID else b2nn.OUT_SOFTMAX) if c.classify else b2nn.OUT_LINEAR,
+              cost=(b2nn.COST_NEGLNMAX if c.cost == cases.COST_NEGLNMAX else b2nn.COST_CROSSENTROPY) if c.classify else b2nn.COST_SQUARED,
+              precision=b2nn.PREC_FP32 if prec == "fp32" else b2nn.PREC_TF32)
+    kw.update(over)
+    return b2nn.make_desc(**kw)
+
+
+def _oracle(O, c, theta0, precision="f32", **over):
+    x_cm, y_cm = cases.oracle_inputs(c)
+    kw = dict(batch_num=c.batch_num, iters=c.iters, display=c.display, momentum=c.momentum, rate=c.rate,
+              hidden_act=c.hidden_act, classify=c.classify, out_act=c.out_act, cost=c.cost, precision=precision)
+    kw.update(over)
+    return O.train(c.layers, x_cm, y_cm, c.m, theta0=theta0, **kw)
+
+
+def _engine(b2nn, c, prec, theta0=None, **over):
+    net = b2nn.Net()
+    net.set_layers(c.layers, c.init_kind, c.seed)
+    th0 = net.get_weights()
+    if theta0 is not None:
+        net.set_weights(theta0)
+    x_cm, y_cm = cases.oracle_inputs(c)
+    net.set_train_data(x_cm, y_cm, c.m)
+    out = net.train(_desc(b2nn, c, prec, **over))
+    th = net.get_weights()
+    return net, th0, th, out
+
+
+ALL = [c.name for c in cases.small_cases()]
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_initial_weights_bit_identical_to_curand_host(b2nn, oracle, name):
+    """setLayers parity (cublasNN.cpp:314-326): same cuRAND XORWOW stream, same rescale arithmetic => same bits."""
+    c = cases.case_by_name(name)
+    net = b2nn.Net()
+    net.set_layers(c.layers, c.init_kind, c.seed)
+    assert np.array_equal(net.get_weights(), oracle.init_weights(c.layers, c.init_kind, c.seed))
+    net.close()
+
+
+def test_set_get_weights_roundtrip(b2nn):
+    net = b2nn.Net()
+    net.set_layers([7, 5, 9, 3], 1, 1)
+    th = np.arange(net.num_weights(), dtype=np.float32) * 0.25 - 3
+    net.set_weights(th)
+    assert np.array_equal(net.get_weights(), th)
+    net.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("name", ALL)
+def test_train_matches_oracle(b2nn, oracle, name, prec):
+    c = cases.case_by_name(name)
+    net, th0, th, out = _engine(b2nn, c, prec)
+    ref = _oracle(oracle, c, th0, "f32")
+    ref64 = _oracle(oracle, c, th0, "f64")
+    tol = TOL[prec]
+    scale = np.abs(ref64.theta).max()
+    err = np.abs(th - ref64.theta).max() / scale
+    err_oracle32 = np.abs(ref.theta - ref64.theta).max() / scale
+    assert err <= max(tol["theta"], 3 * err_oracle32), (name, prec, err, err_oracle32)
+    assert list(out.log_iter) == list(ref.log_iter)
+    np.testing.assert_allclose(out.log_J, ref64.log_J, rtol=tol["J"])
+    assert abs(out.final_cost - ref64.final_cost) <= tol["J"] * abs(ref64.final_cost) + 1e-7
+    if c.classify:
+        assert abs(out.error_count - ref64.error_count) <= max(1.0, 0.005 * c.m)
+    assert out.steps == c.iters * c.batch_num
+    if prec == "tf32" and name in ("wide_mini", "mnist_mini"):
+        assert out.gemm_tc_launches > 0, "tf32 mode must run the large contractions on the tcgen05 kernel"
+    if prec == "fp32":
+        assert out.gemm_tc_launches == 0
+    net.close()
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_train_matches_reference_live(b2nn, oracle, name):
+    """Same GPU, same seed, same data: reference cuBLAS build vs this engine in fp32 mode."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libcublasml_ref.so did not travel")
+    c = cases.case_by_name(name)
+    r = oracle.ref_train(c.layers, c.x, c.y, batch_num=c.batch_num, iters=c.iters, display=c.display,
+                         momentum=c.momentum, rate=c.rate, hidden_act=c.hidden_act, classify=c.classify,
+                         out_act=c.out_act, cost=c.cost, init_kind=c.init_kind, seed=c.seed)
+    net, th0, th, out = _engine(b2nn, c, "fp32")
+    assert np.array_equal(th0, r.theta0), "initial weights must be bit-identical to the reference's"
+    scale = np.abs(r.theta).max()
+    assert np.abs(th - r.theta).max() <= TOL["fp32"]["theta"] * scale
+    if c.compare_log:
+        assert list(out.log_iter) == list(r.log_iter)
+        np.testing.assert_allclose(out.log_J, r.log_J, rtol=5e-4)     # the reference prints 6 significant digits
+    assert abs(out.final_cost - r.final_cost) <= 5e-4 * abs(r.final_cost) + 1e-6
+    if c.classify:
+        assert abs(out.error_count - r.error_count) <= max(1.0, 0.002 * c.m)
+    net.close()
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_engine_matches_golden(b2nn, name):
+    path = cases.golden_path(name)
+    if not os.path.exists(path):
+        pytest.skip("golden vectors not committed yet")
+    g = np.load(path)
+    c = cases.case_by_name(name)
+    net, th0, th, out = _engine(b2nn, c, "fp32")
+    assert np.array_equal(th0, g["theta0"])
+    assert np.abs(th - g["theta"]).max() <= TOL["fp32"]["theta"] * np.abs(g["theta"]).max()
+    if c.compare_log:
+        np.testing.assert_allclose(out.log_J, g["log_J"], rtol=5e-4)
+    net.close()
+
+
+@pytest.mark.parametrize("name", ["clf_tanh_softmax", "reg_sigmoid_bikeshare512", "mnist_mini"])
+def test_predict_and_evaluate_match_oracle(b2nn, oracle, name):
+    c = cases.case_by_name(name)
+    net, th0, th, out = _engine(b2nn, c, "fp32")
+    x_cm, y_cm = cases.oracle_inputs(c)
+    d = _desc(b2nn, c, "fp32")
+    got, probs = net.predict(d, x_cm, c.m)
+    want, wprobs = oracle.predict(c.layers, th, x_cm, c.m, hidden_act=c.hidden_act, classify=c.classify,
+                                  out_act=c.out_act, precision="f64")
+    np.testing.assert_allclose(probs, wprobs, rtol=2e-4, atol=2e-5 * max(1.0, float(np.abs(wprobs).max())))
+    if c.classify:
+        assert (got != want).mean() <= 0.002
+        cost, errs = net.evaluate(d, x_cm, c.y[:, 0], c.m, y_is_labels=True)      # validate(): raw labels
+        cost2, errs2 = net.evaluate(d, x_cm, y_cm, c.m, y_is_labels=False)
+        assert abs(cost - out.final_cost) <= 1e-5 * abs(out.final_cost) + 1e-7 and errs == out.error_count
+        assert abs(cost2 - cost) <= 1e-6 * abs(cost) + 1e-9 and errs2 == errs
+    else:
+        np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-5 * max(1.0, float(np.abs(want).max())))
+        cost, _ = net.evaluate(d, x_cm, y_cm, c.m)
+        assert abs(cost - out.final_cost) <= 1e-5 * abs(out.final_cost)
+    net.close()
+
+
+def test_train_step_host_equals_resident_training(b2nn):
+    """The end-to-end entry (host buffers, H2D inside the call) must walk the same trajectory as b2nn_train."""
+    import ctypes
+    c = cases.case_by_name("clf_tanh_softmax")
+    x_cm, y_cm = cases.oracle_inputs(c)
+    net, th0, th, out = _engine(b2nn, c, "fp32", skip_final_cost=True)
+    net2 = b2nn.Net()
+    net2.set_layers(c.layers, c.init_kind, c.seed)
+    d = _desc(b2nn, c, "fp32")
+    n1, K = c.layers[0] + 1, c.layers[-1]
+    bs = c.m // c.batch_num
+    X = x_cm.reshape(n1, c.m)
+    Y = y_cm.reshape(K, c.m)
+    Js = []
+    for it in range(c.iters):
+        for b in range(c.batch_num):
+            lo, hi = b * bs, (c.m if b == c.batch_num - 1 else (b + 1) * bs)
+            xb = np.ascontiguousarray(X[:, lo:hi]).reshape(-1)
+            yb = np.ascontiguousarray(Y[:, lo:hi]).reshape(-1)
+            J = net2.train_step_host(d, ctypes.c_void_p(xb.ctypes.data), ctypes.c_void_p(yb.ctypes.data), hi - lo)
+            if (it + 1) % c.display == 0 and b == 0:
+                Js.append(J)
+    th2 = net2.get_weights()
+    assert np.abs(th2 - th).max() <= 1e-6 * np.abs(th).max()
+    np.testing.assert_allclose(Js, out.log_J, rtol=1e-5)
+    net.close(); net2.close()
+
+
+def _torch_step_fp64(layers, W, X, Y, rate, hidden):
+    """fp64 restatement of one classify step (softmax / cross-entropy, mu = 0) on the GPU: returns new weights.
+    W[j]: (l_j+1, l_{j+1}) reference layout (bias row 0); X: (B, l_0); Y: (B, K) one-hot."""
+    B = X.shape[0]
+    ones = torch.ones(B, 1, dtype=torch.float64, device=X.device)
+    acts = [torch.cat([ones, X], 1)]
+    for j in range(len(W) - 1):
+        z = acts[-1] @ W[j]
+        a = torch.tanh(z) if hidden == "tanh" else torch.sigmoid(z)
+        acts.append(torch.cat([ones, a], 1))
+    z = acts[-1] @ W[-1]
+    h = torch.softmax(z, 1)
+    J = -(Y * torch.log(h)).sum() / B
+    delta = h - Y
+    new = []
+    for j in range(len(W) - 1, -1, -1):
+        G = acts[j].t() @ delta
+        if j > 0:
+            a = acts[j][:, 1:]
+            d = (delta @ W[j].t())[:, 1:]
+            delta = d * ((1 - a * a) if hidden == "tanh" else a * (1 - a))
+        new.append(W[j] - (rate / B) * G)
+    return new[::-1], float(J)
+
+
+@pytest.mark.parametrize("prec", ["tf32"])
+def test_c3_full_size_one_step_against_fp64(b2nn, oracle, prec):
+    """BASELINE.json config C3 at full size (784-4096-4096-10, batch 8192): one momentum-free step on the engine vs an
+    fp64 restatement of the same step; also the printed cost.  The CPU oracle is too slow at this size, so the
+    check is the step's defining property: theta_1 = theta_0 - rate/B * dJ/dtheta."""
+    layers, B, K = [784, 4096, 4096, 10], 8192, 10
+    rng = np.random.Generator(np.random.PCG64(1))
+    X = rng.standard_normal((B, 784)).astype(np.float32)
+    teacher = rng.standard_normal((784, K)).astype(np.float32)
+    lab = (X @ teacher).argmax(1)
+    net = b2nn.Net()
+    net.set_layers(layers, b2nn.INIT_2, 42)
+    th0 = net.get_weights()
+    x_cm = oracle.with_bias_colmajor(X)
+    y_cm = oracle.one_hot_colmajor(lab, K)
+    net.set_train_data(x_cm, y_cm, B)
+    rate = 0.5
+    d = b2nn.make_desc(momentum=0.0, rate=rate, iters=1, display=1, batch_num=1, classify=True, act=b2nn.ACT_TANH,
+                       out=b2nn.OUT_SOFTMAX, cost=b2nn.COST_CROSSENTROPY,
+                       precision=b2nn.PREC_TF32 if prec == "tf32" else b2nn.PREC_FP32, skip_final_cost=True)
+    out = net.train(d)
+    th1 = net.get_weights()
+    assert out.gemm_tc_launches >= 7
+    W = []
+    for pos, r, cdim in oracle.theta_offsets(layers):
+        W.append(torch.tensor(th0[pos:pos + r * cdim].reshape(cdim, r).T.copy(), dtype=torch.float64, device="cuda"))
+    Wn, J = _torch_step_fp64(layers, W, torch.tensor(X, dtype=torch.float64, device="cuda"),
+                             torch.tensor(np.eye(K)[lab], dtype=torch.float64, device="cuda"), rate, "tanh")
+    assert abs(out.log_J[0] - J) <= 2e-3 * abs(J)
+    for (pos, r, cdim), w0, wn in zip(oracle.theta_offsets(layers), W, Wn):
+        got = torch.tensor(th1[pos:pos + r * cdim].reshape(cdim, r).T.copy(), dtype=torch.float64, device="cuda")
+        step_ref = wn - w0
+        step_got = got - w0
+        denom = float(step_ref.abs().max())
+        assert denom > 0
+        # the UPDATE (not just theta) must match: relative to the largest update entry of the layer
+        assert float((step_got - step_ref).abs().max()) <= 2e-2 * denom, (pos, denom)
+        # and theta itself to fp32 resolution of the update
+        assert float((got - wn).abs().max()) <= 2e-2 * denom + 1e-7
+    net.close()
