@@ -136,6 +136,17 @@ __global__ void multiply_kernel(const float* a, const float* b, float* out, int6
     if (i < n) out[i] = a[i] * b[i];
 }
 
+__global__ void split_batches_kernel(const float* __restrict__ src, int64_t ld_src, float* __restrict__ dst, int64_t ld_dst,
+                                     int64_t rows, int64_t bs, int64_t bs_pad, int nb) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    int64_t b = i / bs;
+    if (b > nb - 1) b = nb - 1;
+    const int64_t r = i - b * bs;
+    const int64_t f = blockIdx.y;
+    dst[f * ld_dst + b * bs_pad + r] = src[f * ld_src + i];
+}
+
 __global__ void fill_kernel(float* p, float v, int64_t count) {
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) p[i] = v;
@@ -206,6 +217,13 @@ cudaError_t stage_x_launch(const float* x_ref, int64_t ld_ref, float* x_int, int
     if (rows <= 0) return cudaSuccess;
     dim3 grid(blocks_for(rows, 256), unsigned(n + 1));
     stage_x_kernel<<<grid, 256, 0, s>>>(x_ref, ld_ref, x_int, ld_int, rows, n);
+    return cudaGetLastError();
+}
+cudaError_t split_batches_launch(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t rows, int64_t bs,
+                                 int64_t bs_pad, int nb, int n_rows, cudaStream_t s) {
+    if (rows <= 0 || n_rows <= 0) return cudaSuccess;
+    dim3 grid(blocks_for(rows, 256), unsigned(n_rows));
+    split_batches_kernel<<<grid, 256, 0, s>>>(src, ld_src, dst, ld_dst, rows, bs, bs_pad, nb);
     return cudaGetLastError();
 }
 cudaError_t fill_launch(float* p, float v, int64_t count, cudaStream_t s) {

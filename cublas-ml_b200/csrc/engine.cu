@@ -133,6 +133,10 @@ struct b2nn_ctx {
     float* Y = nullptr; int64_t ldy = 0;
     int64_t m = 0; int n = 0, K = 0;
 
+    // batch-aligned copy of the training set (splitData, cublasNN.cpp:498-524): every batch starts on a 32-sample
+    // boundary so MN-major TMA boxes can address it as whole 32-float atoms.  Built per train call when needed.
+    float* Xsp = nullptr; float* Ysp = nullptr; int64_t ldsp = 0; int sp_nb = 0; int64_t sp_stride = 0;
+
     // host-step staging (b2nn_train_step_host)
     float* Xs = nullptr; float* Ys = nullptr; int64_t lds = 0, caps = 0;
 
@@ -141,6 +145,7 @@ struct b2nn_ctx {
     int plans_prec = -1;
     const float* plans_x = nullptr;
     int64_t plans_ldx = 0, plans_xtotal = 0;
+    bool plans_xaligned = false;
     int plans_act = -1;
 
     double* d_acc = nullptr;             // device accumulators: [0] cost, [1] errors, [2..] display slots
@@ -259,7 +264,9 @@ void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
             if (s > 1) { g.split_k = s; op.zero_first = true; }
         }
     }
-    if (prec == B2NN_PREC_TF32 && work >= double(1 << 20) && g.M >= 32) {
+    // tcgen05 only where tensor cores pay: below ~2^26 multiply-adds a contraction is launch / HBM bound and stays on
+    // the exact fp32 FFMA kernel (the bikeshare-sized nets of config C2 never leave fp32).
+    if (prec == B2NN_PREC_TF32 && work >= double(1 << 26) && g.M >= 32) {
         std::string err;
         if (tc_plan_build(op.plan, g, err)) op.tc = true;
     }
@@ -275,11 +282,14 @@ void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
 
 // x_total: number of sample columns of X that hold data.  The tensor maps over X span all of them so one plan serves
 // every batch of the same size; the batch start only moves the TMA coordinates (run_gemm).
-StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64_t x_total, int prec, int act_kind) {
+// x_aligned: every batch start passed to run_gemm is a multiple of 32 samples (one 3-D TMA box per X tile).
+StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64_t x_total, bool x_aligned, int prec,
+                   int act_kind) {
     if (c->plans_prec != prec || c->plans_x != X || c->plans_ldx != ldx || c->plans_act != act_kind ||
-        c->plans_xtotal != x_total) {
+        c->plans_xtotal != x_total || c->plans_xaligned != x_aligned) {
         c->plans.clear();
         c->plans_prec = prec; c->plans_x = X; c->plans_ldx = ldx; c->plans_act = act_kind; c->plans_xtotal = x_total;
+        c->plans_xaligned = x_aligned;
     }
     auto it = c->plans.find(rows);
     if (it != c->plans.end()) return it->second;
@@ -295,7 +305,8 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         // forward  z_j = [a_{j-1}, 1] W_j^T     (cublasNN.cpp:645-646, 653-654, 658-659)
         GemmOp& f = sp.fwd[j];
         f.g = GemmDesc();
-        if (j == 0) { f.g.A = X; f.g.lda = ldx; f.a_is_x = true; f.g.a_mn_end = x_total; } else { f.g.A = w.a[j - 1]; f.g.lda = w.ld; }
+        if (j == 0) { f.g.A = X; f.g.lda = ldx; f.a_is_x = true; f.g.a_mn_end = x_total; f.g.mn_slack = x_aligned; }
+        else { f.g.A = w.a[j - 1]; f.g.lda = w.ld; f.g.mn_slack = true; }       // workspace rows are padded to 32 samples
         f.g.a_major = 1;
         f.g.B = c->W + li.w_off; f.g.ldb = li.ldw; f.g.b_major = 0;
         f.g.M = int(rows); f.g.N = li.out; f.g.K = li.in + 1;
@@ -324,6 +335,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
             GemmOp& b = sp.bwd[j];
             b.g = GemmDesc();
             b.g.A = w.delta[j]; b.g.lda = w.ld; b.g.a_major = 1;
+            b.g.mn_slack = true;      // delta rows are padded to 32 samples; the weight arena carries 64 floats of slack
             b.g.B = c->W + li.w_off; b.g.ldb = li.ldw; b.g.b_major = 1;
             b.g.M = int(rows); b.g.N = li.in; b.g.K = li.out;
             if (custom) { b.g.D = w.scratch; b.g.ldd = w.ld; b.g.epi = EPI_STORE; }
@@ -443,9 +455,9 @@ int output_and_delta(b2nn_ctx* c, const b2nn_train_desc* d, const float* Y, int6
 }
 
 // One mini-batch step on device-resident data: forward, output, backward, momentum update.
-int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, int64_t ldx, int64_t x_total, const float* Y,
-               int64_t ldy, int64_t x_start, int64_t rows, int64_t global_rows, double* cost_slot) {
-    StepPlan& sp = get_plan(c, rows, X, ldx, x_total, prec, d->act_kind);
+int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, int64_t ldx, int64_t x_total, bool x_aligned,
+               const float* Y, int64_t ldy, int64_t x_start, int64_t rows, int64_t global_rows, double* cost_slot) {
+    StepPlan& sp = get_plan(c, rows, X, ldx, x_total, x_aligned, prec, d->act_kind);
     int rc = forward_pass(c, sp, x_start, d);
     if (rc) return rc;
     rc = output_and_delta(c, d, Y + x_start, ldy, rows, cost_slot);
@@ -497,15 +509,17 @@ int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float
     const int64_t chunk_cap = std::max<int64_t>(c->ws.cap, std::min<int64_t>(rows, 1 << 16));
     rc = ensure_workspace(c, chunk_cap, d->act_kind == B2NN_ACT_CUSTOM);
     if (rc) return rc;
+    // chunk starts stay on 32-sample boundaries so the forward contractions keep their one-box TMA loads
+    const int64_t chunk = rows <= c->ws.cap ? c->ws.cap : std::max<int64_t>(32, c->ws.cap / 32 * 32);
     const int out_kind = d->classify ? d->out_kind : B2NN_OUT_LINEAR;
     const int cost_kind = d->classify ? d->cost_kind : B2NN_COST_SQUARED;
     if (out_kind == B2NN_OUT_CUSTOM || cost_kind == B2NN_COST_CUSTOM) {
         set_error("custom output activation / cost function pointers are not supported by the fused output kernel yet");
         return B2NN_ERR_ARG;
     }
-    for (int64_t s = 0; s < rows; s += c->ws.cap) {
-        const int64_t r = std::min<int64_t>(c->ws.cap, rows - s);
-        StepPlan& sp = get_plan(c, r, X, ldx, rows, prec, d->act_kind);
+    for (int64_t s = 0; s < rows; s += chunk) {
+        const int64_t r = std::min<int64_t>(chunk, rows - s);
+        StepPlan& sp = get_plan(c, r, X, ldx, rows, true, prec, d->act_kind);
         rc = forward_pass(c, sp, s, d);
         if (rc) return rc;
         OutputArgs a{};
@@ -587,7 +601,7 @@ void b2nn_destroy(b2nn_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     c->ws.release();
     cudaFree(c->W); cudaFree(c->V); cudaFree(c->G);
-    cudaFree(c->X); cudaFree(c->Y); cudaFree(c->Xs); cudaFree(c->Ys);
+    cudaFree(c->X); cudaFree(c->Y); cudaFree(c->Xs); cudaFree(c->Ys); cudaFree(c->Xsp); cudaFree(c->Ysp);
     cudaFree(c->d_acc);
     if (c->h_acc) cudaFreeHost(c->h_acc);
     for (auto e : c->log_events) cudaEventDestroy(e);
@@ -625,14 +639,15 @@ int b2nn_set_layers(b2nn_ctx* c, const int* layers, int n_layers, int init_kind,
     cudaFree(c->W); cudaFree(c->V); cudaFree(c->G);
     c->W = c->V = c->G = nullptr;
     c->plans.clear(); c->ws.release();
-    if (cudaMalloc(&c->W, sizeof(float) * c->total_int) != cudaSuccess ||
+    // + 64 floats: the folded 3-D TMA view of the last weight rows may read one 32-float atom past the arena's end
+    if (cudaMalloc(&c->W, sizeof(float) * (c->total_int + 64)) != cudaSuccess ||
         cudaMalloc(&c->V, sizeof(float) * c->total_int) != cudaSuccess ||
         cudaMalloc(&c->G, sizeof(float) * c->total_int) != cudaSuccess) {
         (void)cudaGetLastError();
         set_error("cudaMalloc Failed");     // reference text, cublasNN.cpp:309
         return B2NN_ERR_ALLOC;
     }
-    B2_CUDA(cudaMemsetAsync(c->W, 0, sizeof(float) * c->total_int, c->stream));
+    B2_CUDA(cudaMemsetAsync(c->W, 0, sizeof(float) * (c->total_int + 64), c->stream));
     B2_CUDA(cudaMemsetAsync(c->V, 0, sizeof(float) * c->total_int, c->stream));
     B2_CUDA(cudaMemsetAsync(c->G, 0, sizeof(float) * c->total_int, c->stream));
 
@@ -698,6 +713,7 @@ int b2nn_set_train_data(b2nn_ctx* c, const float* x, const float* y, int64_t m, 
     if (n_plus_1 != c->layers[0] + 1 || k != c->layers.back()) { set_error("data shape does not match the layers"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
     cudaFree(c->X); cudaFree(c->Y); c->X = c->Y = nullptr;
+    cudaFree(c->Xsp); cudaFree(c->Ysp); c->Xsp = c->Ysp = nullptr; c->sp_nb = 0;
     c->plans.clear();
     c->m = m; c->n = n_plus_1 - 1; c->K = k;
     c->ldx = round_up(m, 32); c->ldy = c->ldx;
@@ -764,6 +780,27 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
         while (c->grad_ready.size() < c->L.size()) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->grad_ready.push_back(e); }
         while (c->grad_reduced.size() < c->L.size()) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->grad_reduced.push_back(e); }
     }
+    // splitData (cublasNN.cpp:498-524): the reference re-lays every batch as a contiguous block.  Here batches are already
+    // contiguous column ranges of X; a copy is only made when the batch starts would not fall on 32-sample boundaries.
+    const float* Xtrain = c->X; const float* Ytrain = c->Y;
+    int64_t ld_train = c->ldx, x_total = c->m, b_stride = bs;
+    bool x_aligned = (nb == 1) || (bs % 32 == 0);
+    if (!x_aligned && bs >= 64 && prec == B2NN_PREC_TF32) {
+        const int64_t bs_pad = round_up(bs, 32);
+        const int64_t ldsp = int64_t(nb - 1) * bs_pad + round_up(last_rows, 32);
+        if (!c->Xsp || c->sp_nb != nb || c->ldsp != ldsp) {
+            cudaFree(c->Xsp); cudaFree(c->Ysp); c->Xsp = c->Ysp = nullptr;
+            B2_CUDA(cudaMalloc(&c->Xsp, sizeof(float) * ldsp * (c->n + 1)));
+            B2_CUDA(cudaMalloc(&c->Ysp, sizeof(float) * ldsp * c->K));
+            c->ldsp = ldsp; c->sp_nb = nb; c->sp_stride = bs_pad;
+        }
+        B2_CUDA(cudaMemsetAsync(c->Xsp, 0, sizeof(float) * ldsp * (c->n + 1), c->stream));
+        B2_CUDA(cudaMemsetAsync(c->Ysp, 0, sizeof(float) * ldsp * c->K, c->stream));
+        B2_CUDA(split_batches_launch(c->X, c->ldx, c->Xsp, ldsp, c->m, bs, bs_pad, nb, c->n + 1, c->stream));
+        B2_CUDA(split_batches_launch(c->Y, c->ldy, c->Ysp, ldsp, c->m, bs, bs_pad, nb, c->K, c->stream));
+        Xtrain = c->Xsp; Ytrain = c->Ysp; ld_train = ldsp; x_total = ldsp; b_stride = bs_pad; x_aligned = true;
+    }
+
     const int64_t launches0 = c->launches, tc0 = c->tc_launches;
     cudaEvent_t ev0, ev1;
     B2_CUDA(cudaEventCreate(&ev0)); B2_CUDA(cudaEventCreate(&ev1));
@@ -791,7 +828,8 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
             const int64_t rows = (b == nb - 1) ? last_rows : bs;
             const bool show = ((it + 1) % display == 0) && b == 0 && issued < n_disp;   // :550, :610
             double* slot = show ? c->d_acc + 2 + issued : nullptr;
-            rc = train_step(c, d, prec, c->X, c->ldx, c->m, c->Y, c->ldy, int64_t(b) * bs, rows, global_rows[b], slot);
+            rc = train_step(c, d, prec, Xtrain, ld_train, x_total, x_aligned, Ytrain, ld_train, int64_t(b) * b_stride, rows,
+                            global_rows[b], slot);
             if (rc) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
             if (show) {
                 if (issued - reported >= int(c->log_events.size())) { rc = flush_logs(true); if (rc) return rc; }
@@ -880,7 +918,7 @@ int b2nn_train_step_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, 
     double* slot = J_out ? c->d_acc + 2 : nullptr;
     if (slot) B2_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), c->stream));
     const int64_t g = global_rows > 0 ? global_rows : rows;
-    rc = train_step(c, d, prec, c->Xs, c->lds, rows, c->Ys, c->lds, 0, rows, g, slot);
+    rc = train_step(c, d, prec, c->Xs, c->lds, rows, true, c->Ys, c->lds, 0, rows, g, slot);
     if (rc) return rc;
     if (slot) {
         if (c->comm) {
@@ -976,7 +1014,8 @@ int b2nn_gemm(b2nn_ctx* c, int backend, const float* A, int64_t lda, int a_major
     GemmDesc g;
     g.A = A; g.lda = lda; g.a_major = a_major; g.B = B; g.ldb = ldb; g.b_major = b_major;
     g.D = D; g.ldd = ldd; g.M = M; g.N = N; g.K = K; g.epi = epi; g.aux = aux; g.ldaux = ldaux;
-    if (backend == 1) {
+    if (backend == 1 || backend == 3) {
+        g.mn_slack = backend == 3;
         TcPlan plan;
         std::string err;
         if (!tc_plan_build(plan, g, err)) { set_error("tcgen05 plan: " + err); return B2NN_ERR_ARG; }

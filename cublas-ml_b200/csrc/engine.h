@@ -32,6 +32,9 @@ struct GemmDesc {
     // Extent of A's allocation along each index when it is larger than origin + size (0 = origin + size).  Lets one
     // tensor map over the whole training matrix serve every batch.
     int64_t a_mn_end = 0, a_k_end = 0;
+    // The caller guarantees that reading up to 31 floats past the M/N extent of an MN-major operand (in every k row,
+    // including the last) stays inside its allocation, which the one-box-per-tile 3-D TMA view relies on.
+    bool mn_slack = false;
 };
 
 // fp32 FFMA backend (gemm_simt.cu)
@@ -48,6 +51,7 @@ struct TcPlan {
     int k_blocks_total = 0;
     unsigned grid_x = 0, grid_y = 0, grid_z = 0;
     size_t smem_bytes = 0;
+    bool a_3d = false, b_3d = false;
     bool valid = false;
 };
 // Returns false (and sets err) when the operands violate a TMA constraint (alignment, stride) so the caller can
@@ -78,6 +82,9 @@ cudaError_t theta_internal_to_ref_launch(const float* w, float* ref, int in, int
 cudaError_t stage_x_launch(const float* x_ref, int64_t ld_ref, float* x_int, int64_t ld_int, int64_t rows, int n,
                            cudaStream_t s);
 cudaError_t fill_launch(float* p, float v, int64_t count, cudaStream_t s);
+// dst[f][b*bs_pad + r] = src[f][b*bs + r] for the nb contiguous batches of allocVarGPU's table (last absorbs the rest)
+cudaError_t split_batches_launch(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t rows, int64_t bs,
+                                 int64_t bs_pad, int nb, int n_rows, cudaStream_t s);
 cudaError_t multiply_launch(const float* a, const float* b, float* out, int64_t count, cudaStream_t s);  // out may alias b
 cudaError_t init_scale_launch(float* theta, int in, int out, int64_t count, int kind, cudaStream_t s);
 cudaError_t labels_to_onehot_launch(const float* labels, float* y, int64_t ldy, int64_t rows, int K, cudaStream_t s);

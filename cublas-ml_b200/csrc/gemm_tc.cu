@@ -18,8 +18,9 @@
 // Tails in every dimension are handled by TMA zero fill on the load side and predication on the store side.
 // Shared-memory tiles use the 128-byte swizzle; the UMMA shared-memory descriptors are built per K step:
 //   K-major  tile: rows of 128 B, 8-row groups 1024 B apart (SBO); K step of 8 floats = +32 B on the start address
-//   MN-major tile: 32-float x 32-k boxes of 4096 B; atoms along M/N are 4096 B apart (LBO), 8-k groups 1024 B (SBO);
-//                  K step of 8 = +1024 B on the start address
+//   MN-major tile: 32-float x 32-k boxes of 4096 B written with the 32-byte-chunk 128 B swizzle (the only one
+//                  tcgen05 accepts for MN-major 4-byte operands); atoms along M/N are 4096 B apart (LBO), 4-k groups
+//                  512 B apart (SBO); K step of 8 = +1024 B on the start address
 #include "engine.h"
 #include "epilogue.cuh"
 #include "ptx.cuh"
@@ -53,7 +54,8 @@ struct TcArgs {
     int epi;
     int atomic;            // split-K: accumulate with red.global.add
     int stages;
-    uint32_t mn_lbo, mn_sbo;   // MN-major descriptor strides in bytes (4096 / 1024; overridable for bring-up)
+    uint32_t mn_lbo, mn_sbo, mn_layout;   // MN-major descriptor: 4096 / 512 / type 1 (overridable for bring-up)
+    int a_3d, b_3d;        // MN-major operand fetched with one 3-D TMA box per tile (origin is a multiple of 32)
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -106,16 +108,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 uint8_t* sb = sa + A_TILE_BYTES;
                 const int kc = (kb_begin + kb) * BK;
                 if (A_MN) {
+                    if (p.a_3d) {
+                        tma_load_3d(sa, &map_a, &full_bar[s], 0, p.a_k0 + kc, (p.a_mn0 + m0) >> 5);
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < BM / 32; ++i)
-                        tma_load_2d(sa + i * ATOM_BYTES, &map_a, &full_bar[s], p.a_mn0 + m0 + i * 32, p.a_k0 + kc);
+                        for (int i = 0; i < BM / 32; ++i)
+                            tma_load_2d(sa + i * ATOM_BYTES, &map_a, &full_bar[s], p.a_mn0 + m0 + i * 32, p.a_k0 + kc);
+                    }
                 } else {
                     tma_load_2d(sa, &map_a, &full_bar[s], p.a_k0 + kc, p.a_mn0 + m0);
                 }
                 if (B_MN) {
+                    if (p.b_3d) {
+                        tma_load_3d(sb, &map_b, &full_bar[s], 0, p.b_k0 + kc, (p.b_mn0 + n0) >> 5);
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < (BN + 31) / 32; ++i)
-                        tma_load_2d(sb + i * ATOM_BYTES, &map_b, &full_bar[s], p.b_mn0 + n0 + i * 32, p.b_k0 + kc);
+                        for (int i = 0; i < (BN + 31) / 32; ++i)
+                            tma_load_2d(sb + i * ATOM_BYTES, &map_b, &full_bar[s], p.b_mn0 + n0 + i * 32, p.b_k0 + kc);
+                    }
                 } else {
                     tma_load_2d(sb, &map_b, &full_bar[s], p.b_k0 + kc, p.b_mn0 + n0);
                 }
@@ -133,9 +143,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t sb = sa + A_TILE_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                    const uint64_t da = A_MN ? umma_smem_desc(sa + kk * 1024, p.mn_lbo, p.mn_sbo)
+                    const uint64_t da = A_MN ? umma_smem_desc(sa + kk * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout)
                                              : umma_smem_desc(sa + kk * UMMA_K * 4, 16, 1024);
-                    const uint64_t db = B_MN ? umma_smem_desc(sb + kk * 1024, p.mn_lbo, p.mn_sbo)
+                    const uint64_t db = B_MN ? umma_smem_desc(sb + kk * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout)
                                              : umma_smem_desc(sb + kk * UMMA_K * 4, 16, 1024);
                     umma_tf32(tmem_base, da, db, IDESC, (kb | kk) != 0 ? 1u : 0u);
                 }
@@ -205,20 +215,36 @@ void load_encode() {
 // Tensor map over the allocation that holds the operand.  The tensor extent ends where the sub-matrix ends, so
 // TMA's out-of-bounds zero fill supplies the K tail (wgrad: nothing past the batch is summed) and the M/N tails.
 bool encode_operand(CUtensorMap* map, const float* base, int64_t ld, bool mn_major, int64_t mn_end, int64_t k_end,
-                    int box_rows, std::string& err) {
+                    int box_rows, bool as_3d, std::string& err) {
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) { err = "operand base not 16-byte aligned"; return false; }
     if ((ld & 3) != 0) { err = "leading dimension not a multiple of 4 floats"; return false; }
     const int64_t inner = mn_major ? mn_end : k_end;
     const int64_t outer = mn_major ? k_end : mn_end;
     if (inner <= 0 || outer <= 0 || inner > ld) { err = "operand extent inconsistent with leading dimension"; return false; }
     if (inner >= (int64_t(1) << 32) || outer >= (int64_t(1) << 32)) { err = "operand extent exceeds TMA limits"; return false; }
-    cuuint64_t gdim[2] = {cuuint64_t(inner), cuuint64_t(outer)};
-    cuuint64_t gstride[1] = {cuuint64_t(ld) * 4};
-    cuuint32_t box[2] = {32u, cuuint32_t(mn_major ? 32 : box_rows)};
-    cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // MN-major fp32 tiles must use the 32-byte-chunk flavour of the 128-byte swizzle (see umma_smem_desc).
+    CUtensorMapSwizzle swz = mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    if (mn_major) if (const char* e = std::getenv("B2NN_TC_MN_TMA_SWIZZLE")) swz = CUtensorMapSwizzle(std::atoi(e));
+    CUresult r;
+    if (mn_major && as_3d) {
+        // The contiguous M/N index is folded into (32 floats, atom): {32, k, atoms} with strides {ld*4, 128} bytes, so a
+        // single box {32, 32, box_rows/32} lands in shared memory exactly as box_rows/32 consecutive 2-D boxes would.
+        // Elements of the last atom past mn_end alias the start of the next k-row (readable: rows are padded, arenas carry
+        // slack); they only feed output rows / columns >= M / N, which the epilogue never stores.
+        cuuint64_t gdim[3] = {32u, cuuint64_t(outer), cuuint64_t((inner + 31) / 32)};
+        cuuint64_t gstride[2] = {cuuint64_t(ld) * 4, 128u};
+        cuuint32_t box[3] = {32u, 32u, cuuint32_t((box_rows + 31) / 32)};
+        cuuint32_t estr[3] = {1u, 1u, 1u};
+        r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t gdim[2] = {cuuint64_t(inner), cuuint64_t(outer)};
+        cuuint64_t gstride[1] = {cuuint64_t(ld) * 4};
+        cuuint32_t box[2] = {32u, cuuint32_t(mn_major ? 32 : box_rows)};
+        cuuint32_t estr[2] = {1u, 1u};
+        r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed, CUresult " + std::to_string(int(r)); return false; }
     return true;
 }
@@ -287,8 +313,13 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
 
     const int64_t a_mn_end = g.a_mn_end > 0 ? g.a_mn_end : g.a_mn0 + g.M;
     const int64_t a_k_end = g.a_k_end > 0 ? g.a_k_end : g.a_k0 + g.K;
-    if (!encode_operand(&plan.map_a, g.A, g.lda, g.a_major != 0, a_mn_end, a_k_end, BM, err)) return false;
-    if (!encode_operand(&plan.map_b, g.B, g.ldb, g.b_major != 0, g.b_mn0 + g.N, g.b_k0 + g.K, bn, err)) return false;
+    // One 3-D box per MN-major tile needs the operand origin on a 32-float atom boundary (tile offsets always are) and
+    // the folded view to stay inside memory the caller owns (mn_slack: the operand allocation is padded accordingly).
+    const bool no3d = std::getenv("B2NN_TC_NO_3D") != nullptr;
+    plan.a_3d = g.a_major && g.mn_slack && !no3d && (g.a_mn0 % 32 == 0);
+    plan.b_3d = g.b_major && g.mn_slack && !no3d && (g.b_mn0 % 32 == 0);
+    if (!encode_operand(&plan.map_a, g.A, g.lda, g.a_major != 0, a_mn_end, a_k_end, BM, plan.a_3d, err)) return false;
+    if (!encode_operand(&plan.map_b, g.B, g.ldb, g.b_major != 0, g.b_mn0 + g.N, g.b_k0 + g.K, bn, plan.b_3d, err)) return false;
     plan.valid = true;
     return true;
 }
@@ -301,9 +332,11 @@ cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream) {
     a.k_blocks = pl.k_blocks; a.k_blocks_total = pl.k_blocks_total;
     a.a_mn0 = int(pl.g.a_mn0); a.a_k0 = int(pl.g.a_k0); a.b_mn0 = int(pl.g.b_mn0); a.b_k0 = int(pl.g.b_k0);
     a.epi = pl.g.epi; a.atomic = pl.grid_z > 1 ? 1 : 0; a.stages = pl.stages;
-    a.mn_lbo = ATOM_BYTES; a.mn_sbo = 1024;
+    a.a_3d = pl.a_3d ? 1 : 0; a.b_3d = pl.b_3d ? 1 : 0;
+    a.mn_lbo = ATOM_BYTES; a.mn_sbo = 512; a.mn_layout = 1;
     if (const char* e = std::getenv("B2NN_TC_MN_LBO")) a.mn_lbo = uint32_t(std::atoi(e));   // bring-up knobs
     if (const char* e = std::getenv("B2NN_TC_MN_SBO")) a.mn_sbo = uint32_t(std::atoi(e));
+    if (const char* e = std::getenv("B2NN_TC_MN_LAYOUT")) a.mn_layout = uint32_t(std::atoi(e));
     switch (pl.block_n) {
         case 16:  return launch_bn<16>(pl, a, stream);
         case 32:  return launch_bn<32>(pl, a, stream);

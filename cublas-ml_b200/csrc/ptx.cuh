@@ -69,6 +69,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
+// 3-D tiled load (used for MN-major operands: {32 floats, k rows, 32-float atoms} so one instruction fills a whole tile).
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::
+            "r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // ---- tcgen05 ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(dst_smem)),
@@ -127,14 +136,18 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 // Shared-memory matrix descriptor for tcgen05.mma (PTX ISA "matrix descriptor"; layout documented field by field in
-// DESIGN.md).  start/lbo/sbo are byte quantities, all multiples of 16.  Swizzle: 128-byte (layout type 2).
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t start_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// DESIGN.md).  start/lbo/sbo are byte quantities, all multiples of 16.
+// layout_type: 2 = SWIZZLE_128B (16-byte chunks XOR row%8; K-major tiles),
+//              1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4; the only swizzle tcgen05 accepts for MN-major
+//                  4-byte operands — TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t start_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 2) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((start_bytes & 0x3FFFFu) >> 4);         // bits [0,14)
     d |= static_cast<uint64_t>((lbo_bytes & 0x3FFFFu) >> 4) << 16;     // bits [16,30)
     d |= static_cast<uint64_t>((sbo_bytes & 0x3FFFFu) >> 4) << 32;     // bits [32,46)
     d |= static_cast<uint64_t>(1) << 46;                               // descriptor version (Blackwell)
-    d |= static_cast<uint64_t>(2) << 61;                               // SWIZZLE_128B
+    d |= static_cast<uint64_t>(layout_type & 7u) << 61;
     return d;
 }
 

@@ -160,7 +160,9 @@ int b2nn_comm_barrier(b2nn_ctx* ctx);
 /* Raw GEMM entry used by the kernel unit tests and the roofline benchmark: D(m,n) = sum_k A(m,k) B(n,k), D stored
  * at D[n*ldd + m].  a_major / b_major: 0 = K contiguous (A[m*lda+k]), 1 = M/N contiguous (A[k*lda+m]).
  * epi: 0 store, 1 sigmoid, 2 tanh, 3 multiply by sigmoid'(aux), 4 multiply by tanh'(aux) with aux = activation values
- * laid out like D.  All pointers are device pointers.  backend: 0 fp32 FFMA, 1 tcgen05 tf32. */
+ * laid out like D.  All pointers are device pointers.  backend: 0 fp32 FFMA, 1 tcgen05 tf32, 3 tcgen05 tf32 where
+ * the caller guarantees 32 floats of readable slack after every row of an M/N-contiguous operand (one TMA box per
+ * tile instead of one per 32-float atom). */
 int b2nn_gemm(b2nn_ctx* ctx, int backend, const float* A, int64_t lda, int a_major, const float* B, int64_t ldb,
               int b_major, float* D, int64_t ldd, int M, int N, int K, int epi, const float* aux, int64_t ldaux);
 /* Momentum update kernel alone: v = mu*v + alpha*g ; theta = theta + v over count elements (device pointers). */

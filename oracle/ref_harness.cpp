@@ -14,6 +14,7 @@
 #include <thread>
 #include <iostream>
 #include <sstream>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cstdint>
@@ -31,6 +32,10 @@
 #include "activations.h"
 #include "costfunctions.h"
 #include "randinitweights.h"
+
+static void trace(const char* what) {
+    if (std::getenv("REF_TRACE")) { std::fprintf(stderr, "[ref_harness] %s\n", what); std::fflush(stderr); }
+}
 
 extern "C" {
 
@@ -95,13 +100,16 @@ int ref_train(const ref_problem* p, const float* theta0, unsigned long long seed
     // makes those free(nullptr).
     void* mem = std::calloc(1, sizeof(cublasNN));
     if (!mem) return 2;
+    trace("construct");
     cublasNN* nn = new (mem) cublasNN;
-
+    trace("seed");
     curandSetPseudoRandomGeneratorSeed(nn->gen, seed);
     curandSetGeneratorOffset(nn->gen, 0ULL);
 
     std::vector<int> layers(p->layers, p->layers + p->n_layers);
+    trace("setLayers");
     nn->setLayers(layers.data(), p->n_layers, p->init_kind == 1 ? randInitWeights1GPU : randInitWeights2GPU);
+    trace("theta io");
     if (theta0)
         cudaMemcpy(nn->thetaBaseGPU, theta0, sizeof(float) * size_t(nn->totalThetaSize), cudaMemcpyHostToDevice);
     if (theta0_out)
@@ -113,13 +121,16 @@ int ref_train(const ref_problem* p, const float* theta0, unsigned long long seed
             xv[size_t(i)].assign(p->x + i * p->n, p->x + (i + 1) * p->n);
             yv[size_t(i)].assign(p->y + i * p->ycols, p->y + (i + 1) * p->ycols);
         }
+        trace("setData");
         nn->setData(xv, yv, p->classify != 0);
     }
+    trace("bias+copy");
     nn->setIters(p->iters);
     nn->setDisplay(p->display > 0 ? p->display : 1);
     nn->addBiasData();
     nn->copyDataGPU();
 
+    trace("train");
     std::ostringstream captured;
     std::streambuf* old = std::cout.rdbuf(captured.rdbuf());
     cudaDeviceSynchronize();
@@ -136,6 +147,7 @@ int ref_train(const ref_problem* p, const float* theta0, unsigned long long seed
     cudaDeviceSynchronize();
     auto t1 = std::chrono::steady_clock::now();
     std::cout.rdbuf(old);
+    trace("trained");
 
     parse_log(captured.str(), log_iter, log_J, log_cap, res);
     res->call_seconds = secs;
@@ -145,8 +157,10 @@ int ref_train(const ref_problem* p, const float* theta0, unsigned long long seed
     cudaError_t e = cudaGetLastError();   // the reference double-frees some device buffers (cublasNN.cpp:742 vs 897)
     (void)e;
 
+    trace("destroy");
     nn->~cublasNN();
     std::free(mem);
+    trace("done");
     return 0;
 }
 

@@ -20,16 +20,19 @@ def _operand(mn, k, major, gen, pad=4):
         t = torch.randn(mn, ld, device="cuda", generator=gen, dtype=torch.float32)
         return t, ld, t[:, :k].double()
     ld = (mn + pad - 1) // pad * pad + pad
-    t = torch.randn(k, ld, device="cuda", generator=gen, dtype=torch.float32)
-    return t, ld, t[:, :mn].double().t()
+    t = torch.randn(k + 1, ld, device="cuda", generator=gen, dtype=torch.float32)   # +1 row: slack for backend 3
+    if pad >= 32:
+        t[:, mn:] = float("nan")     # the slack may be read (backend 3) but must never reach a stored output
+    return t, ld, t[:k, :mn].double().t()
 
 
 def _run(net, b2nn, backend, M, N, K, majors, epi=0, seed=0):
     gen = torch.Generator(device="cuda")
     gen.manual_seed(seed)
     a_major, b_major = majors
-    A, lda, Ad = _operand(M, K, a_major, gen)
-    B, ldb, Bd = _operand(N, K, b_major, gen)
+    pad = 32 if backend == 3 else 4
+    A, lda, Ad = _operand(M, K, a_major, gen, pad)
+    B, ldb, Bd = _operand(N, K, b_major, gen, pad)
     ldd = (M + 3) // 4 * 4 + 8
     D = torch.full((N, ldd), 7.0, device="cuda", dtype=torch.float32)
     aux = torch.tanh(torch.randn(N, ldd, device="cuda", generator=gen, dtype=torch.float32)) * 0.9
@@ -63,12 +66,14 @@ def test_ffma_gemm_matches_fp64(net, b2nn, kind, shape):
     assert torch.all(err <= 4e-6 * bound + 1e-6), (kind, shape, float(err.max()))
 
 
+@pytest.mark.parametrize("backend", [1, 3])
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("kind", list(MAJORS))
-def test_tcgen05_gemm_matches_fp64_within_tf32(net, b2nn, kind, shape):
-    """TF32 keeps 10 mantissa bits of each input: |err| <= ~2^-9 * sum|a||b| per output element."""
+def test_tcgen05_gemm_matches_fp64_within_tf32(net, b2nn, kind, shape, backend):
+    """TF32 keeps 10 mantissa bits of each input: |err| <= ~2^-9 * sum|a||b| per output element.
+    backend 3 = one 3-D TMA box per M/N-contiguous tile (padded operands, NaN in the padding)."""
     M, N, K = shape
-    got, ref, bound = _run(net, b2nn, 1, M, N, K, MAJORS[kind])
+    got, ref, bound = _run(net, b2nn, backend, M, N, K, MAJORS[kind])
     err = (got - ref).abs()
     tol = 1.25 * 2.0 ** -9 * bound + 1e-5
     bad = err > tol
@@ -76,7 +81,7 @@ def test_tcgen05_gemm_matches_fp64_within_tf32(net, b2nn, kind, shape):
 
 
 @pytest.mark.parametrize("epi", [1, 2, 3, 4])
-@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("backend", [0, 1, 3])
 def test_fused_epilogues(net, b2nn, backend, epi):
     M, N, K = 520, 96, 200
     got, ref, bound = _run(net, b2nn, backend, M, N, K, MAJORS["fwd" if epi < 3 else "bwd"], epi=epi, seed=epi)
