@@ -49,7 +49,9 @@ struct TcPlan {
     int stages = 0;
     int k_blocks = 0;         // per split
     int k_blocks_total = 0;
-    unsigned grid_x = 0, grid_y = 0, grid_z = 0;
+    int ncta = 1;             // 1: one CTA per 128-row tile; 2: CTA pair (cta_group::2) per 256-row tile
+    int tiles_m = 0, tiles_n = 0, splits = 1;
+    unsigned grid_x = 0;      // persistent grid: min(work items, SMs / ncta) * ncta
     size_t smem_bytes = 0;
     bool a_3d = false, b_3d = false;
     bool valid = false;

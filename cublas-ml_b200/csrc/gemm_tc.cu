@@ -25,6 +25,7 @@
 #include "epilogue.cuh"
 #include "ptx.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -32,162 +33,273 @@
 namespace b2 {
 namespace {
 
-constexpr int BM = 128;
+constexpr int BM = 128;                // rows of the output tile owned by ONE CTA (TMEM lanes)
 constexpr int BK = 32;                 // floats per K block = 128 bytes
 constexpr int UMMA_K = 8;              // tf32: 32 bytes per instruction
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;           // 2 warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int A_TILE_BYTES = BM * BK * 4;
 constexpr int ATOM_BYTES = 32 * BK * 4;   // one MN-major box: 32 (mn) x 32 (k) floats
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int MAX_STAGES = 8;
 
-__host__ __device__ constexpr int b_tile_bytes(int bn, bool b_mn) {
-    return b_mn ? ((bn + 31) / 32) * ATOM_BYTES : bn * BK * 4;
+// bytes of the B tile ONE CTA stages: `rows` = N rows this CTA loads (BN, or BN/2 in a CTA pair)
+__host__ __device__ constexpr int b_tile_bytes(int rows, bool b_mn) {
+    return b_mn ? ((rows + 31) / 32) * ATOM_BYTES : rows * BK * 4;
 }
 
 struct TcArgs {
     float* D; int64_t ldd;
     const float* aux; int64_t ldaux;
     int M, N;
-    int k_blocks;          // K blocks handled by one CTA (per split)
+    int tiles_m, tiles_n, splits;   // work item = (tile_m, tile_n, split); tile_m counts (128 * NCTA)-row tiles
+    int k_blocks;                   // K blocks per split
     int k_blocks_total;
     int a_mn0, a_k0, b_mn0, b_k0;
     int epi;
-    int atomic;            // split-K: accumulate with red.global.add
+    int atomic;                     // split-K: accumulate with red.global.add
     int stages;
     uint32_t mn_lbo, mn_sbo, mn_layout;   // MN-major descriptor: 4096 / 512 / type 1 (overridable for bring-up)
-    int a_3d, b_3d;        // MN-major operand fetched with one 3-D TMA box per tile (origin is a multiple of 32)
+    int a_3d, b_3d;                 // MN-major operand fetched with one 3-D TMA box per tile
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// Fast forms for the tensor-core epilogue (tf32 mode): MUFU.EX2 + MUFU.RCP, relative error ~1e-6 — three orders below
+// the tf32 rounding of the contraction they follow.  The fp32 FFMA path keeps expf / tanhf (epilogue.cuh).
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// Persistent, warp-specialised tcgen05 GEMM.  NCTA = 1: one CTA per 128 x BN tile.  NCTA = 2: a CTA pair (cluster of
+// two, cta_group::2) per 256 x BN tile — each CTA stages its own 128 rows of A and HALF of B, so the L2 -> shared
+// traffic per multiply-add drops by a third; the leader CTA issues the MMAs for both.
+//   warp 0      TMA producer (ring of `stages` slots, runs ahead across tiles)
+//   warp 1      TMEM allocator; in the leader CTA also the MMA issuer (one lane)
+//   warps 2..9  epilogue: TMEM -> registers -> fused activation / derivative -> coalesced global stores.  Two
+//               accumulator buffers in TMEM (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+template <int BN, bool A_MN, bool B_MN, int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcArgs p) {
-    constexpr int B_TILE = b_tile_bytes(BN, B_MN);
-    constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-    constexpr uint32_t IDESC = umma_idesc_tf32(BM, BN, A_MN, B_MN);
+    constexpr int B_ROWS = BN / NCTA;                       // N rows of B this CTA stages
+    constexpr int B_TILE = b_tile_bytes(B_ROWS, B_MN);
+    constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE;      // per CTA
+    constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;        // TMEM columns of one accumulator buffer
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;            // 64 .. 512, always a power of two
+    constexpr uint32_t IDESC = umma_idesc_tf32(BM * NCTA, BN, A_MN, B_MN);
+    static_assert(!(B_MN && NCTA == 2 && BN < 64), "a CTA of a pair must stage whole 32-float atoms of B");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
-    uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + size_t(stages) * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + stages;
-    uint64_t* tmem_full = empty_bar + stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* full_bar   = reinterpret_cast<uint64_t*>(smem + size_t(stages) * STAGE_BYTES);
+    uint64_t* empty_bar  = full_bar + MAX_STAGES;
+    uint64_t* tmem_full  = empty_bar + MAX_STAGES;          // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                   // [2]
+    uint32_t* tmem_slot  = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    const int kb_begin = blockIdx.z * p.k_blocks;
-    int nkb = p.k_blocks_total - kb_begin;
-    if (nkb > p.k_blocks) nkb = p.k_blocks;
+    const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int worker = NCTA == 2 ? int(cluster_id_x()) : int(blockIdx.x);
+    const int n_workers = NCTA == 2 ? int(num_clusters_x()) : int(gridDim.x);
+    const int tiles_mn = p.tiles_m * p.tiles_n;
+    const int total_work = tiles_mn * p.splits;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
-        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], NCTA); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS * NCTA); }
         mbar_fence_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
+        if (NCTA == 2) { tmem_alloc_pair(tmem_slot, TMEM_COLS); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
     }
+    __syncwarp();                 // warp 0 diverged for the barrier init; cluster barriers need converged warps
     tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (kb / stages) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
-                uint8_t* sb = sa + A_TILE_BYTES;
-                const int kc = (kb_begin + kb) * BK;
-                if (A_MN) {
-                    if (p.a_3d) {
-                        tma_load_3d(sa, &map_a, &full_bar[s], 0, p.a_k0 + kc, (p.a_mn0 + m0) >> 5);
-                    } else {
+            int it = 0;
+            for (int w = worker; w < total_work; w += n_workers) {
+                const int split = w / tiles_mn, rem = w - split * tiles_mn;
+                const int tile_n = rem / p.tiles_m, tile_m = rem - tile_n * p.tiles_m;
+                const int m0 = (tile_m * NCTA + int(rank)) * BM;          // this CTA's 128 rows of A
+                const int n0 = tile_n * BN + int(rank) * B_ROWS;          // this CTA's share of B
+                const int kb0 = split * p.k_blocks;
+                int nkb = p.k_blocks_total - kb0;
+                if (nkb > p.k_blocks) nkb = p.k_blocks;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
+                    uint8_t* sb = sa + A_TILE_BYTES;
+                    uint64_t* bar = &full_bar[s];
+                    const int kc = (kb0 + kb) * BK;
+                    if (NCTA == 1) mbar_expect_tx(bar, STAGE_BYTES);
+                    if (A_MN) {
+                        if (p.a_3d) {
+                            if (NCTA == 2) tma_load_3d_pair(sa, &map_a, bar, 0, p.a_k0 + kc, (p.a_mn0 + m0) >> 5);
+                            else tma_load_3d(sa, &map_a, bar, 0, p.a_k0 + kc, (p.a_mn0 + m0) >> 5);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < BM / 32; ++i)
-                            tma_load_2d(sa + i * ATOM_BYTES, &map_a, &full_bar[s], p.a_mn0 + m0 + i * 32, p.a_k0 + kc);
-                    }
-                } else {
-                    tma_load_2d(sa, &map_a, &full_bar[s], p.a_k0 + kc, p.a_mn0 + m0);
-                }
-                if (B_MN) {
-                    if (p.b_3d) {
-                        tma_load_3d(sb, &map_b, &full_bar[s], 0, p.b_k0 + kc, (p.b_mn0 + n0) >> 5);
+                            for (int i = 0; i < BM / 32; ++i) {
+                                if (NCTA == 2) tma_load_2d_pair(sa + i * ATOM_BYTES, &map_a, bar, p.a_mn0 + m0 + i * 32, p.a_k0 + kc);
+                                else tma_load_2d(sa + i * ATOM_BYTES, &map_a, bar, p.a_mn0 + m0 + i * 32, p.a_k0 + kc);
+                            }
+                        }
                     } else {
-#pragma unroll
-                        for (int i = 0; i < (BN + 31) / 32; ++i)
-                            tma_load_2d(sb + i * ATOM_BYTES, &map_b, &full_bar[s], p.b_mn0 + n0 + i * 32, p.b_k0 + kc);
+                        if (NCTA == 2) tma_load_2d_pair(sa, &map_a, bar, p.a_k0 + kc, p.a_mn0 + m0);
+                        else tma_load_2d(sa, &map_a, bar, p.a_k0 + kc, p.a_mn0 + m0);
                     }
-                } else {
-                    tma_load_2d(sb, &map_b, &full_bar[s], p.b_k0 + kc, p.b_mn0 + n0);
+                    if (B_MN) {
+                        if (p.b_3d) {
+                            if (NCTA == 2) tma_load_3d_pair(sb, &map_b, bar, 0, p.b_k0 + kc, (p.b_mn0 + n0) >> 5);
+                            else tma_load_3d(sb, &map_b, bar, 0, p.b_k0 + kc, (p.b_mn0 + n0) >> 5);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < (B_ROWS + 31) / 32; ++i) {
+                                if (NCTA == 2) tma_load_2d_pair(sb + i * ATOM_BYTES, &map_b, bar, p.b_mn0 + n0 + i * 32, p.b_k0 + kc);
+                                else tma_load_2d(sb + i * ATOM_BYTES, &map_b, bar, p.b_mn0 + n0 + i * 32, p.b_k0 + kc);
+                            }
+                        }
+                    } else {
+                        if (NCTA == 2) tma_load_2d_pair(sb, &map_b, bar, p.b_k0 + kc, p.b_mn0 + n0);
+                        else tma_load_2d(sb, &map_b, bar, p.b_k0 + kc, p.b_mn0 + n0);
+                    }
+                    if (NCTA == 2) {
+                        // the leader's barrier counts one arrival per CTA and the bytes of BOTH CTAs' boxes
+                        if (leader) mbar_expect_tx(bar, 2 * STAGE_BYTES);
+                        else mbar_arrive_remote(bar, 0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % stages;
-            const uint32_t ph = (kb / stages) & 1;
-            mbar_wait(&full_bar[s], ph);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t sa = smem_u32(smem + size_t(s) * STAGE_BYTES);
-                const uint32_t sb = sa + A_TILE_BYTES;
+        // ---------------- MMA issuer (leader CTA only) ----------------
+        if (leader) {
+            int it = 0, t = 0;
+            for (int w = worker; w < total_work; w += n_workers, ++t) {
+                const int split = w / tiles_mn;
+                const int kb0 = split * p.k_blocks;
+                int nkb = p.k_blocks_total - kb0;
+                if (nkb > p.k_blocks) nkb = p.k_blocks;
+                const int acc = t & 1;
+                const uint32_t acc_ph = (t >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_ph ^ 1);          // epilogue has drained this accumulator buffer
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + uint32_t(acc) * ACC_COLS;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_u32(smem + size_t(s) * STAGE_BYTES);
+                        const uint32_t sb = sa + A_TILE_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                    const uint64_t da = A_MN ? umma_smem_desc(sa + kk * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout)
-                                             : umma_smem_desc(sa + kk * UMMA_K * 4, 16, 1024);
-                    const uint64_t db = B_MN ? umma_smem_desc(sb + kk * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout)
-                                             : umma_smem_desc(sb + kk * UMMA_K * 4, 16, 1024);
-                    umma_tf32(tmem_base, da, db, IDESC, (kb | kk) != 0 ? 1u : 0u);
+                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                            const uint64_t da = A_MN ? umma_smem_desc(sa + kk * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                     : umma_smem_desc(sa + kk * UMMA_K * 4, 16, 1024);
+                            const uint64_t db = B_MN ? umma_smem_desc(sb + kk * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                     : umma_smem_desc(sb + kk * UMMA_K * 4, 16, 1024);
+                            if (NCTA == 2) umma_tf32_pair(tmem_d, da, db, IDESC, (kb | kk) != 0 ? 1u : 0u);
+                            else umma_tf32(tmem_d, da, db, IDESC, (kb | kk) != 0 ? 1u : 0u);
+                        }
+                        // slot reusable (in both CTAs) once these MMAs have read it; accumulator complete after the last
+                        if (NCTA == 2) umma_commit_pair(&empty_bar[s], 3); else umma_commit(&empty_bar[s]);
+                        if (kb == nkb - 1) { if (NCTA == 2) umma_commit_pair(&tmem_full[acc], 3); else umma_commit(&tmem_full[acc]); }
+                    }
+                    __syncwarp();
                 }
-                umma_commit(&empty_bar[s]);                 // slot reusable once these MMAs have read it
-                if (kb == nkb - 1) umma_commit(tmem_full);  // accumulator complete
             }
-            __syncwarp();
         }
     } else {
         // ---------------- epilogue ----------------
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const int q = warp & 3;                       // TMEM lane quarter this warp may read
-        const int m = m0 + q * 32 + lane;
-        const bool m_ok = m < p.M;
-        const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+        const int q = warp & 3;                          // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                // which half of the tile's columns
         constexpr int CH = BN < 32 ? 16 : 32;
+        constexpr int COLS_PER_WARP = (BN / 2 >= CH) ? BN / 2 : CH;
+        const int c_begin = half * COLS_PER_WARP;
+        const int c_end = (c_begin + COLS_PER_WARP < BN) ? c_begin + COLS_PER_WARP : BN;
+        const float* __restrict__ aux = p.aux;
+        float* __restrict__ Dp = p.D;
+        int t = 0;
+        for (int w = worker; w < total_work; w += n_workers, ++t) {
+            const int split = w / tiles_mn, rem = w - split * tiles_mn;
+            const int tile_n = rem / p.tiles_m, tile_m = rem - tile_n * p.tiles_m;
+            const int m = (tile_m * NCTA + int(rank)) * BM + q * 32 + lane;
+            const int n0 = tile_n * BN;
+            const bool m_ok = m < p.M;
+            const int acc = t & 1;
+            const uint32_t acc_ph = (t >> 1) & 1;
+            mbar_wait(&tmem_full[acc], acc_ph);
+            tc_fence_after();
+            const uint32_t lane_addr = tmem_base + uint32_t(acc) * ACC_COLS + (uint32_t(q * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += CH) {
-            if (n0 + c0 >= p.N) break;                // warp-uniform
-            uint32_t r[CH];
-            if constexpr (CH == 32) tmem_ld_32x32(lane_addr + c0, r); else tmem_ld_32x16(lane_addr + c0, r);
-            tmem_ld_wait();
+            for (int c0 = c_begin; c0 < c_end; c0 += CH) {
+                if (n0 + c0 >= p.N) break;                // warp-uniform
+                // derivative epilogues: issue the whole chunk's activation loads first so they overlap the TMEM read
+                float av[CH];
+                if (p.epi >= EPI_DSIGMOID) {
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                const int n = n0 + c0 + j;
-                if (n < p.N && m_ok) {
-                    float v = __uint_as_float(r[j]);
-                    if (p.epi != EPI_STORE) {
-                        const float a = (p.epi >= EPI_DSIGMOID) ? __ldg(p.aux + int64_t(n) * p.ldaux + m) : 0.f;
-                        v = apply_epilogue(p.epi, v, a);
+                    for (int j = 0; j < CH; ++j) {
+                        const int n = n0 + c0 + j;
+                        av[j] = (n < p.N && m_ok) ? __ldg(aux + int64_t(n) * p.ldaux + m) : 0.f;
                     }
-                    float* dst = p.D + int64_t(n) * p.ldd + m;
-                    if (p.atomic) atomicAdd(dst, v); else *dst = v;
+                }
+                uint32_t r[CH];
+                if constexpr (CH == 32) tmem_ld_32x32(lane_addr + c0, r); else tmem_ld_32x16(lane_addr + c0, r);
+                tmem_ld_wait();
+                float v[CH];
+                switch (p.epi) {                          // warp-uniform
+                    case EPI_SIGMOID:
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = sigmoid_fast(__uint_as_float(r[j]));
+                        break;
+                    case EPI_TANH:
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = tanh_fast(__uint_as_float(r[j]));
+                        break;
+                    case EPI_DSIGMOID:
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) * (av[j] * (1.0f - av[j]));
+                        break;
+                    case EPI_DTANH:
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) * (1.0f - av[j] * av[j]);
+                        break;
+                    default:
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+                        break;
+                }
+                if (m_ok) {
+                    float* dst = Dp + int64_t(n0 + c0) * p.ldd + m;
+                    if (p.atomic) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) if (n0 + c0 + j < p.N) atomicAdd(dst + int64_t(j) * p.ldd, v[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) if (n0 + c0 + j < p.N) dst[int64_t(j) * p.ldd] = v[j];
+                    }
                 }
             }
+            // this warp is done reading the accumulator buffer: hand it back to the MMA issuer (leader CTA)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (NCTA == 2) mbar_arrive_remote(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
         }
     }
 
+    __syncwarp();                 // producer / issuer lanes rejoin their warps
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) { if (NCTA == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------
@@ -249,27 +361,46 @@ bool encode_operand(CUtensorMap* map, const float* base, int64_t ld, bool mn_maj
     return true;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+int g_num_sms = 0;
+
+template <int BN, bool A_MN, bool B_MN, int NCTA>
 cudaError_t launch_one(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NCTA>;
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid(pl.grid_x, pl.grid_y, pl.grid_z);
-    kern<<<grid, NUM_THREADS, pl.smem_bytes, stream>>>(pl.map_a, pl.map_b, a);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(pl.grid_x, 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = NCTA == 2 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, pl.map_a, pl.map_b, a);
+}
+
+template <int BN, int NCTA>
+cudaError_t launch_majors(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
+    const bool am = pl.g.a_major != 0, bm = pl.g.b_major != 0;
+    if (am && bm) {
+        if constexpr (NCTA == 2 && BN < 64) return cudaErrorInvalidValue; else return launch_one<BN, true, true, NCTA>(pl, a, stream);
+    }
+    if (am && !bm) return launch_one<BN, true, false, NCTA>(pl, a, stream);
+    if (!am && bm) {
+        if constexpr (NCTA == 2 && BN < 64) return cudaErrorInvalidValue; else return launch_one<BN, false, true, NCTA>(pl, a, stream);
+    }
+    return launch_one<BN, false, false, NCTA>(pl, a, stream);
 }
 
 template <int BN>
 cudaError_t launch_bn(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
-    const bool am = pl.g.a_major != 0, bm = pl.g.b_major != 0;
-    if (am && bm) return launch_one<BN, true, true>(pl, a, stream);
-    if (am && !bm) return launch_one<BN, true, false>(pl, a, stream);
-    if (!am && bm) return launch_one<BN, false, true>(pl, a, stream);
-    return launch_one<BN, false, false>(pl, a, stream);
+    return pl.ncta == 2 ? launch_majors<BN, 2>(pl, a, stream) : launch_majors<BN, 1>(pl, a, stream);
 }
 
 }  // namespace
@@ -294,9 +425,22 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     plan.block_n = bn;
     plan.g = g;
 
-    const int stage_bytes = A_TILE_BYTES + b_tile_bytes(bn, g.b_major != 0);
+    if (g_num_sms == 0) {
+        int dev = 0, n = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        g_num_sms = n;
+    }
+    // CTA pairs (cta_group::2, 256-row tiles) whenever there are at least two 128-row tiles to pair up
+    // CTA pairs are numerically verified but currently slower than single CTAs (profiles/): opt-in via B2NN_TC_NCTA=2
+    int ncta = 1;
+    if (const char* e = std::getenv("B2NN_TC_NCTA")) { if (std::atoi(e) == 2 && g.M > BM) ncta = 2; }
+    if (g.b_major && bn < 64) ncta = 1;
+    plan.ncta = ncta;
+
+    const int stage_bytes = A_TILE_BYTES + b_tile_bytes(bn / ncta, g.b_major != 0);
     int stages = (SMEM_LIMIT - 1024 - 256) / stage_bytes;
-    if (stages > 8) stages = 8;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) { err = "tile does not fit shared memory"; return false; }
     plan.stages = stages;
     plan.smem_bytes = size_t(stages) * stage_bytes + 1024 + 256;
@@ -306,10 +450,13 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     if (splits > plan.k_blocks_total) splits = plan.k_blocks_total;
     plan.k_blocks = (plan.k_blocks_total + splits - 1) / splits;
     splits = (plan.k_blocks_total + plan.k_blocks - 1) / plan.k_blocks;
-    plan.grid_x = unsigned((g.M + BM - 1) / BM);
-    plan.grid_y = unsigned((g.N + bn - 1) / bn);
-    plan.grid_z = unsigned(splits);
-    if (plan.grid_y > 65535u || plan.grid_z > 65535u) { err = "grid too large"; return false; }
+    plan.tiles_m = (g.M + BM * ncta - 1) / (BM * ncta);
+    plan.tiles_n = (g.N + bn - 1) / bn;
+    plan.splits = splits;
+    const int64_t work = int64_t(plan.tiles_m) * plan.tiles_n * splits;
+    if (work >= (int64_t(1) << 30)) { err = "too many tiles"; return false; }
+    const int64_t max_workers = g_num_sms / ncta;
+    plan.grid_x = unsigned(std::min<int64_t>(work, max_workers) * ncta);      // persistent: one CTA (pair) per SM (pair)
 
     const int64_t a_mn_end = g.a_mn_end > 0 ? g.a_mn_end : g.a_mn0 + g.M;
     const int64_t a_k_end = g.a_k_end > 0 ? g.a_k_end : g.a_k0 + g.K;
@@ -319,7 +466,7 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     plan.a_3d = g.a_major && g.mn_slack && !no3d && (g.a_mn0 % 32 == 0);
     plan.b_3d = g.b_major && g.mn_slack && !no3d && (g.b_mn0 % 32 == 0);
     if (!encode_operand(&plan.map_a, g.A, g.lda, g.a_major != 0, a_mn_end, a_k_end, BM, plan.a_3d, err)) return false;
-    if (!encode_operand(&plan.map_b, g.B, g.ldb, g.b_major != 0, g.b_mn0 + g.N, g.b_k0 + g.K, bn, plan.b_3d, err)) return false;
+    if (!encode_operand(&plan.map_b, g.B, g.ldb, g.b_major != 0, g.b_mn0 + g.N, g.b_k0 + g.K, bn / ncta, plan.b_3d, err)) return false;   // each CTA of a pair stages half of B
     plan.valid = true;
     return true;
 }
@@ -329,9 +476,10 @@ cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream) {
     TcArgs a;
     a.D = pl.g.D; a.ldd = pl.g.ldd; a.aux = pl.g.aux; a.ldaux = pl.g.ldaux;
     a.M = pl.g.M; a.N = pl.g.N;
+    a.tiles_m = pl.tiles_m; a.tiles_n = pl.tiles_n; a.splits = pl.splits;
     a.k_blocks = pl.k_blocks; a.k_blocks_total = pl.k_blocks_total;
     a.a_mn0 = int(pl.g.a_mn0); a.a_k0 = int(pl.g.a_k0); a.b_mn0 = int(pl.g.b_mn0); a.b_k0 = int(pl.g.b_k0);
-    a.epi = pl.g.epi; a.atomic = pl.grid_z > 1 ? 1 : 0; a.stages = pl.stages;
+    a.epi = pl.g.epi; a.atomic = pl.splits > 1 ? 1 : 0; a.stages = pl.stages;
     a.a_3d = pl.a_3d ? 1 : 0; a.b_3d = pl.b_3d ? 1 : 0;
     a.mn_lbo = ATOM_BYTES; a.mn_sbo = 512; a.mn_layout = 1;
     if (const char* e = std::getenv("B2NN_TC_MN_LBO")) a.mn_lbo = uint32_t(std::atoi(e));   // bring-up knobs

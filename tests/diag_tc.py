@@ -1,5 +1,5 @@
-"""Bring-up diagnostic for the tcgen05 GEMM (not a test): prints error statistics per operand-major combination and
-shape so one GPU call tells which descriptor path is wrong.  python tests/diag_tc.py [--sweep]"""
+"""Bring-up diagnostic for the tcgen05 GEMM (not a test): error statistics per operand-major combination, CTA-pair
+mode and TMA box mode, then timings of the config-C3 contractions.  python tests/diag_tc.py [--perf-only]"""
 import os
 import sys
 
@@ -11,59 +11,95 @@ from conftest import load_b2nn  # noqa: E402
 
 b2nn = load_b2nn()
 MAJORS = {"wgrad(K,K)": (0, 0), "fwd(MN,K)": (1, 0), "kmn(K,MN)": (0, 1), "bwd(MN,MN)": (1, 1)}
-SHAPES = [(128, 256, 32), (128, 256, 64), (128, 64, 32), (128, 16, 32), (256, 256, 128), (300, 70, 45),
-          (4200, 50, 785), (785, 50, 4200), (1000, 513, 130)]
+SHAPES = [(128, 256, 32), (256, 256, 64), (128, 16, 32), (384, 64, 96), (300, 70, 45), (4200, 50, 785),
+          (785, 50, 4200), (1000, 513, 130), (2048, 768, 512)]
 
 
-def operand(mn, k, major, gen):
+def operand(mn, k, major, gen, pad):
     if major == 0:
         ld = (k + 3) // 4 * 4 + 4
         t = torch.randn(mn, ld, device="cuda", generator=gen)
         return t, ld, t[:, :k].double()
-    ld = (mn + 3) // 4 * 4 + 4
-    t = torch.randn(k, ld, device="cuda", generator=gen)
-    return t, ld, t[:, :mn].double().t()
+    ld = (mn + pad - 1) // pad * pad + pad
+    t = torch.randn(k + 1, ld, device="cuda", generator=gen)
+    return t, ld, t[:k, :mn].double().t()
 
 
-def run(net, M, N, K, majors):
+def run(net, backend, M, N, K, majors):
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1)
-    A, lda, Ad = operand(M, K, majors[0], gen)
-    B, ldb, Bd = operand(N, K, majors[1], gen)
+    pad = 32 if backend == 3 else 4
+    A, lda, Ad = operand(M, K, majors[0], gen, pad)
+    B, ldb, Bd = operand(N, K, majors[1], gen, pad)
     ldd = (M + 3) // 4 * 4
     D = torch.zeros(N, ldd, device="cuda")
-    net.gemm(1, A.data_ptr(), lda, majors[0], B.data_ptr(), ldb, majors[1], D.data_ptr(), ldd, M, N, K)
+    net.gemm(backend, A.data_ptr(), lda, majors[0], B.data_ptr(), ldb, majors[1], D.data_ptr(), ldd, M, N, K)
     torch.cuda.synchronize()
     ref = (Ad @ Bd.t()).t()
     bound = (Ad.abs() @ Bd.abs().t()).t() * 2.0 ** -9 * 1.25 + 1e-5
     err = (D[:, :M].double() - ref).abs()
     bad = err > bound
-    return float(err.max()), float((err / bound).max()), float(bad.float().mean()), float(ref.abs().mean())
+    return float(err.max()), float((err / bound).max()), float(bad.float().mean())
+
+
+def perf(net):
+    B, H, I, O = 8192, 4096, 784, 10
+    # (name, M, N, K, a_major, b_major, epi)
+    gemms = [("fwd0", B, H, I + 1, 1, 0, 2), ("fwd1", B, H, H + 1, 1, 0, 2), ("fwd2", B, O, H + 1, 1, 0, 0),
+             ("bwd2", B, H, O, 1, 1, 4), ("bwd1", B, H, H, 1, 1, 4),
+             ("wgrad0", I + 1, H, B, 0, 0, 0), ("wgrad1", H + 1, H, B, 0, 0, 0), ("wgrad2", H + 1, O, B, 0, 0, 0)]
+    stream = torch.cuda.ExternalStream(net.stream())
+    for name, M, N, K, am, bm, epi in gemms:
+        def buf(mn, k, major):
+            if major == 0:
+                ld = (k + 31) // 32 * 32 + 32
+                return torch.randn(mn + 1, ld, device="cuda") * 0.05, ld
+            ld = (mn + 31) // 32 * 32 + 32
+            return torch.randn(k + 1, ld, device="cuda") * 0.05, ld
+        A, lda = buf(M, K, am)
+        Bm, ldb = buf(N, K, bm)
+        ldd = (M + 31) // 32 * 32
+        D = torch.empty(N, ldd, device="cuda")
+        aux = torch.rand(N, ldd, device="cuda")
+        for mode in ("pair", "single"):
+            os.environ["B2NN_TC_NCTA"] = "1" if mode == "single" else "2"
+            try:
+                for _ in range(2):
+                    net.gemm(3, A.data_ptr(), lda, am, Bm.data_ptr(), ldb, bm, D.data_ptr(), ldd, M, N, K, epi, aux.data_ptr(), ldd)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                reps = 5
+                for _ in range(reps):
+                    net.gemm(3, A.data_ptr(), lda, am, Bm.data_ptr(), ldb, bm, D.data_ptr(), ldd, M, N, K, epi, aux.data_ptr(), ldd)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                print(f"perf {name:7s} {mode:6s} M,N,K=({M},{N},{K}) {ms * 1e3:8.1f} us  {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s", flush=True)
+            except Exception as ex:  # noqa: BLE001
+                print(f"perf {name} {mode} EXC {ex}", flush=True)
+                return
+    os.environ["B2NN_TC_NCTA"] = "1"
 
 
 def main():
     net = b2nn.Net()
     ok_all = True
-    for name, mj in MAJORS.items():
-        for shp in SHAPES:
-            try:
-                e, ratio, frac, mag = run(net, *shp, mj)
-                status = "OK " if frac == 0 else "BAD"
-                ok_all &= frac == 0
-                print(f"{status} {name:12s} M,N,K={shp} max_err={e:.3e} err/tol={ratio:.2f} bad_frac={frac:.4f} |ref|={mag:.2f}", flush=True)
-            except Exception as ex:  # noqa: BLE001
-                ok_all = False
-                print(f"EXC {name} {shp}: {ex}", flush=True)
-                return 1
-    if "--sweep" in sys.argv and not ok_all:
-        for lbo, sbo in ((1024, 4096), (4096, 128), (128, 1024), (1024, 128), (128, 4096)):
-            os.environ["B2NN_TC_MN_LBO"], os.environ["B2NN_TC_MN_SBO"] = str(lbo), str(sbo)
+    if "--perf-only" not in sys.argv:
+        for mode, backend, ncta in (("single/2d", 1, "1"), ("single/3d", 3, "1"), ("pair/2d", 1, "2"), ("pair/3d", 3, "2")):
+            os.environ["B2NN_TC_NCTA"] = ncta
             for name, mj in MAJORS.items():
-                if mj == (0, 0):
-                    continue
-                e, ratio, frac, mag = run(net, 128, 256, 64, mj)
-                print(f"sweep LBO={lbo} SBO={sbo} {name:12s} max_err={e:.3e} bad_frac={frac:.4f}", flush=True)
-    print("ALL OK" if ok_all else "SOME BAD")
+                for shp in SHAPES:
+                    try:
+                        e, ratio, frac = run(net, backend, *shp, mj)
+                        status = "OK " if frac == 0 else "BAD"
+                        ok_all &= frac == 0
+                        print(f"{status} {mode:9s} {name:12s} M,N,K={shp} max_err={e:.3e} err/tol={ratio:.2f} bad_frac={frac:.4f}", flush=True)
+                    except Exception as ex:  # noqa: BLE001
+                        print(f"EXC {mode} {name} {shp}: {ex}", flush=True)
+                        return 1
+        print("ALL OK" if ok_all else "SOME BAD", flush=True)
+    os.environ["B2NN_TC_NCTA"] = "1"
+    perf(net)
     return 0
 
 
