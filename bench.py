@@ -286,7 +286,9 @@ def run_ours(args):
     line = None
     if rank == 0:
         # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload ---------------------
-        cpu = cpu_baseline(layers, min(B, 2048 if args.workload != "c1" else B))
+        # rank 0 at N = 1 only (torchrun pins OMP_NUM_THREADS=1 for N > 1, which would misreport the host cores)
+        cpu = cpu_baseline(layers, min(B, 2048 if args.workload != "c1" else B)) if world == 1 else \
+            {"value": None, "unit": "samples/s", "cores": None, "kind": "port", "sample": "measured at N=1 only"}
         line = {
             "metric": "train_samples_per_sec", "value": round(value, 1), "unit": "samples/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": round(secs / K * 1e3, 4), "higher_is_better": True,
