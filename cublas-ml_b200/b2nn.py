@@ -45,7 +45,7 @@ class TrainResult(C.Structure):
 ABI_SYMBOLS = [
     "b2nn_create", "b2nn_destroy", "b2nn_last_error", "b2nn_device_ok", "b2nn_version", "b2nn_set_layers",
     "b2nn_num_weights", "b2nn_get_weights", "b2nn_set_weights", "b2nn_set_train_data", "b2nn_train",
-    "b2nn_train_step_host", "b2nn_reset_velocity", "b2nn_evaluate", "b2nn_predict", "b2nn_predict_device",
+    "b2nn_train_step_host", "b2nn_train_host", "b2nn_reset_velocity", "b2nn_evaluate", "b2nn_predict", "b2nn_predict_device",
     "b2nn_builtin_kind", "b2nn_comm_unique_id", "b2nn_comm_init", "b2nn_comm_barrier", "b2nn_gemm",
     "b2nn_momentum_update", "b2nn_stream", "b2nn_profile_enable", "b2nn_profile_read",
 ]
@@ -84,6 +84,9 @@ def lib():
     L.b2nn_train.argtypes = [vp, C.POINTER(TrainDesc), vp, vp, C.POINTER(TrainResult)]
     L.b2nn_train_step_host.restype = C.c_int
     L.b2nn_train_step_host.argtypes = [vp, C.POINTER(TrainDesc), vp, vp, i64, i64, C.POINTER(C.c_float)]
+    L.b2nn_train_host.restype = C.c_int
+    L.b2nn_train_host.argtypes = [vp, C.POINTER(TrainDesc), vp, vp, i64, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                  C.POINTER(TrainResult)]
     L.b2nn_reset_velocity.restype = C.c_int
     L.b2nn_reset_velocity.argtypes = [vp]
     L.b2nn_evaluate.restype = C.c_int
@@ -228,6 +231,15 @@ class Net:
         _check(lib().b2nn_train_step_host(self._h, C.byref(desc), x_cm_ptr, y_cm_ptr, rows, global_rows, C.byref(J)),
                "b2nn_train_step_host")
         return float(J.value)
+
+    def train_host(self, desc: TrainDesc, x_ptr, y_ptr, m: int):
+        """Streaming trainer over host buffers (ctypes pointers).  Returns (per-step costs, TrainResult)."""
+        steps = desc.iters * desc.batch_num
+        J = np.empty(steps, dtype=np.float32)
+        r = TrainResult()
+        _check(lib().b2nn_train_host(self._h, C.byref(desc), x_ptr, y_ptr, m, self.layers[0] + 1, self.layers[-1],
+                                     J.ctypes.data_as(C.POINTER(C.c_float)), C.byref(r)), "b2nn_train_host")
+        return J, r
 
     def reset_velocity(self):
         _check(lib().b2nn_reset_velocity(self._h), "b2nn_reset_velocity")

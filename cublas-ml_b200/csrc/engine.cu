@@ -139,11 +139,17 @@ struct b2nn_ctx {
     // boundary so MN-major TMA boxes can address it as whole 32-float atoms.  Built per train call when needed.
     float* Xsp = nullptr; float* Ysp = nullptr; int64_t ldsp = 0; int sp_nb = 0; int64_t sp_stride = 0;
 
+    // double-buffered staging of b2nn_train_host (streaming trainer)
+    float* Xst[2] = {nullptr, nullptr}; float* Yst[2] = {nullptr, nullptr}; int64_t ldst = 0, capst = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t st_copied[2] = {nullptr, nullptr}, st_consumed[2] = {nullptr, nullptr};
+    double* d_jsteps = nullptr; double* h_jsteps = nullptr; int64_t jsteps_cap = 0;
+
     // host-step staging (b2nn_train_step_host)
     float* Xs = nullptr; float* Ys = nullptr; int64_t lds = 0, caps = 0;
 
     Workspace ws;
-    std::map<int64_t, StepPlan> plans;   // keyed by rows; valid for (ws, X, precision) they were built with
+    std::map<std::pair<int64_t, const float*>, StepPlan> plans;   // keyed by (rows, X base); valid for the (ws, ldx, precision, ...) below
     int plans_prec = -1;
     const float* plans_x = nullptr;
     int64_t plans_ldx = 0, plans_xtotal = 0;
@@ -287,15 +293,17 @@ void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
 // x_aligned: every batch start passed to run_gemm is a multiple of 32 samples (one 3-D TMA box per X tile).
 StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64_t x_total, bool x_aligned, int prec,
                    int act_kind) {
-    if (c->plans_prec != prec || c->plans_x != X || c->plans_ldx != ldx || c->plans_act != act_kind ||
-        c->plans_xtotal != x_total || c->plans_xaligned != x_aligned) {
+    if (c->plans_prec != prec || c->plans_ldx != ldx || c->plans_act != act_kind || c->plans_xtotal != x_total ||
+        c->plans_xaligned != x_aligned) {
         c->plans.clear();
-        c->plans_prec = prec; c->plans_x = X; c->plans_ldx = ldx; c->plans_act = act_kind; c->plans_xtotal = x_total;
+        c->plans_prec = prec; c->plans_ldx = ldx; c->plans_act = act_kind; c->plans_xtotal = x_total;
         c->plans_xaligned = x_aligned;
     }
-    auto it = c->plans.find(rows);
+    const auto key = std::make_pair(rows, X);
+    auto it = c->plans.find(key);
     if (it != c->plans.end()) return it->second;
-    StepPlan& sp = c->plans[rows];
+    if (c->plans.size() > 64) c->plans.clear();        // bounded: a few batch sizes x a few input buffers
+    StepPlan& sp = c->plans[key];
     sp.rows = rows;
     const int nl = int(c->layers.size());
     const int nw = nl - 1;
@@ -659,6 +667,14 @@ void b2nn_destroy(b2nn_ctx* c) {
     cudaFree(c->W); cudaFree(c->V); cudaFree(c->G);
     cudaFree(c->X); cudaFree(c->Y); cudaFree(c->Xs); cudaFree(c->Ys); cudaFree(c->Xsp); cudaFree(c->Ysp);
     cudaFree(c->d_acc);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->Xst[i]); cudaFree(c->Yst[i]);
+        if (c->st_copied[i]) cudaEventDestroy(c->st_copied[i]);
+        if (c->st_consumed[i]) cudaEventDestroy(c->st_consumed[i]);
+    }
+    cudaFree(c->d_jsteps);
+    if (c->h_jsteps) cudaFreeHost(c->h_jsteps);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->h_acc) cudaFreeHost(c->h_acc);
     for (auto e : c->log_events) cudaEventDestroy(e);
     for (auto& r : c->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -1031,6 +1047,102 @@ int b2nn_train_step_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, 
         B2_CUDA(cudaStreamSynchronize(c->stream));
         const double J = c->h_acc[2];
         *J_out = float(d->classify ? J / double(g) : J / (2.0 * double(g)));
+    }
+    return B2NN_OK;
+}
+
+int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const float* y, int64_t m, int n_plus_1, int k,
+                    float* J_steps, b2nn_train_result* result) {
+    auto t_call0 = std::chrono::steady_clock::now();
+    int rc = validate_desc(c, d);
+    if (rc) return rc;
+    if (!x || !y || m < 1) { set_error("train_host: bad arguments"); return B2NN_ERR_ARG; }
+    if (n_plus_1 != c->layers[0] + 1 || k != c->layers.back()) { set_error("data shape does not match the layers"); return B2NN_ERR_ARG; }
+    if (d->batch_num < 1 || int64_t(d->batch_num) > m) { set_error("batch_num must be in [1, m]"); return B2NN_ERR_ARG; }
+    if (c->comm) { set_error("train_host: data-parallel streaming is not implemented (use b2nn_train)"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    const int prec = resolve_precision(d->precision);
+    const int n = n_plus_1 - 1, nb = d->batch_num;
+    const int64_t bs = m / nb, last_rows = m - int64_t(nb - 1) * bs;
+    const int64_t steps = int64_t(d->iters) * nb;
+
+    if (!c->copy_stream) B2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        if (!c->st_copied[i]) B2_CUDA(cudaEventCreateWithFlags(&c->st_copied[i], cudaEventDisableTiming));
+        if (!c->st_consumed[i]) B2_CUDA(cudaEventCreateWithFlags(&c->st_consumed[i], cudaEventDisableTiming));
+    }
+    if (last_rows > c->capst) {
+        c->capst = last_rows; c->ldst = round_up(last_rows, 32);
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(c->Xst[i]); cudaFree(c->Yst[i]); c->Xst[i] = c->Yst[i] = nullptr;
+            B2_CUDA(cudaMalloc(&c->Xst[i], sizeof(float) * c->ldst * n_plus_1));
+            B2_CUDA(cudaMalloc(&c->Yst[i], sizeof(float) * c->ldst * k));
+            B2_CUDA(cudaMemsetAsync(c->Xst[i], 0, sizeof(float) * c->ldst * n_plus_1, c->stream));
+            B2_CUDA(cudaMemsetAsync(c->Yst[i], 0, sizeof(float) * c->ldst * k, c->stream));
+            B2_CUDA(fill_launch(c->Xst[i] + int64_t(n) * c->ldst, 1.0f, c->ldst, c->stream));
+        }
+    }
+    if (steps > c->jsteps_cap) {
+        cudaFree(c->d_jsteps); if (c->h_jsteps) cudaFreeHost(c->h_jsteps);
+        c->d_jsteps = nullptr; c->h_jsteps = nullptr;
+        B2_CUDA(cudaMalloc(&c->d_jsteps, sizeof(double) * steps));
+        B2_CUDA(cudaMallocHost(&c->h_jsteps, sizeof(double) * steps));
+        c->jsteps_cap = steps;
+    }
+    rc = ensure_workspace(c, last_rows, d->act_kind == B2NN_ACT_CUSTOM);
+    if (rc) return rc;
+    B2_CUDA(cudaMemsetAsync(c->V, 0, sizeof(float) * c->total_int, c->stream));
+    B2_CUDA(cudaMemsetAsync(c->d_jsteps, 0, sizeof(double) * steps, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));                 // staging buffers initialised before the copy stream touches them
+
+    auto batch_rows = [&](int b) { return b == nb - 1 ? last_rows : bs; };
+    auto issue_copy = [&](int64_t s) -> int {                   // H2D of step s's batch into staging buffer s & 1
+        const int buf = int(s & 1), b = int(s % nb);
+        const int64_t rows = batch_rows(b), start = int64_t(b) * bs;
+        if (s >= 2) B2_CUDA(cudaStreamWaitEvent(c->copy_stream, c->st_consumed[buf], 0));
+        // column f+1 of the reference matrix is feature row f of the engine matrix (its ones column is not copied)
+        B2_CUDA(cudaMemcpy2DAsync(c->Xst[buf], sizeof(float) * c->ldst, x + m + start, sizeof(float) * m, sizeof(float) * rows,
+                                  size_t(n), cudaMemcpyHostToDevice, c->copy_stream));
+        B2_CUDA(cudaMemcpy2DAsync(c->Yst[buf], sizeof(float) * c->ldst, y + start, sizeof(float) * m, sizeof(float) * rows,
+                                  size_t(k), cudaMemcpyHostToDevice, c->copy_stream));
+        B2_CUDA(cudaEventRecord(c->st_copied[buf], c->copy_stream));
+        return B2NN_OK;
+    };
+
+    const int64_t launches0 = c->launches, tc0 = c->tc_launches;
+    cudaEvent_t ev0, ev1;
+    B2_CUDA(cudaEventCreate(&ev0)); B2_CUDA(cudaEventCreate(&ev1));
+    B2_CUDA(cudaEventRecord(ev0, c->stream));
+    rc = issue_copy(0);
+    if (rc) return rc;
+    for (int64_t s = 0; s < steps; ++s) {
+        const int buf = int(s & 1), b = int(s % nb);
+        if (s + 1 < steps) { rc = issue_copy(s + 1); if (rc) return rc; }      // next batch travels while this one computes
+        B2_CUDA(cudaStreamWaitEvent(c->stream, c->st_copied[buf], 0));
+        rc = train_step(c, d, prec, c->Xst[buf], c->ldst, c->ldst, true, c->Yst[buf], c->ldst, 0, batch_rows(b), batch_rows(b),
+                        c->d_jsteps + s);
+        if (rc) return rc;
+        B2_CUDA(cudaEventRecord(c->st_consumed[buf], c->stream));
+        B2_CUDA(cudaMemcpyAsync(c->h_jsteps + s, c->d_jsteps + s, sizeof(double), cudaMemcpyDeviceToHost, c->stream));   // this step's loss
+    }
+    B2_CUDA(cudaEventRecord(ev1, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    B2_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (J_steps)
+        for (int64_t s = 0; s < steps; ++s) {
+            const double rows = double(batch_rows(int(s % nb)));
+            J_steps[s] = float(d->classify ? c->h_jsteps[s] / rows : c->h_jsteps[s] / (2.0 * rows));
+        }
+    auto t_call1 = std::chrono::steady_clock::now();
+    if (result) {
+        std::memset(result, 0, sizeof(*result));
+        result->call_seconds = std::chrono::duration<double>(t_call1 - t_call0).count();
+        result->loop_seconds = double(ms) * 1e-3;
+        result->steps = steps;
+        result->kernel_launches = c->launches - launches0;
+        result->gemm_tc_launches = c->tc_launches - tc0;
     }
     return B2NN_OK;
 }

@@ -131,6 +131,15 @@ int b2nn_train_step_host(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float
                          int64_t global_rows, float* J_out);
 int b2nn_reset_velocity(b2nn_ctx* ctx);
 
+/* Streaming trainer for a HOST-resident training set (it never has to fit on the device): same loop as b2nn_train,
+ * every batch travels host -> device through two staging buffers on a copy stream, so the copy of batch b+1 overlaps
+ * the compute of batch b.  x: m x n_plus_1 (ones column first), y: m x k, column-major HOST buffers (pinned memory
+ * gives the full PCIe rate).  J_steps (optional, iters*batch_num floats): the cost of EVERY step, each read back with
+ * its own asynchronous D2H.  No final cost pass (the data is not resident); velocity is zeroed at entry like
+ * train*Momentum (cublasNN.cpp:533-534). */
+int b2nn_train_host(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x, const float* y, int64_t m, int n_plus_1,
+                    int k, float* J_steps, b2nn_train_result* result);
+
 /* ---- evaluation / inference --------------------------------------------------------------------------------- */
 /* replaces calcFinalCost / validate (cublasNN.cpp:687-881) on caller data.  y_is_labels: y is rows x 1 class ids
  * (validate, cublasNN.cpp:788-790) instead of rows x k one-hot. */

@@ -63,7 +63,7 @@ def test_bikeshare_example_matches_oracle(tmp_path, oracle):
     _write_csv(d / "testPF1_1.csv", with_col1(b["xp"]), "%.9g")
     exe = tmp_path / "bikeshare_example"
     _build(os.path.join(ROOT, "examples", "bikeshare_example.cpp"), str(exe))
-    iters, seed = 300, 42
+    iters, seed = 150, 42       # stops before the trajectory starts to oscillate (around iteration 180 at rate 0.003)
     env = dict(os.environ, B2NN_EXAMPLE_FP32="1")
     r = subprocess.run([str(exe), str(d), str(iters), str(seed)], capture_output=True, text=True, cwd=tmp_path, env=env,
                        timeout=600)
@@ -86,11 +86,8 @@ def test_bikeshare_example_matches_oracle(tmp_path, oracle):
                        theta0=th0, precision="f64")
     assert [i for i, _ in its] == list(ref.log_iter)
     got = np.array([c for _, c in its])
-    np.testing.assert_allclose(got[:5], ref.log_J[:5], rtol=2e-5)       # 6 printed digits
-    # rate 0.003 on targets ~10^2 oscillates (J rises again around iteration 180): fp32 vs fp64 trajectories separate
-    # by ~1 % there; the reference's own fp32 run does the same
-    np.testing.assert_allclose(got, ref.log_J, rtol=2e-2)
-    assert abs(final - ref.final_cost) <= 2e-2 * ref.final_cost
+    np.testing.assert_allclose(got, ref.log_J, rtol=1e-4)               # the class prints 6 significant digits
+    assert abs(final - ref.final_cost) <= 1e-3 * ref.final_cost
     assert val > 0
 
 

@@ -191,6 +191,26 @@ def test_train_step_host_equals_resident_training(b2nn):
     net.close(); net2.close()
 
 
+@pytest.mark.parametrize("name", ["clf_tanh_softmax", "reg_tanh_ragged", "wide_mini"])
+def test_streaming_host_trainer_equals_resident_training(b2nn, name):
+    """b2nn_train_host (data stays on the host, double-buffered H2D) must walk the same trajectory as b2nn_train and
+    report the cost of every step."""
+    import ctypes
+    c = cases.case_by_name(name)
+    x_cm, y_cm = cases.oracle_inputs(c)
+    net, th0, th, out = _engine(b2nn, c, "fp32", skip_final_cost=True, display=1)
+    net2 = b2nn.Net()
+    net2.set_layers(c.layers, c.init_kind, c.seed)
+    d = _desc(b2nn, c, "fp32", display=1)
+    J, r = net2.train_host(d, ctypes.c_void_p(x_cm.ctypes.data), ctypes.c_void_p(y_cm.ctypes.data), c.m)
+    th2 = net2.get_weights()
+    assert r.steps == c.iters * c.batch_num and J.shape == (r.steps,)
+    assert np.abs(th2 - th).max() <= 2e-6 * np.abs(th).max()
+    np.testing.assert_allclose(J[::c.batch_num], out.log_J, rtol=1e-5)       # batch 0 of every epoch = the printed cost
+    assert np.all(np.isfinite(J)) and J[-1] < J[0]
+    net.close(); net2.close()
+
+
 def _torch_step_fp64(layers, W, X, Y, rate, hidden):
     """fp64 restatement of one classify step (softmax / cross-entropy, mu = 0) on the GPU: returns new weights.
     W[j]: (l_j+1, l_{j+1}) reference layout (bias row 0); X: (B, l_0); Y: (B, K) one-hot."""
