@@ -176,7 +176,7 @@ def run_ours(args):
     if args.batch:
         B = args.batch
     K, W = args.steps, max(args.warmup, 3)
-    prec = b2nn.PREC_TF32 if args.precision == "tf32" else b2nn.PREC_FP32
+    prec = {"tf32": b2nn.PREC_TF32, "fp32": b2nn.PREC_FP32, "tf32x3": b2nn.PREC_TF32X3}[args.precision]
 
     net = b2nn.Net(local)
     net.set_layers(layers, b2nn.INIT_2, 42)
@@ -240,12 +240,15 @@ def run_ours(args):
         # MEASURED_PEAKS.json holds dense bf16; kind::tf32 runs at half the bf16 rate on the same tensor pipe.
         peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0)) / 2.0
         peak_note = f"0.5 x bf16_tflops_sustained ({pk_src}): tf32 is half-rate on the tcgen05 pipe"
+    elif args.precision == "tf32x3":
+        peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0)) / 6.0
+        peak_note = f"bf16_tflops_sustained / 6 ({pk_src}): three tf32 MMAs per algorithmic multiply-add"
     else:
         peak = 75.0
         peak_note = "fp32 FFMA planning value (BASELINE.md); not measured"
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::tf32) x3 contractions" if args.precision == "tf32" else "gemm_simt_kernel",
+        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::tf32) x3 contractions" if args.precision != "fp32" else "gemm_simt_kernel",
         "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
         "traffic": None, "peak_source": peak_note,
         "launches": gemm_launches, "avg_launch_ms": round(gemm_ms / max(gemm_launches, 1), 4),
@@ -407,7 +410,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "tf32x3"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -147,6 +147,26 @@ __global__ void split_batches_kernel(const float* __restrict__ src, int64_t ld_s
     dst[f * ld_dst + b * bs_pad + r] = src[f * ld_src + i];
 }
 
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+__global__ void __launch_bounds__(256) split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, int64_t count) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) lo[i] = tf32_lo(x[i]);
+}
+
+__global__ void __launch_bounds__(256) momentum_update_lo_kernel(float* __restrict__ theta, float* __restrict__ vel,
+                                                                 const float* __restrict__ grad, float* __restrict__ theta_lo,
+                                                                 int64_t count, float mu, float alpha) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const float v = fmaf(mu, vel[i], alpha * grad[i]);
+        const float t = theta[i] + v;
+        vel[i] = v;
+        theta[i] = t;
+        theta_lo[i] = tf32_lo(t);
+    }
+}
+
 __global__ void fill_kernel(float* p, float v, int64_t count) {
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) p[i] = v;
@@ -224,6 +244,19 @@ cudaError_t split_batches_launch(const float* src, int64_t ld_src, float* dst, i
     if (rows <= 0 || n_rows <= 0) return cudaSuccess;
     dim3 grid(blocks_for(rows, 256), unsigned(n_rows));
     split_batches_kernel<<<grid, 256, 0, s>>>(src, ld_src, dst, ld_dst, rows, bs, bs_pad, nb);
+    return cudaGetLastError();
+}
+cudaError_t split_lo_launch(const float* x, float* lo, int64_t count, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    const int64_t want = (count + 255) / 256;
+    split_lo_kernel<<<unsigned(want < 148 * 8 ? want : 148 * 8), 256, 0, s>>>(x, lo, count);
+    return cudaGetLastError();
+}
+cudaError_t momentum_update_lo_launch(float* theta, float* vel, const float* grad, float* theta_lo, int64_t count, float mu,
+                                      float alpha, cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    const int64_t want = (count + 255) / 256;
+    momentum_update_lo_kernel<<<unsigned(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(theta, vel, grad, theta_lo, count, mu, alpha);
     return cudaGetLastError();
 }
 cudaError_t fill_launch(float* p, float v, int64_t count, cudaStream_t s) {

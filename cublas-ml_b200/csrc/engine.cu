@@ -70,10 +70,14 @@ struct Workspace {
     std::vector<float*> z;       // only for custom activations (L-2 buffers)
     float* z_last = nullptr;     // K rows
     float* scratch = nullptr;    // custom path: act'(z) / product
+    std::vector<float*> a_lo, delta_lo;   // fp32-grade tensor-core mode: x - trunc_tf32(x) of a / delta (same shapes)
     void release() {
         for (float* p : a) cudaFree(p);
         for (float* p : delta) cudaFree(p);
         for (float* p : z) cudaFree(p);
+        for (float* p : a_lo) cudaFree(p);
+        for (float* p : delta_lo) cudaFree(p);
+        a_lo.clear(); delta_lo.clear();
         cudaFree(z_last); cudaFree(scratch);
         a.clear(); delta.clear(); z.clear(); z_last = nullptr; scratch = nullptr; cap = ld = 0;
     }
@@ -129,6 +133,8 @@ struct b2nn_ctx {
     std::vector<LayerInfo> L;
     int64_t total_ref = 0, total_int = 0;
     float *W = nullptr, *V = nullptr, *G = nullptr;
+    float* W_lo = nullptr; bool w_lo_valid = false;      // low parts of the weights (fp32-grade tensor-core mode)
+    std::map<const float*, std::pair<float*, int64_t>> lo_cache;   // low-part companions of input matrices, by base pointer
 
     // training set, engine layout
     float* X = nullptr; int64_t ldx = 0;
@@ -198,10 +204,44 @@ int check_device(int device, std::string& why) {
 }
 
 int resolve_precision(int prec) {
-    if (prec == B2NN_PREC_FP32 || prec == B2NN_PREC_TF32) return prec;
+    if (prec == B2NN_PREC_FP32 || prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3) return prec;
     const char* e = std::getenv("B2NN_PRECISION");
     if (e && (std::strcmp(e, "fp32") == 0 || std::strcmp(e, "FP32") == 0)) return B2NN_PREC_FP32;
+    if (e && (std::strcmp(e, "tf32x3") == 0 || std::strcmp(e, "TF32X3") == 0)) return B2NN_PREC_TF32X3;
     return B2NN_PREC_TF32;
+}
+
+// Low-part companion buffer of an input matrix (allocated on demand, content refreshed by the caller with split_lo).
+float* lo_buffer(b2nn_ctx* c, const float* x, int64_t count) {
+    auto it = c->lo_cache.find(x);
+    if (it != c->lo_cache.end() && it->second.second >= count) return it->second.first;
+    if (it != c->lo_cache.end()) { cudaFree(it->second.first); c->lo_cache.erase(it); }
+    float* lo = nullptr;
+    if (cudaMalloc(&lo, sizeof(float) * size_t(count)) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    c->lo_cache[x] = std::make_pair(lo, count);
+    c->plans.clear();            // plans embed tensor maps over the low-part buffers
+    return lo;
+}
+void drop_lo(b2nn_ctx* c, const float* x) {
+    auto it = c->lo_cache.find(x);
+    if (it != c->lo_cache.end()) { cudaFree(it->second.first); c->lo_cache.erase(it); c->plans.clear(); }
+}
+const float* find_lo(const b2nn_ctx* c, const float* x) {
+    auto it = c->lo_cache.find(x);
+    return it == c->lo_cache.end() ? nullptr : it->second.first;
+}
+
+int ensure_w_lo(b2nn_ctx* c) {
+    if (!c->W_lo) {
+        B2_CUDA(cudaMalloc(&c->W_lo, sizeof(float) * (c->total_int + 64)));
+        B2_CUDA(cudaMemsetAsync(c->W_lo, 0, sizeof(float) * (c->total_int + 64), c->stream));
+        c->w_lo_valid = false;
+    }
+    if (!c->w_lo_valid) {
+        B2_CUDA(split_lo_launch(c->W, c->W_lo, c->total_int, c->stream));
+        c->w_lo_valid = true;
+    }
+    return B2NN_OK;
 }
 
 int epi_forward(int act_kind) { return act_kind == B2NN_ACT_SIGMOID ? EPI_SIGMOID : act_kind == B2NN_ACT_TANH ? EPI_TANH : EPI_STORE; }
@@ -218,11 +258,12 @@ int ensure_acc(b2nn_ctx* c, int slots) {
     return B2NN_OK;
 }
 
-int ensure_workspace(b2nn_ctx* c, int64_t rows, bool custom) {
+int ensure_workspace(b2nn_ctx* c, int64_t rows, bool custom, bool want_lo = false) {
     Workspace& w = c->ws;
     const int nl = int(c->layers.size());
     const bool need_z = custom && w.z.empty();
-    if (rows <= w.cap && !need_z) return B2NN_OK;
+    const bool need_lo = want_lo && w.a_lo.empty();
+    if (rows <= w.cap && !need_z && !need_lo) return B2NN_OK;
     if (rows > w.cap) {
         w.release();
         c->plans.clear();
@@ -252,6 +293,34 @@ int ensure_workspace(b2nn_ctx* c, int64_t rows, bool custom) {
         }
         B2_CUDA(cudaMalloc(&w.scratch, sizeof(float) * zmax));
     }
+    if (want_lo && w.a_lo.empty()) {
+        c->plans.clear();
+        w.a_lo.assign(nl - 2, nullptr);
+        w.delta_lo.assign(nl - 1, nullptr);
+        for (int j = 0; j < nl - 2; ++j) {
+            const size_t bytes = sizeof(float) * size_t(c->layers[j + 1] + 1) * w.ld;       // low part of the ones row is 0
+            B2_CUDA(cudaMalloc(&w.a_lo[j], bytes));
+            B2_CUDA(cudaMemsetAsync(w.a_lo[j], 0, bytes, c->stream));
+        }
+        for (int j = 0; j < nl - 1; ++j) {
+            const size_t bytes = sizeof(float) * size_t(c->layers[j + 1]) * w.ld;
+            B2_CUDA(cudaMalloc(&w.delta_lo[j], bytes));
+            B2_CUDA(cudaMemsetAsync(w.delta_lo[j], 0, bytes, c->stream));
+        }
+    }
+    return B2NN_OK;
+}
+
+// Everything the fp32-grade tensor-core mode needs around one input matrix X (count floats): workspace low parts,
+// weight low parts, and X's own low part, freshly split.
+int prepare_x3(b2nn_ctx* c, const float* X, int64_t count, int64_t rows, bool custom) {
+    int rc = ensure_workspace(c, std::max<int64_t>(rows, c->ws.cap), custom, true);
+    if (rc) return rc;
+    rc = ensure_w_lo(c);
+    if (rc) return rc;
+    float* lo = lo_buffer(c, X, count);
+    if (!lo) { set_error("cudaMalloc Failed"); return B2NN_ERR_ALLOC; }
+    B2_CUDA(split_lo_launch(X, lo, count, c->stream));
     return B2NN_OK;
 }
 
@@ -263,8 +332,9 @@ void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
     if (allow_split) {
         // Weight gradient: K = batch rows is long while M x N can be a handful of tiles (50 x 785, 10 x 4097).  Split K so
         // the grid covers the 148 SMs; partial sums meet in a zeroed gradient block via red.global.add.f32.
-        const int tile_m = (prec == B2NN_PREC_TF32) ? 128 : 64;
-        const int tile_n = (prec == B2NN_PREC_TF32) ? (g.N > 128 ? 256 : g.N > 64 ? 128 : g.N > 32 ? 64 : g.N > 16 ? 32 : 16) : 64;
+        const bool tc_mode = prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3;
+        const int tile_m = tc_mode ? 128 : 64;
+        const int tile_n = tc_mode ? (g.N > 128 ? 256 : g.N > 64 ? 128 : g.N > 32 ? 64 : g.N > 16 ? 32 : 16) : 64;
         const int64_t tiles = int64_t((g.M + tile_m - 1) / tile_m) * ((g.N + tile_n - 1) / tile_n);
         const int kblk = (g.K + 31) / 32;
         if (tiles < 74 && kblk >= 16) {
@@ -274,7 +344,7 @@ void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
     }
     // tcgen05 only where tensor cores pay: below ~2^26 multiply-adds a contraction is launch / HBM bound and stays on
     // the exact fp32 FFMA kernel (the bikeshare-sized nets of config C2 never leave fp32).
-    if (prec == B2NN_PREC_TF32 && work >= double(1 << 26) && g.M >= 32) {
+    if ((prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3) && work >= double(1 << 26) && g.M >= 32) {
         std::string err;
         if (tc_plan_build(op.plan, g, err)) op.tc = true;
     }
@@ -309,6 +379,8 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
     const int nw = nl - 1;
     Workspace& w = c->ws;
     const bool custom = act_kind == B2NN_ACT_CUSTOM;
+    const bool x3 = prec == B2NN_PREC_TF32X3 && !custom && !w.a_lo.empty() && c->W_lo != nullptr;
+    const float* X_lo = x3 ? find_lo(c, X) : nullptr;
     sp.fwd.resize(nw); sp.wgrad.resize(nw); sp.bwd.resize(nw);
     {
         const LayerInfo& last = c->L[nw - 1];
@@ -332,6 +404,12 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         } else {
             f.g.D = w.z_last; f.g.ldd = w.ld; f.g.epi = EPI_STORE;
         }
+        if (x3) {
+            f.g.A_lo = (j == 0) ? X_lo : w.a_lo[j - 1];
+            f.g.B_lo = c->W_lo + li.w_off;
+            f.g.D_lo = (j < nw - 1) ? w.a_lo[j] : nullptr;
+            if (!f.g.A_lo) { f.g.B_lo = nullptr; f.g.D_lo = nullptr; }
+        }
         if (!tail_layer) bind_backend(c, f, prec, false);
 
         // weight gradient  G_j = delta_j^T [a_{j-1}, 1]  in W_j's layout   (cublasNN.cpp:680-684)
@@ -345,6 +423,11 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         g.g.D = c->G + li.w_off; g.g.ldd = li.ldw;
         g.g.M = li.in + 1; g.g.N = li.out; g.g.K = int(rows);
         g.g.epi = EPI_STORE;
+        if (x3) {
+            g.g.A_lo = (j == 0) ? X_lo : w.a_lo[j - 1];
+            g.g.B_lo = w.delta_lo[j];
+            if (!g.g.A_lo) g.g.B_lo = nullptr;
+        }
         if (!(tail_layer && sp.tail_inline_g)) bind_backend(c, g, prec, true);
 
         // delta backprop  delta_{j-1} = (delta_j W_j)[:, no bias] .* f'(z_{j-1})   (cublasNN.cpp:673-676)
@@ -357,6 +440,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
             b.g.M = int(rows); b.g.N = li.in; b.g.K = li.out;
             if (custom) { b.g.D = w.scratch; b.g.ldd = w.ld; b.g.epi = EPI_STORE; }
             else { b.g.D = w.delta[j - 1]; b.g.ldd = w.ld; b.g.epi = epi_backward(act_kind); b.g.aux = w.a[j - 1]; b.g.ldaux = w.ld; }
+            if (x3 && !custom) { b.g.A_lo = w.delta_lo[j]; b.g.B_lo = c->W_lo + li.w_off; b.g.D_lo = w.delta_lo[j - 1]; }
             if (!tail_layer) bind_backend(c, b, prec, false);
         }
     }
@@ -397,6 +481,8 @@ int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind) {
         GemmDesc g = op.g;
         if (op.a_is_x) { if (g.a_major) g.a_mn0 += x_start; else g.a_k0 += x_start; }
         B2_CUDA(gemm_simt_launch(g, c->stream));
+        // fp32-grade mode: a later tensor-core contraction may consume this output, so it needs its low part too
+        if (g.D_lo) B2_CUDA(split_lo_launch(g.D, g.D_lo, int64_t(g.N) * g.ldd, c->stream));
     }
     ++c->launches;
     return B2NN_OK;
@@ -517,6 +603,12 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
     if (sp.use_tail) rc = run_tail(c, sp, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
     else rc = output_and_delta(c, d, Y + x_start, ldy, rows, cost_slot);
     if (rc) return rc;
+    if (prec == B2NN_PREC_TF32X3 && !c->ws.delta_lo.empty()) {
+        const int nwl = int(c->L.size());
+        B2_CUDA(split_lo_launch(c->ws.delta[nwl - 1], c->ws.delta_lo[nwl - 1], int64_t(c->L[nwl - 1].out) * c->ws.ld, c->stream));
+        if (sp.use_tail)
+            B2_CUDA(split_lo_launch(c->ws.delta[nwl - 2], c->ws.delta_lo[nwl - 2], int64_t(c->L[nwl - 1].in) * c->ws.ld, c->stream));
+    }
     rc = backward_pass(c, sp, x_start, d);
     if (rc) return rc;
     const float alpha = -d->rate / float(global_rows);      // cublasNN.cpp:544, 601
@@ -536,8 +628,12 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
             B2_CUDA(cudaStreamWaitEvent(c->stream, c->grad_reduced[j], 0));
             {
                 ProfScope scope(c, 4, false, 0.0, 20.0 * double(li.ldw) * li.out);
-                B2_CUDA(momentum_update_launch(c->W + li.w_off, c->V + li.w_off, c->G + li.w_off, li.ldw * li.out,
-                                               d->momentum, alpha, c->stream));
+                if (prec == B2NN_PREC_TF32X3 && c->W_lo)
+                    B2_CUDA(momentum_update_lo_launch(c->W + li.w_off, c->V + li.w_off, c->G + li.w_off, c->W_lo + li.w_off,
+                                                      li.ldw * li.out, d->momentum, alpha, c->stream));
+                else
+                    B2_CUDA(momentum_update_launch(c->W + li.w_off, c->V + li.w_off, c->G + li.w_off, li.ldw * li.out,
+                                                   d->momentum, alpha, c->stream));
             }
             ++c->launches;
         }
@@ -545,7 +641,10 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
         // all layers in one pass: W, V, G share one arena layout (cublasNN.cpp:558-566 is 2 launches per layer)
         {
             ProfScope scope(c, 4, false, 0.0, 20.0 * double(c->total_int));
-            B2_CUDA(momentum_update_launch(c->W, c->V, c->G, c->total_int, d->momentum, alpha, c->stream));
+            if (prec == B2NN_PREC_TF32X3 && c->W_lo)
+                B2_CUDA(momentum_update_lo_launch(c->W, c->V, c->G, c->W_lo, c->total_int, d->momentum, alpha, c->stream));
+            else
+                B2_CUDA(momentum_update_launch(c->W, c->V, c->G, c->total_int, d->momentum, alpha, c->stream));
         }
         ++c->launches;
     }
@@ -564,6 +663,10 @@ int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float
     const int64_t chunk_cap = std::max<int64_t>(c->ws.cap, std::min<int64_t>(rows, 1 << 16));
     rc = ensure_workspace(c, chunk_cap, d->act_kind == B2NN_ACT_CUSTOM);
     if (rc) return rc;
+    if (prec == B2NN_PREC_TF32X3 && d->act_kind != B2NN_ACT_CUSTOM) {
+        rc = prepare_x3(c, X, ldx * int64_t(c->layers[0] + 1), c->ws.cap, false);
+        if (rc) return rc;
+    }
     // chunk starts stay on 32-sample boundaries so the forward contractions keep their one-box TMA loads
     const int64_t chunk = rows <= c->ws.cap ? c->ws.cap : std::max<int64_t>(32, c->ws.cap / 32 * 32);
     const int out_kind = d->classify ? d->out_kind : B2NN_OUT_LINEAR;
@@ -664,7 +767,8 @@ void b2nn_destroy(b2nn_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     c->ws.release();
-    cudaFree(c->W); cudaFree(c->V); cudaFree(c->G);
+    cudaFree(c->W); cudaFree(c->V); cudaFree(c->G); cudaFree(c->W_lo);
+    for (auto& kv : c->lo_cache) cudaFree(kv.second.first);
     cudaFree(c->X); cudaFree(c->Y); cudaFree(c->Xs); cudaFree(c->Ys); cudaFree(c->Xsp); cudaFree(c->Ysp);
     cudaFree(c->d_acc);
     for (int i = 0; i < 2; ++i) {
@@ -708,8 +812,8 @@ int b2nn_set_layers(b2nn_ctx* c, const int* layers, int n_layers, int init_kind,
         c->total_ref += li.ref_size;
         c->total_int += li.ldw * li.out;      // multiple of 4 floats: every layer block starts 16-byte aligned
     }
-    cudaFree(c->W); cudaFree(c->V); cudaFree(c->G);
-    c->W = c->V = c->G = nullptr;
+    cudaFree(c->W); cudaFree(c->V); cudaFree(c->G); cudaFree(c->W_lo);
+    c->W = c->V = c->G = c->W_lo = nullptr; c->w_lo_valid = false;
     c->plans.clear(); c->ws.release();
     // + 64 floats: the folded 3-D TMA view of the last weight rows may read one 32-float atom past the arena's end
     if (cudaMalloc(&c->W, sizeof(float) * (c->total_int + 64)) != cudaSuccess ||
@@ -774,6 +878,7 @@ int b2nn_set_weights(b2nn_ctx* c, const float* host, int64_t count) {
     B2_CUDA(cudaMemcpyAsync(ref, host, sizeof(float) * c->total_ref, cudaMemcpyHostToDevice, c->stream));
     for (const LayerInfo& li : c->L)
         B2_CUDA(theta_ref_to_internal_launch(ref + li.ref_off, c->W + li.w_off, li.in, li.out, li.ldw, c->stream));
+    c->w_lo_valid = false;
     B2_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(ref);
     return B2NN_OK;
@@ -784,6 +889,7 @@ int b2nn_set_train_data(b2nn_ctx* c, const float* x, const float* y, int64_t m, 
     if (c->layers.empty()) { set_error("set_layers must precede set_train_data (main.cpp:125)"); return B2NN_ERR_ARG; }
     if (n_plus_1 != c->layers[0] + 1 || k != c->layers.back()) { set_error("data shape does not match the layers"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
+    drop_lo(c, c->X); drop_lo(c, c->Xsp);
     cudaFree(c->X); cudaFree(c->Y); c->X = c->Y = nullptr;
     cudaFree(c->Xsp); cudaFree(c->Ysp); c->Xsp = c->Ysp = nullptr; c->sp_nb = 0;
     c->plans.clear();
@@ -857,10 +963,11 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
     const float* Xtrain = c->X; const float* Ytrain = c->Y;
     int64_t ld_train = c->ldx, x_total = c->m, b_stride = bs;
     bool x_aligned = (nb == 1) || (bs % 32 == 0);
-    if (!x_aligned && bs >= 64 && prec == B2NN_PREC_TF32) {
+    if (!x_aligned && bs >= 64 && prec != B2NN_PREC_FP32) {
         const int64_t bs_pad = round_up(bs, 32);
         const int64_t ldsp = int64_t(nb - 1) * bs_pad + round_up(last_rows, 32);
         if (!c->Xsp || c->sp_nb != nb || c->ldsp != ldsp) {
+            drop_lo(c, c->Xsp);
             cudaFree(c->Xsp); cudaFree(c->Ysp); c->Xsp = c->Ysp = nullptr;
             B2_CUDA(cudaMalloc(&c->Xsp, sizeof(float) * ldsp * (c->n + 1)));
             B2_CUDA(cudaMalloc(&c->Ysp, sizeof(float) * ldsp * c->K));
@@ -871,6 +978,13 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
         B2_CUDA(split_batches_launch(c->X, c->ldx, c->Xsp, ldsp, c->m, bs, bs_pad, nb, c->n + 1, c->stream));
         B2_CUDA(split_batches_launch(c->Y, c->ldy, c->Ysp, ldsp, c->m, bs, bs_pad, nb, c->K, c->stream));
         Xtrain = c->Xsp; Ytrain = c->Ysp; ld_train = ldsp; x_total = ldsp; b_stride = bs_pad; x_aligned = true;
+    }
+
+    if (prec == B2NN_PREC_TF32X3 && d->act_kind != B2NN_ACT_CUSTOM) {
+        rc = prepare_x3(c, Xtrain, ld_train * int64_t(c->n + 1), last_rows, false);
+        if (rc) return rc;
+    } else {
+        c->w_lo_valid = false;       // the weights are about to change without their low parts being refreshed
     }
 
     const int64_t launches0 = c->launches, tc0 = c->tc_launches;
@@ -1033,6 +1147,12 @@ int b2nn_train_step_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, 
     if (rc) return rc;
     B2_CUDA(cudaMemcpy2DAsync(c->Ys, sizeof(float) * c->lds, y, sizeof(float) * rows, sizeof(float) * rows, size_t(K),
                               cudaMemcpyHostToDevice, c->stream));
+    if (prec == B2NN_PREC_TF32X3 && d->act_kind != B2NN_ACT_CUSTOM) {
+        rc = prepare_x3(c, c->Xs, c->lds * int64_t(n + 1), rows, false);
+        if (rc) return rc;
+    } else {
+        c->w_lo_valid = false;
+    }
     double* slot = J_out ? c->d_acc + 2 : nullptr;
     if (slot) B2_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), c->stream));
     const int64_t g = global_rows > 0 ? global_rows : rows;
@@ -1091,6 +1211,12 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
     }
     rc = ensure_workspace(c, last_rows, d->act_kind == B2NN_ACT_CUSTOM);
     if (rc) return rc;
+    const bool x3 = prec == B2NN_PREC_TF32X3 && d->act_kind != B2NN_ACT_CUSTOM;
+    if (x3) {
+        for (int i = 0; i < 2; ++i) { rc = prepare_x3(c, c->Xst[i], c->ldst * int64_t(n_plus_1), last_rows, false); if (rc) return rc; }
+    } else {
+        c->w_lo_valid = false;
+    }
     B2_CUDA(cudaMemsetAsync(c->V, 0, sizeof(float) * c->total_int, c->stream));
     B2_CUDA(cudaMemsetAsync(c->d_jsteps, 0, sizeof(double) * steps, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));                 // staging buffers initialised before the copy stream touches them
@@ -1119,6 +1245,7 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
         const int buf = int(s & 1), b = int(s % nb);
         if (s + 1 < steps) { rc = issue_copy(s + 1); if (rc) return rc; }      // next batch travels while this one computes
         B2_CUDA(cudaStreamWaitEvent(c->stream, c->st_copied[buf], 0));
+        if (x3) B2_CUDA(split_lo_launch(c->Xst[buf], lo_buffer(c, c->Xst[buf], c->ldst * int64_t(n_plus_1)), c->ldst * int64_t(n_plus_1), c->stream));
         rc = train_step(c, d, prec, c->Xst[buf], c->ldst, c->ldst, true, c->Yst[buf], c->ldst, 0, batch_rows(b), batch_rows(b),
                         c->d_jsteps + s);
         if (rc) return rc;
@@ -1175,6 +1302,7 @@ int b2nn_evaluate(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const f
     if (!rc) rc = evaluate_device(c, d, prec, xd, ld, yd, ld, lab, rows, nullptr, nullptr, 0, cost_out, errors_out);
     cudaStreamSynchronize(c->stream);
     c->plans.clear();      // plans reference xd
+    drop_lo(c, xd);
     cudaFree(xd); cudaFree(yd); cudaFree(lab);
     return rc;
 }
@@ -1206,6 +1334,7 @@ int b2nn_predict(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, int64_t 
     }
     cudaStreamSynchronize(c->stream);
     c->plans.clear();
+    drop_lo(c, xd);
     cudaFree(xd); cudaFree(pd); cudaFree(hd);
     return rc;
 }
@@ -1228,12 +1357,24 @@ int b2nn_gemm(b2nn_ctx* c, int backend, const float* A, int64_t lda, int a_major
     GemmDesc g;
     g.A = A; g.lda = lda; g.a_major = a_major; g.B = B; g.ldb = ldb; g.b_major = b_major;
     g.D = D; g.ldd = ldd; g.M = M; g.N = N; g.K = K; g.epi = epi; g.aux = aux; g.ldaux = ldaux;
-    if (backend == 1 || backend == 3) {
-        g.mn_slack = backend == 3;
+    if (backend == 1 || backend == 3 || backend == 5 || backend == 7) {
+        g.mn_slack = (backend & 2) != 0;
+        float *alo = nullptr, *blo = nullptr;
+        if (backend & 4) {          // fp32-grade mode: split the operands into temporaries first
+            const int64_t na = (a_major ? int64_t(K) : int64_t(M)) * lda + (g.mn_slack ? 32 : 0);
+            const int64_t nbb = (b_major ? int64_t(K) : int64_t(N)) * ldb + (g.mn_slack ? 32 : 0);
+            B2_CUDA(cudaMalloc(&alo, sizeof(float) * na));
+            B2_CUDA(cudaMalloc(&blo, sizeof(float) * nbb));
+            B2_CUDA(split_lo_launch(A, alo, na, c->stream));
+            B2_CUDA(split_lo_launch(B, blo, nbb, c->stream));
+            g.A_lo = alo; g.B_lo = blo;
+        }
         TcPlan plan;
         std::string err;
-        if (!tc_plan_build(plan, g, err)) { set_error("tcgen05 plan: " + err); return B2NN_ERR_ARG; }
-        B2_CUDA(tc_plan_launch(plan, c->stream));
+        if (!tc_plan_build(plan, g, err)) { cudaFree(alo); cudaFree(blo); set_error("tcgen05 plan: " + err); return B2NN_ERR_ARG; }
+        cudaError_t le = tc_plan_launch(plan, c->stream);
+        if (backend & 4) { cudaStreamSynchronize(c->stream); cudaFree(alo); cudaFree(blo); }
+        B2_CUDA(le);
         ++c->tc_launches;
     } else {
         B2_CUDA(gemm_simt_launch(g, c->stream));

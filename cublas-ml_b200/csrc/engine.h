@@ -35,6 +35,9 @@ struct GemmDesc {
     // The caller guarantees that reading up to 31 floats past the M/N extent of an MN-major operand (in every k row,
     // including the last) stays inside its allocation, which the one-box-per-tile 3-D TMA view relies on.
     bool mn_slack = false;
+    // fp32-grade tensor-core mode (3xTF32): low parts x - trunc_tf32(x) of both operands, same layout and leading
+    // dimension as A / B; D_lo (optional) receives the low part of the output.  Null = plain tf32.
+    const float* A_lo = nullptr; const float* B_lo = nullptr; float* D_lo = nullptr;
 };
 
 // fp32 FFMA backend (gemm_simt.cu)
@@ -44,6 +47,9 @@ cudaError_t gemm_simt_launch(const GemmDesc& g, cudaStream_t stream);
 struct TcPlan {
     alignas(64) CUtensorMap map_a;
     alignas(64) CUtensorMap map_b;
+    alignas(64) CUtensorMap map_a_lo;
+    alignas(64) CUtensorMap map_b_lo;
+    bool x3 = false;
     GemmDesc g;
     int block_n = 0;          // tile N: 16, 32, 64, 128 or 256
     int stages = 0;
@@ -84,6 +90,11 @@ cudaError_t theta_internal_to_ref_launch(const float* w, float* ref, int in, int
 cudaError_t stage_x_launch(const float* x_ref, int64_t ld_ref, float* x_int, int64_t ld_int, int64_t rows, int n,
                            cudaStream_t s);
 cudaError_t fill_launch(float* p, float v, int64_t count, cudaStream_t s);
+// lo[i] = x[i] - trunc_tf32(x[i])  (exact; what tcgen05 kind::tf32 drops from x)
+cudaError_t split_lo_launch(const float* x, float* lo, int64_t count, cudaStream_t s);
+// momentum update that also refreshes the low parts of the weights
+cudaError_t momentum_update_lo_launch(float* theta, float* vel, const float* grad, float* theta_lo, int64_t count, float mu,
+                                      float alpha, cudaStream_t stream);
 // dst[f][b*bs_pad + r] = src[f][b*bs + r] for the nb contiguous batches of allocVarGPU's table (last absorbs the rest)
 cudaError_t split_batches_launch(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t rows, int64_t bs,
                                  int64_t bs_pad, int nb, int n_rows, cudaStream_t s);

@@ -50,6 +50,7 @@ __host__ __device__ constexpr int b_tile_bytes(int rows, bool b_mn) {
 
 struct TcArgs {
     float* D; int64_t ldd;
+    float* D_lo;                    // X3 only: x - trunc_tf32(x) of every stored output (may be null)
     const float* aux; int64_t ldaux;
     int M, N;
     int tiles_m, tiles_n, splits;   // work item = (tile_m, tile_n, split); tile_m counts (128 * NCTA)-row tiles
@@ -75,12 +76,19 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f,
 //   warp 1      TMEM allocator; in the leader CTA also the MMA issuer (one lane)
 //   warps 2..9  epilogue: TMEM -> registers -> fused activation / derivative -> coalesced global stores.  Two
 //               accumulator buffers in TMEM (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
-template <int BN, bool A_MN, bool B_MN, int NCTA>
+//
+// X3 = true is the fp32-grade mode ("3xTF32"): tcgen05 TRUNCATES fp32 inputs to tf32 (measured, tools/
+// probe_tf32_rounding.py), so an fp32 array already is its own high part hi = x & 0xFFFFE000; the producers additionally
+// keep lo = x - hi (exact).  Each K step then issues A*B + A*B_lo + A_lo*B into the same fp32 accumulator; the dropped
+// lo*lo term is 2^-22 relative.  Four tiles per stage instead of two.
+template <int BN, bool A_MN, bool B_MN, int NCTA, bool X3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcArgs p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo, const TcArgs p) {
     constexpr int B_ROWS = BN / NCTA;                       // N rows of B this CTA stages
     constexpr int B_TILE = b_tile_bytes(B_ROWS, B_MN);
-    constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE;      // per CTA
+    constexpr int HALF_STAGE = A_TILE_BYTES + B_TILE;       // one (A, B) tile pair
+    constexpr int STAGE_BYTES = X3 ? 2 * HALF_STAGE : HALF_STAGE;      // per CTA
     constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;        // TMEM columns of one accumulator buffer
     constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;            // 64 .. 512, always a power of two
     constexpr uint32_t IDESC = umma_idesc_tf32(BM * NCTA, BN, A_MN, B_MN);
@@ -106,6 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
+        if (X3) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
         for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], NCTA); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS * NCTA); }
         mbar_fence_init();
@@ -141,36 +150,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     uint64_t* bar = &full_bar[s];
                     const int kc = (kb0 + kb) * BK;
                     if (NCTA == 1) mbar_expect_tx(bar, STAGE_BYTES);
-                    if (A_MN) {
-                        if (p.a_3d) {
-                            if (NCTA == 2) tma_load_3d_pair(sa, &map_a, bar, 0, p.a_k0 + kc, (p.a_mn0 + m0) >> 5);
-                            else tma_load_3d(sa, &map_a, bar, 0, p.a_k0 + kc, (p.a_mn0 + m0) >> 5);
-                        } else {
+                    auto load_pair = [&](uint8_t* ta, uint8_t* tb, const CUtensorMap* ma, const CUtensorMap* mb) {
+                        if (A_MN) {
+                            if (p.a_3d) {
+                                if (NCTA == 2) tma_load_3d_pair(ta, ma, bar, 0, p.a_k0 + kc, (p.a_mn0 + m0) >> 5);
+                                else tma_load_3d(ta, ma, bar, 0, p.a_k0 + kc, (p.a_mn0 + m0) >> 5);
+                            } else {
 #pragma unroll
-                            for (int i = 0; i < BM / 32; ++i) {
-                                if (NCTA == 2) tma_load_2d_pair(sa + i * ATOM_BYTES, &map_a, bar, p.a_mn0 + m0 + i * 32, p.a_k0 + kc);
-                                else tma_load_2d(sa + i * ATOM_BYTES, &map_a, bar, p.a_mn0 + m0 + i * 32, p.a_k0 + kc);
+                                for (int i = 0; i < BM / 32; ++i) {
+                                    if (NCTA == 2) tma_load_2d_pair(ta + i * ATOM_BYTES, ma, bar, p.a_mn0 + m0 + i * 32, p.a_k0 + kc);
+                                    else tma_load_2d(ta + i * ATOM_BYTES, ma, bar, p.a_mn0 + m0 + i * 32, p.a_k0 + kc);
+                                }
                             }
-                        }
-                    } else {
-                        if (NCTA == 2) tma_load_2d_pair(sa, &map_a, bar, p.a_k0 + kc, p.a_mn0 + m0);
-                        else tma_load_2d(sa, &map_a, bar, p.a_k0 + kc, p.a_mn0 + m0);
-                    }
-                    if (B_MN) {
-                        if (p.b_3d) {
-                            if (NCTA == 2) tma_load_3d_pair(sb, &map_b, bar, 0, p.b_k0 + kc, (p.b_mn0 + n0) >> 5);
-                            else tma_load_3d(sb, &map_b, bar, 0, p.b_k0 + kc, (p.b_mn0 + n0) >> 5);
                         } else {
-#pragma unroll
-                            for (int i = 0; i < (B_ROWS + 31) / 32; ++i) {
-                                if (NCTA == 2) tma_load_2d_pair(sb + i * ATOM_BYTES, &map_b, bar, p.b_mn0 + n0 + i * 32, p.b_k0 + kc);
-                                else tma_load_2d(sb + i * ATOM_BYTES, &map_b, bar, p.b_mn0 + n0 + i * 32, p.b_k0 + kc);
-                            }
+                            if (NCTA == 2) tma_load_2d_pair(ta, ma, bar, p.a_k0 + kc, p.a_mn0 + m0);
+                            else tma_load_2d(ta, ma, bar, p.a_k0 + kc, p.a_mn0 + m0);
                         }
-                    } else {
-                        if (NCTA == 2) tma_load_2d_pair(sb, &map_b, bar, p.b_k0 + kc, p.b_mn0 + n0);
-                        else tma_load_2d(sb, &map_b, bar, p.b_k0 + kc, p.b_mn0 + n0);
-                    }
+                        if (B_MN) {
+                            if (p.b_3d) {
+                                if (NCTA == 2) tma_load_3d_pair(tb, mb, bar, 0, p.b_k0 + kc, (p.b_mn0 + n0) >> 5);
+                                else tma_load_3d(tb, mb, bar, 0, p.b_k0 + kc, (p.b_mn0 + n0) >> 5);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < (B_ROWS + 31) / 32; ++i) {
+                                    if (NCTA == 2) tma_load_2d_pair(tb + i * ATOM_BYTES, mb, bar, p.b_mn0 + n0 + i * 32, p.b_k0 + kc);
+                                    else tma_load_2d(tb + i * ATOM_BYTES, mb, bar, p.b_mn0 + n0 + i * 32, p.b_k0 + kc);
+                                }
+                            }
+                        } else {
+                            if (NCTA == 2) tma_load_2d_pair(tb, mb, bar, p.b_k0 + kc, p.b_mn0 + n0);
+                            else tma_load_2d(tb, mb, bar, p.b_k0 + kc, p.b_mn0 + n0);
+                        }
+                    };
+                    load_pair(sa, sb, &map_a, &map_b);
+                    if (X3) load_pair(sa + HALF_STAGE, sb + HALF_STAGE, &map_a_lo, &map_b_lo);
                     if (NCTA == 2) {
                         // the leader's barrier counts one arrival per CTA and the bytes of BOTH CTAs' boxes
                         if (leader) mbar_expect_tx(bar, 2 * STAGE_BYTES);
@@ -203,12 +216,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint32_t sb = sa + A_TILE_BYTES;
 #pragma unroll
                         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                            const uint64_t da = A_MN ? umma_smem_desc(sa + kk * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout)
-                                                     : umma_smem_desc(sa + kk * UMMA_K * 4, 16, 1024);
-                            const uint64_t db = B_MN ? umma_smem_desc(sb + kk * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout)
-                                                     : umma_smem_desc(sb + kk * UMMA_K * 4, 16, 1024);
-                            if (NCTA == 2) umma_tf32_pair(tmem_d, da, db, IDESC, (kb | kk) != 0 ? 1u : 0u);
-                            else umma_tf32(tmem_d, da, db, IDESC, (kb | kk) != 0 ? 1u : 0u);
+                            auto desc_a = [&](uint32_t base) { return A_MN ? umma_smem_desc(base + kk * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                                           : umma_smem_desc(base + kk * UMMA_K * 4, 16, 1024); };
+                            auto desc_b = [&](uint32_t base) { return B_MN ? umma_smem_desc(base + kk * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                                           : umma_smem_desc(base + kk * UMMA_K * 4, 16, 1024); };
+                            auto mma = [&](uint64_t da, uint64_t db, uint32_t accumulate) {
+                                if (NCTA == 2) umma_tf32_pair(tmem_d, da, db, IDESC, accumulate);
+                                else umma_tf32(tmem_d, da, db, IDESC, accumulate);
+                            };
+                            const uint64_t da = desc_a(sa), db = desc_b(sb);
+                            mma(da, db, (kb | kk) != 0 ? 1u : 0u);
+                            if (X3) {
+                                mma(da, desc_b(sb + HALF_STAGE), 1u);            // hi(A) * lo(B)
+                                mma(desc_a(sa + HALF_STAGE), db, 1u);            // lo(A) * hi(B)
+                            }
                         }
                         // slot reusable (in both CTAs) once these MMAs have read it; accumulator complete after the last
                         if (NCTA == 2) umma_commit_pair(&empty_bar[s], 3); else umma_commit(&empty_bar[s]);
@@ -277,6 +298,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
                         break;
+                }
+                if (X3 && p.D_lo != nullptr && m_ok) {
+                    // low part of the output for the next contraction that consumes it: exact remainder of the truncation
+                    float* dlo = p.D_lo + int64_t(n0 + c0) * p.ldd + m;
+#pragma unroll
+                    for (int j = 0; j < CH; ++j)
+                        if (n0 + c0 + j < p.N) dlo[int64_t(j) * p.ldd] = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
                 }
                 if (m_ok) {
                     float* dst = Dp + int64_t(n0 + c0) * p.ldd + m;
@@ -363,9 +391,9 @@ bool encode_operand(CUtensorMap* map, const float* base, int64_t ld, bool mn_maj
 
 int g_num_sms = 0;
 
-template <int BN, bool A_MN, bool B_MN, int NCTA>
+template <int BN, bool A_MN, bool B_MN, int NCTA, bool X3>
 cudaError_t launch_one(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NCTA>;
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NCTA, X3>;
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
@@ -382,25 +410,29 @@ cudaError_t launch_one(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
     attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = NCTA == 2 ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, pl.map_a, pl.map_b, a);
+    return cudaLaunchKernelEx(&cfg, kern, pl.map_a, pl.map_b, X3 ? pl.map_a_lo : pl.map_a, X3 ? pl.map_b_lo : pl.map_b, a);
 }
 
-template <int BN, int NCTA>
+template <int BN, int NCTA, bool X3>
 cudaError_t launch_majors(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
     const bool am = pl.g.a_major != 0, bm = pl.g.b_major != 0;
     if (am && bm) {
-        if constexpr (NCTA == 2 && BN < 64) return cudaErrorInvalidValue; else return launch_one<BN, true, true, NCTA>(pl, a, stream);
+        if constexpr (NCTA == 2 && BN < 64) return cudaErrorInvalidValue; else return launch_one<BN, true, true, NCTA, X3>(pl, a, stream);
     }
-    if (am && !bm) return launch_one<BN, true, false, NCTA>(pl, a, stream);
+    if (am && !bm) return launch_one<BN, true, false, NCTA, X3>(pl, a, stream);
     if (!am && bm) {
-        if constexpr (NCTA == 2 && BN < 64) return cudaErrorInvalidValue; else return launch_one<BN, false, true, NCTA>(pl, a, stream);
+        if constexpr (NCTA == 2 && BN < 64) return cudaErrorInvalidValue; else return launch_one<BN, false, true, NCTA, X3>(pl, a, stream);
     }
-    return launch_one<BN, false, false, NCTA>(pl, a, stream);
+    return launch_one<BN, false, false, NCTA, X3>(pl, a, stream);
 }
 
 template <int BN>
 cudaError_t launch_bn(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
-    return pl.ncta == 2 ? launch_majors<BN, 2>(pl, a, stream) : launch_majors<BN, 1>(pl, a, stream);
+    if (pl.x3) {
+        // the fp32-grade mode keeps 4 tiles per stage: single CTAs, tiles up to 128 columns
+        if constexpr (BN <= 128) return launch_majors<BN, 1, true>(pl, a, stream); else return cudaErrorInvalidValue;
+    }
+    return pl.ncta == 2 ? launch_majors<BN, 2, false>(pl, a, stream) : launch_majors<BN, 1, false>(pl, a, stream);
 }
 
 }  // namespace
@@ -422,6 +454,8 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     int bn;
     if (g.N > 128) bn = 256; else if (g.N > 64) bn = 128; else if (g.N > 32) bn = 64; else if (g.N > 16) bn = 32; else bn = 16;
     if (g.b_major && bn < 32) bn = 32;     // an MN-major box is 32 floats wide
+    plan.x3 = g.A_lo != nullptr && g.B_lo != nullptr;
+    if (plan.x3 && bn > 128) bn = 128;     // four tiles per stage: 128 x 128 keeps three stages in flight
     plan.block_n = bn;
     plan.g = g;
 
@@ -436,9 +470,10 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     int ncta = 1;
     if (const char* e = std::getenv("B2NN_TC_NCTA")) { if (std::atoi(e) == 2 && g.M > BM) ncta = 2; }
     if (g.b_major && bn < 64) ncta = 1;
+    if (plan.x3) ncta = 1;
     plan.ncta = ncta;
 
-    const int stage_bytes = A_TILE_BYTES + b_tile_bytes(bn / ncta, g.b_major != 0);
+    const int stage_bytes = (A_TILE_BYTES + b_tile_bytes(bn / ncta, g.b_major != 0)) * (plan.x3 ? 2 : 1);
     int stages = (SMEM_LIMIT - 1024 - 256) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) { err = "tile does not fit shared memory"; return false; }
@@ -467,6 +502,10 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     plan.b_3d = g.b_major && g.mn_slack && !no3d && (g.b_mn0 % 32 == 0);
     if (!encode_operand(&plan.map_a, g.A, g.lda, g.a_major != 0, a_mn_end, a_k_end, BM, plan.a_3d, err)) return false;
     if (!encode_operand(&plan.map_b, g.B, g.ldb, g.b_major != 0, g.b_mn0 + g.N, g.b_k0 + g.K, bn / ncta, plan.b_3d, err)) return false;   // each CTA of a pair stages half of B
+    if (plan.x3) {
+        if (!encode_operand(&plan.map_a_lo, g.A_lo, g.lda, g.a_major != 0, a_mn_end, a_k_end, BM, plan.a_3d, err)) return false;
+        if (!encode_operand(&plan.map_b_lo, g.B_lo, g.ldb, g.b_major != 0, g.b_mn0 + g.N, g.b_k0 + g.K, bn / ncta, plan.b_3d, err)) return false;
+    }
     plan.valid = true;
     return true;
 }
@@ -475,6 +514,7 @@ cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream) {
     if (!pl.valid) return cudaErrorInvalidValue;
     TcArgs a;
     a.D = pl.g.D; a.ldd = pl.g.ldd; a.aux = pl.g.aux; a.ldaux = pl.g.ldaux;
+    a.D_lo = pl.x3 ? pl.g.D_lo : nullptr;
     a.M = pl.g.M; a.N = pl.g.N;
     a.tiles_m = pl.tiles_m; a.tiles_n = pl.tiles_n; a.splits = pl.splits;
     a.k_blocks = pl.k_blocks; a.k_blocks_total = pl.k_blocks_total;

@@ -54,7 +54,9 @@ enum { B2NN_INIT_1 = 1 /* eps = 1/sqrt(in)          */, B2NN_INIT_2 = 2 /* eps =
 /* Arithmetic of the three contractions (forward, delta backprop, weight gradient). */
 enum { B2NN_PREC_FP32 = 0 /* fp32 FFMA, matches cublasSgemm default math up to summation order          */,
        B2NN_PREC_TF32 = 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM; small layers stay on fp32 FFMA   */,
-       B2NN_PREC_AUTO = 2 /* B2NN_PRECISION env var ("fp32" | "tf32"), default tf32                         */ };
+       B2NN_PREC_AUTO = 2 /* B2NN_PRECISION env var ("fp32" | "tf32" | "tf32x3"), default tf32              */,
+       B2NN_PREC_TF32X3 = 3 /* fp32-grade on tensor cores: every operand carries its tf32 remainder and each K step
+                               issues hi*hi + hi*lo + lo*hi (3 tcgen05.mma) into the fp32 TMEM accumulator            */ };
 
 /* Function-pointer shapes of the reference's pluggable device ops (cublasNN.h:33, 45-50).  All pointers are DEVICE
  * pointers; the functions are HOST functions that enqueue work on the legacy default stream. */
@@ -171,7 +173,8 @@ int b2nn_comm_barrier(b2nn_ctx* ctx);
  * epi: 0 store, 1 sigmoid, 2 tanh, 3 multiply by sigmoid'(aux), 4 multiply by tanh'(aux) with aux = activation values
  * laid out like D.  All pointers are device pointers.  backend: 0 fp32 FFMA, 1 tcgen05 tf32, 3 tcgen05 tf32 where
  * the caller guarantees 32 floats of readable slack after every row of an M/N-contiguous operand (one TMA box per
- * tile instead of one per 32-float atom). */
+ * tile instead of one per 32-float atom); 5 / 7 = the same two with the fp32-grade 3xTF32 arithmetic (operand low
+ * parts are split into temporaries inside the call). */
 int b2nn_gemm(b2nn_ctx* ctx, int backend, const float* A, int64_t lda, int a_major, const float* B, int64_t ldb,
               int b_major, float* D, int64_t ldd, int M, int N, int K, int epi, const float* aux, int64_t ldaux);
 /* Momentum update kernel alone: v = mu*v + alpha*g ; theta = theta + v over count elements (device pointers). */

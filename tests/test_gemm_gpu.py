@@ -30,7 +30,7 @@ def _run(net, b2nn, backend, M, N, K, majors, epi=0, seed=0):
     gen = torch.Generator(device="cuda")
     gen.manual_seed(seed)
     a_major, b_major = majors
-    pad = 32 if backend == 3 else 4
+    pad = 32 if backend in (3, 7) else 4
     A, lda, Ad = _operand(M, K, a_major, gen, pad)
     B, ldb, Bd = _operand(N, K, b_major, gen, pad)
     ldd = (M + 3) // 4 * 4 + 8
@@ -78,6 +78,21 @@ def test_tcgen05_gemm_matches_fp64_within_tf32(net, b2nn, kind, shape, backend):
     tol = 1.25 * 2.0 ** -9 * bound + 1e-5
     bad = err > tol
     assert not bool(bad.any()), (kind, shape, float(err.max()), int(bad.sum()), bad.nonzero()[:4].tolist())
+
+
+@pytest.mark.parametrize("backend", [5, 7])
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("kind", list(MAJORS))
+def test_tcgen05_3xtf32_gemm_is_fp32_grade(net, b2nn, kind, shape, backend):
+    """fp32-grade tensor-core mode: hi*hi + hi*lo + lo*hi with hi = trunc_tf32(x), lo = x - hi (lo is itself truncated
+    to 11 bits by the MMA, the lo*lo term is dropped): per product error <= ~3 * 2^-21 |a||b|, i.e. >= 2^11 times tighter
+    than plain tf32; the bound below also covers fp32 accumulation over K."""
+    M, N, K = shape
+    got, ref, bound = _run(net, b2nn, backend, M, N, K, MAJORS[kind])
+    err = (got - ref).abs()
+    tol = 2.0 ** -18 * bound + 1e-6
+    bad = err > tol
+    assert not bool(bad.any()), (kind, shape, float(err.max()), float((err / bound).max()), int(bad.sum()))
 
 
 @pytest.mark.parametrize("epi", [1, 2, 3, 4])

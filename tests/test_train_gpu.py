@@ -20,7 +20,9 @@ pytestmark = pytest.mark.gpu
 #              Over hundreds of steps on an ill-conditioned regression (bikeshare targets ~ 10^2) the reduced-precision
 #              trajectory drifts away in theta while the cost — the quantity the user sees — stays within bound, so
 #              long tf32 runs are judged on the cost curve only (LONG_TF32).
-TOL = {"fp32": dict(theta=2e-4, J=2e-4), "tf32": dict(theta=2e-2, J=3e-2)}
+#   tf32x3   : fp32-grade on tensor cores (hi*hi + hi*lo + lo*hi per product, fp32 accumulate) — held to the fp32 bounds.
+TOL = {"fp32": dict(theta=2e-4, J=2e-4), "tf32": dict(theta=2e-2, J=3e-2), "tf32x3": dict(theta=2e-4, J=2e-4)}
+PREC = {"fp32": 0, "tf32": 1, "tf32x3": 3}
 LONG_TF32 = {"reg_sigmoid_bikeshare512"}
 
 
@@ -29,7 +31,7 @@ def _desc(b2nn, c, prec, **over):
               classify=c.classify, act=b2nn.ACT_SIGMOID if c.hidden_act == cases.SIGMOID else b2nn.ACT_TANH,
               out=(b2nn.OUT_SIGMOID if c.out_act == cases.OUT_SIGMOID else b2nn.OUT_SOFTMAX) if c.classify else b2nn.OUT_LINEAR,
               cost=(b2nn.COST_NEGLNMAX if c.cost == cases.COST_NEGLNMAX else b2nn.COST_CROSSENTROPY) if c.classify else b2nn.COST_SQUARED,
-              precision=b2nn.PREC_FP32 if prec == "fp32" else b2nn.PREC_TF32)
+              precision=PREC[prec])
     kw.update(over)
     return b2nn.make_desc(**kw)
 
@@ -77,7 +79,7 @@ def test_set_get_weights_roundtrip(b2nn):
     net.close()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "tf32x3"])
 @pytest.mark.parametrize("name", ALL)
 def test_train_matches_oracle(b2nn, oracle, name, prec):
     c = cases.case_by_name(name)
@@ -96,8 +98,8 @@ def test_train_matches_oracle(b2nn, oracle, name, prec):
     if c.classify:
         assert abs(out.error_count - ref64.error_count) <= max(1.0, 0.005 * c.m)
     assert out.steps == c.iters * c.batch_num
-    if prec == "tf32" and name == "wide_mini":
-        assert out.gemm_tc_launches > 0, "tf32 mode must run the large contractions on the tcgen05 kernel"
+    if prec in ("tf32", "tf32x3") and name == "wide_mini":
+        assert out.gemm_tc_launches > 0, "tensor-core modes must run the large contractions on the tcgen05 kernel"
     if prec == "fp32":
         assert out.gemm_tc_launches == 0
     net.close()
@@ -236,7 +238,7 @@ def _torch_step_fp64(layers, W, X, Y, rate, hidden):
     return new[::-1], float(J)
 
 
-@pytest.mark.parametrize("prec", ["tf32"])
+@pytest.mark.parametrize("prec", ["tf32", "tf32x3"])
 def test_c3_full_size_one_step_against_fp64(b2nn, oracle, prec):
     """BASELINE.json config C3 at full size (784-4096-4096-10, batch 8192): one momentum-free step on the engine vs an
     fp64 restatement of the same step; also the printed cost.  The CPU oracle is too slow at this size, so the
@@ -255,16 +257,17 @@ def test_c3_full_size_one_step_against_fp64(b2nn, oracle, prec):
     rate = 0.5
     d = b2nn.make_desc(momentum=0.0, rate=rate, iters=1, display=1, batch_num=1, classify=True, act=b2nn.ACT_TANH,
                        out=b2nn.OUT_SOFTMAX, cost=b2nn.COST_CROSSENTROPY,
-                       precision=b2nn.PREC_TF32 if prec == "tf32" else b2nn.PREC_FP32, skip_final_cost=True)
+                       precision=PREC[prec], skip_final_cost=True)
     out = net.train(d)
     th1 = net.get_weights()
+    rel = 2e-2 if prec == "tf32" else 5e-4
     assert out.gemm_tc_launches >= 5
     W = []
     for pos, r, cdim in oracle.theta_offsets(layers):
         W.append(torch.tensor(th0[pos:pos + r * cdim].reshape(cdim, r).T.copy(), dtype=torch.float64, device="cuda"))
     Wn, J = _torch_step_fp64(layers, W, torch.tensor(X, dtype=torch.float64, device="cuda"),
                              torch.tensor(np.eye(K)[lab], dtype=torch.float64, device="cuda"), rate, "tanh")
-    assert abs(out.log_J[0] - J) <= 2e-3 * abs(J)
+    assert abs(out.log_J[0] - J) <= (2e-3 if prec == "tf32" else 2e-5) * abs(J)
     for (pos, r, cdim), w0, wn in zip(oracle.theta_offsets(layers), W, Wn):
         got = torch.tensor(th1[pos:pos + r * cdim].reshape(cdim, r).T.copy(), dtype=torch.float64, device="cuda")
         step_ref = wn - w0
@@ -272,7 +275,7 @@ def test_c3_full_size_one_step_against_fp64(b2nn, oracle, prec):
         denom = float(step_ref.abs().max())
         assert denom > 0
         # the UPDATE (not just theta) must match: relative to the largest update entry of the layer
-        assert float((step_got - step_ref).abs().max()) <= 2e-2 * denom, (pos, denom)
+        assert float((step_got - step_ref).abs().max()) <= rel * denom + 2e-7, (pos, denom)   # + fp32 ulp of theta itself
         # and theta itself to fp32 resolution of the update
-        assert float((got - wn).abs().max()) <= 2e-2 * denom + 1e-7
+        assert float((got - wn).abs().max()) <= rel * denom + 2e-7
     net.close()
