@@ -247,10 +247,17 @@ def run_ours(args):
         peak = 75.0
         peak_note = "fp32 FFMA planning value (BASELINE.md); not measured"
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    try:        # DRAM bytes per tcgen05 launch from the committed ncu --set full capture of this workload (profiles/)
+        if args.workload == "c3" and args.precision == "tf32" and B == 8192:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["gemm_tc_kernel"]["dram_bytes_per_launch_mean"]
+    except Exception:
+        traffic = None
     roofline = {
         "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::tf32) x3 contractions" if args.precision != "fp32" else "gemm_simt_kernel",
         "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-        "traffic": None, "peak_source": peak_note,
+        "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read+write per launch, mean over the 7 tcgen05 launches of a step)" if traffic else None,
+        "algorithmic_flops_per_launch_mean": round(gemm_fl / max(gemm_launches, 1)), "peak_source": peak_note,
         "launches": gemm_launches, "avg_launch_ms": round(gemm_ms / max(gemm_launches, 1), 4),
         "share_of_step": round(gemm_ms / total_ms, 4) if total_ms > 0 else None,
         "by_kind": {k: {"ms_per_step": round(v["ms"] / K, 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 and v["flops"] > 0 else None,
