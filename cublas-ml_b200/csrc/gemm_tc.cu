@@ -390,6 +390,7 @@ bool encode_operand(CUtensorMap* map, const float* base, int64_t ld, bool mn_maj
 }
 
 int g_num_sms = 0;
+int g_reserved_sms = 0;      // SMs left free for a concurrent communication kernel (data parallel)
 
 template <int BN, bool A_MN, bool B_MN, int NCTA, bool X3>
 cudaError_t launch_one(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
@@ -436,6 +437,8 @@ cudaError_t launch_bn(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace
+
+void tc_set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : n; }
 
 bool tc_runtime_ok(std::string& err) {
     std::call_once(g_encode_once, load_encode);
@@ -490,7 +493,10 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     plan.splits = splits;
     const int64_t work = int64_t(plan.tiles_m) * plan.tiles_n * splits;
     if (work >= (int64_t(1) << 30)) { err = "too many tiles"; return false; }
-    const int64_t max_workers = g_num_sms / ncta;
+    int usable = g_num_sms - g_reserved_sms;
+    if (const char* e = std::getenv("B2NN_TC_RESERVE_SMS")) usable = g_num_sms - std::atoi(e);
+    if (usable < 2 * ncta) usable = 2 * ncta;
+    const int64_t max_workers = usable / ncta;
     plan.grid_x = unsigned(std::min<int64_t>(work, max_workers) * ncta);      // persistent: one CTA (pair) per SM (pair)
 
     const int64_t a_mn_end = g.a_mn_end > 0 ? g.a_mn_end : g.a_mn0 + g.M;
