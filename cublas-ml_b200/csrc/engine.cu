@@ -346,7 +346,14 @@ void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
     // the exact fp32 FFMA kernel (the bikeshare-sized nets of config C2 never leave fp32).
     if ((prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3) && work >= double(1 << 26) && g.M >= 32) {
         std::string err;
-        if (tc_plan_build(op.plan, g, err)) op.tc = true;
+        const int requested = g.split_k;
+        if (g.epi == EPI_STORE && (allow_split || g.N <= 32)) g.split_k = 0;     // let the tcgen05 plan pick the split
+        if (tc_plan_build(op.plan, g, err)) {
+            op.tc = true;
+            op.zero_first = op.plan.splits > 1;
+        } else {
+            g.split_k = requested;
+        }
     }
     if (!op.tc && g.split_k > 1) {
         // FFMA tiles are 64 x 64: re-derive the split for that grid

@@ -28,7 +28,7 @@ struct GemmDesc {
     int M = 0, N = 0, K = 0;
     int epi = EPI_STORE;
     const float* aux = nullptr; int64_t ldaux = 0;
-    int split_k = 1;          // > 1: partial sums are added atomically into a pre-zeroed D (EPI_STORE only)
+    int split_k = 1;          // > 1: partial sums are added atomically into a pre-zeroed D (EPI_STORE only); 0: the tcgen05 plan picks
     // Extent of A's allocation along each index when it is larger than origin + size (0 = origin + size).  Lets one
     // tensor map over the whole training matrix serve every batch.
     int64_t a_mn_end = 0, a_k_end = 0;

@@ -54,6 +54,7 @@ struct TcArgs {
     const float* aux; int64_t ldaux;
     int M, N;
     int tiles_m, tiles_n, splits;   // work item = (tile_m, tile_n, split); tile_m counts (128 * NCTA)-row tiles
+    int group_m;                    // rasterisation group (see decode_tile)
     int k_blocks;                   // K blocks per split
     int k_blocks_total;
     int a_mn0, a_k0, b_mn0, b_k0;
@@ -63,6 +64,20 @@ struct TcArgs {
     uint32_t mn_lbo, mn_sbo, mn_layout;   // MN-major descriptor: 4096 / 512 / type 1 (overridable for bring-up)
     int a_3d, b_3d;                 // MN-major operand fetched with one 3-D TMA box per tile
 };
+
+// Work item -> output tile.  Tiles are walked in groups of `group_m` row-tiles: inside a group the row-tile index is
+// fastest, then the column-tile index, so the ~148 tiles in flight at any time touch about group_m panels of A and
+// 148 / group_m panels of B.  group_m = 1 sweeps all column tiles of one row-tile first (B stays L2 resident when it is
+// the small operand, e.g. the weights in forward / backprop); large group_m approaches row-fastest order.
+__device__ __forceinline__ void decode_tile(int rem, int tiles_m, int tiles_n, int group_m, int& tile_m, int& tile_n) {
+    const int per_group = group_m * tiles_n;
+    const int g = rem / per_group;
+    const int first_m = g * group_m;
+    const int gsize = min(group_m, tiles_m - first_m);
+    const int in_g = rem - g * per_group;
+    tile_m = first_m + in_g % gsize;
+    tile_n = in_g / gsize;
+}
 
 // Fast forms for the tensor-core epilogue (tf32 mode): MUFU.EX2 + MUFU.RCP, relative error ~1e-6 — three orders below
 // the tf32 rounding of the contraction they follow.  The fp32 FFMA path keeps expf / tanhf (epilogue.cuh).
@@ -135,7 +150,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int it = 0;
             for (int w = worker; w < total_work; w += n_workers) {
                 const int split = w / tiles_mn, rem = w - split * tiles_mn;
-                const int tile_n = rem / p.tiles_m, tile_m = rem - tile_n * p.tiles_m;
+                int tile_m, tile_n; decode_tile(rem, p.tiles_m, p.tiles_n, p.group_m, tile_m, tile_n);
                 const int m0 = (tile_m * NCTA + int(rank)) * BM;          // this CTA's 128 rows of A
                 const int n0 = tile_n * BN + int(rank) * B_ROWS;          // this CTA's share of B
                 const int kb0 = split * p.k_blocks;
@@ -252,7 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int t = 0;
         for (int w = worker; w < total_work; w += n_workers, ++t) {
             const int split = w / tiles_mn, rem = w - split * tiles_mn;
-            const int tile_n = rem / p.tiles_m, tile_m = rem - tile_n * p.tiles_m;
+            int tile_m, tile_n; decode_tile(rem, p.tiles_m, p.tiles_n, p.group_m, tile_m, tile_n);
             const int m = (tile_m * NCTA + int(rank)) * BM + q * 32 + lane;
             const int n0 = tile_n * BN;
             const bool m_ok = m < p.M;
@@ -484,19 +499,36 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     plan.smem_bytes = size_t(stages) * stage_bytes + 1024 + 256;
 
     plan.k_blocks_total = (g.K + BK - 1) / BK;
-    int splits = (g.split_k > 1 && g.epi == EPI_STORE) ? g.split_k : 1;
+    plan.tiles_m = (g.M + BM * ncta - 1) / (BM * ncta);
+    plan.tiles_n = (g.N + bn - 1) / bn;
+    int usable_sms = g_num_sms - g_reserved_sms;
+    if (const char* e = std::getenv("B2NN_TC_RESERVE_SMS")) usable_sms = g_num_sms - std::atoi(e);
+    if (usable_sms < 2 * ncta) usable_sms = 2 * ncta;
+    const int64_t max_workers = usable_sms / ncta;
+    int splits = 1;
+    if (g.epi == EPI_STORE && g.split_k > 1) splits = g.split_k;
+    else if (g.epi == EPI_STORE && g.split_k == 0) {
+        // auto split-K: few output tiles but a long K (weight gradients, the 10-column output layer).  Model: time ~
+        // waves * (K blocks per item + fixed per-item cost); items beyond one wave only pay when they shorten it.
+        const int64_t tiles = int64_t(plan.tiles_m) * plan.tiles_n;
+        if (tiles < max_workers) {
+            double best = 1e30;
+            const int smax = std::min(64, std::max(1, plan.k_blocks_total / 4));
+            for (int sp = 1; sp <= smax; ++sp) {
+                const int64_t items = tiles * sp;
+                const int64_t waves = (items + max_workers - 1) / max_workers;
+                const int kb = (plan.k_blocks_total + sp - 1) / sp;
+                const double cost = double(waves) * (kb + 6.0) + 0.02 * sp;       // tie-break towards fewer atomics
+                if (cost < best) { best = cost; splits = sp; }
+            }
+        }
+    }
     if (splits > plan.k_blocks_total) splits = plan.k_blocks_total;
     plan.k_blocks = (plan.k_blocks_total + splits - 1) / splits;
     splits = (plan.k_blocks_total + plan.k_blocks - 1) / plan.k_blocks;
-    plan.tiles_m = (g.M + BM * ncta - 1) / (BM * ncta);
-    plan.tiles_n = (g.N + bn - 1) / bn;
     plan.splits = splits;
     const int64_t work = int64_t(plan.tiles_m) * plan.tiles_n * splits;
     if (work >= (int64_t(1) << 30)) { err = "too many tiles"; return false; }
-    int usable = g_num_sms - g_reserved_sms;
-    if (const char* e = std::getenv("B2NN_TC_RESERVE_SMS")) usable = g_num_sms - std::atoi(e);
-    if (usable < 2 * ncta) usable = 2 * ncta;
-    const int64_t max_workers = usable / ncta;
     plan.grid_x = unsigned(std::min<int64_t>(work, max_workers) * ncta);      // persistent: one CTA (pair) per SM (pair)
 
     const int64_t a_mn_end = g.a_mn_end > 0 ? g.a_mn_end : g.a_mn0 + g.M;
@@ -523,6 +555,14 @@ cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream) {
     a.D_lo = pl.x3 ? pl.g.D_lo : nullptr;
     a.M = pl.g.M; a.N = pl.g.N;
     a.tiles_m = pl.tiles_m; a.tiles_n = pl.tiles_n; a.splits = pl.splits;
+    {
+        // measured on the 8192 x 4096 x 4096 contractions: 582 (row-fastest) -> 611 TFLOP/s with groups of 8-16 row-tiles
+        int gm = 16;
+        if (const char* e = std::getenv("B2NN_TC_GROUP_M")) gm = std::atoi(e);
+        if (gm < 1) gm = 1;
+        if (gm > pl.tiles_m) gm = pl.tiles_m;
+        a.group_m = gm;
+    }
     a.k_blocks = pl.k_blocks; a.k_blocks_total = pl.k_blocks_total;
     a.a_mn0 = int(pl.g.a_mn0); a.a_k0 = int(pl.g.a_k0); a.b_mn0 = int(pl.g.b_mn0); a.b_k0 = int(pl.g.b_k0);
     a.epi = pl.g.epi; a.atomic = pl.splits > 1 ? 1 : 0; a.stages = pl.stages;
