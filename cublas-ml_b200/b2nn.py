@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "b2nn_create", "b2nn_destroy", "b2nn_last_error", "b2nn_device_ok", "b2nn_version", "b2nn_set_layers",
     "b2nn_num_weights", "b2nn_get_weights", "b2nn_set_weights", "b2nn_set_train_data", "b2nn_train",
     "b2nn_train_step_host", "b2nn_train_host", "b2nn_reset_velocity", "b2nn_evaluate", "b2nn_predict", "b2nn_predict_device",
-    "b2nn_builtin_kind", "b2nn_comm_unique_id", "b2nn_comm_init", "b2nn_comm_barrier", "b2nn_gemm",
+    "b2nn_builtin_kind", "b2nn_comm_unique_id", "b2nn_comm_init", "b2nn_comm_barrier", "b2nn_comm_p2p_export", "b2nn_comm_p2p_open", "b2nn_gemm",
     "b2nn_momentum_update", "b2nn_stream", "b2nn_profile_enable", "b2nn_profile_read",
 ]
 PROFILE_KINDS = ("forward", "backprop", "wgrad", "output", "update")
@@ -104,6 +104,10 @@ def lib():
     L.b2nn_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.b2nn_comm_barrier.restype = C.c_int
     L.b2nn_comm_barrier.argtypes = [vp]
+    L.b2nn_comm_p2p_export.restype = C.c_int
+    L.b2nn_comm_p2p_export.argtypes = [vp, vp]
+    L.b2nn_comm_p2p_open.restype = C.c_int
+    L.b2nn_comm_p2p_open.argtypes = [vp, vp]
     L.b2nn_gemm.restype = C.c_int
     L.b2nn_gemm.argtypes = [vp, C.c_int, vp, i64, C.c_int, vp, i64, C.c_int, vp, i64, C.c_int, C.c_int, C.c_int,
                             C.c_int, vp, i64]
@@ -298,6 +302,15 @@ class Net:
     def comm_init(self, rank: int, nranks: int, uid: bytes):
         buf = C.create_string_buffer(uid, 128)
         _check(lib().b2nn_comm_init(self._h, rank, nranks, buf), "b2nn_comm_init")
+
+    def comm_p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(192)
+        _check(lib().b2nn_comm_p2p_export(self._h, buf), "b2nn_comm_p2p_export")
+        return buf.raw
+
+    def comm_p2p_open(self, blobs: bytes):
+        buf = C.create_string_buffer(blobs, len(blobs))
+        _check(lib().b2nn_comm_p2p_open(self._h, buf), "b2nn_comm_p2p_open")
 
     def comm_barrier(self):
         _check(lib().b2nn_comm_barrier(self._h), "b2nn_comm_barrier")

@@ -59,6 +59,7 @@ struct StepPlan {
     std::vector<GemmOp> fwd;     // L-1 entries
     std::vector<GemmOp> wgrad;   // L-1 entries
     std::vector<GemmOp> bwd;     // entry j computes delta_{j-1} from delta_j (index 0 unused)
+    std::vector<char> fused;     // data parallel over peer memory: layer's gradient is scattered to its owners by the GEMM
     bool use_tail = false;       // skinny last layer: forward + output + delta backprop fused in tail.cu
     bool tail_inline_g = false;  // ... and its weight gradient too
 };
@@ -170,6 +171,15 @@ struct b2nn_ctx {
     // data parallel
     void* comm = nullptr; int rank = 0, nranks = 1;
     std::vector<cudaEvent_t> grad_ready, grad_reduced;
+    // ... over NVLink peer memory (p2p.cu): fused reduce-scatter / update / all-gather for the large layers
+    bool p2p = false;
+    P2pPeers peers{};
+    int* p2p_flags = nullptr;                 // local flag block: [kind][layer][rank], kind 0 = wg_done, 1 = w_done
+    int p2p_step = 0;
+    cudaStream_t upd_stream = nullptr;
+    std::vector<cudaEvent_t> p2p_wg_ev;
+    cudaEvent_t p2p_upd_done = nullptr;
+    std::vector<void*> p2p_opened;
 
     int64_t launches = 0, tc_launches = 0;
 
@@ -389,6 +399,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
     const bool x3 = prec == B2NN_PREC_TF32X3 && !custom && !w.a_lo.empty() && c->W_lo != nullptr;
     const float* X_lo = x3 ? find_lo(c, X) : nullptr;
     sp.fwd.resize(nw); sp.wgrad.resize(nw); sp.bwd.resize(nw);
+    sp.fused.assign(nw, 0);
     {
         const LayerInfo& last = c->L[nw - 1];
         const bool no_tail = std::getenv("B2NN_NO_TAIL") != nullptr;
@@ -435,7 +446,16 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
             g.g.B_lo = w.delta_lo[j];
             if (!g.g.A_lo) g.g.B_lo = nullptr;
         }
-        if (!(tail_layer && sp.tail_inline_g)) bind_backend(c, g, prec, true);
+        // Peer-memory exchange: the layer's rows split evenly over the ranks in whole 256-column tiles of the gradient GEMM
+        const bool want_fused = c->p2p && prec == B2NN_PREC_TF32 && !custom && !tail_layer && nw <= P2P_MAX_LAYERS &&
+                                li.out % (256 * c->nranks) == 0;
+        if (want_fused) {
+            for (int o = 0; o < c->nranks; ++o) g.g.scatter_base[o] = c->peers.G[o] + li.w_off;
+            g.g.scatter_world = c->nranks; g.g.scatter_rank = c->rank; g.g.scatter_rows = li.out / c->nranks;
+            bind_backend(c, g, prec, false);
+            if (g.tc) sp.fused[j] = 1;
+            else { g.g.scatter_world = 0; bind_backend(c, g, prec, true); }
+        } else if (!(tail_layer && sp.tail_inline_g)) bind_backend(c, g, prec, true);
 
         // delta backprop  delta_{j-1} = (delta_j W_j)[:, no bias] .* f'(z_{j-1})   (cublasNN.cpp:673-676)
         if (j > 0) {
@@ -521,10 +541,17 @@ int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_d
     for (int j = nw - 1; j >= 0; --j) {
         const bool tail_layer = sp.use_tail && j == nw - 1;
         int rc = B2NN_OK;
+        // With the peer-memory exchange an owner may overwrite W_j on this rank as soon as every rank has signalled its
+        // gradient of layer j, so the delta backprop that still reads W_j goes first.
+        const bool bwd_first = c->p2p;
+        if (bwd_first && j > 0 && !tail_layer) { rc = run_gemm(c, sp.bwd[j], 0, 1); if (rc) return rc; }
         if (!(tail_layer && sp.tail_inline_g)) rc = run_gemm(c, sp.wgrad[j], x_start, 2);
         if (rc) return rc;
-        if (c->comm && !c->grad_ready.empty()) B2_CUDA(cudaEventRecord(c->grad_ready[j], c->stream));
-        if (j > 0 && !tail_layer) {
+        if (sp.fused[j]) {
+            B2_CUDA(p2p_signal_launch(c->peers, (0 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD + c->rank, c->p2p_step, c->stream));
+            B2_CUDA(cudaEventRecord(c->p2p_wg_ev[j], c->stream));
+        } else if (c->comm && !c->grad_ready.empty()) B2_CUDA(cudaEventRecord(c->grad_ready[j], c->stream));
+        if (!bwd_first && j > 0 && !tail_layer) {
             rc = run_gemm(c, sp.bwd[j], 0, 1);
             if (rc) return rc;
             if (custom) {
@@ -601,10 +628,24 @@ int run_tail(b2nn_ctx* c, const StepPlan& sp, const b2nn_train_desc* d, const fl
     return B2NN_OK;
 }
 
+bool p2p_layer_was_fused(b2nn_ctx* c, int j) {
+    for (auto& kv : c->plans) if (int(kv.second.fused.size()) > j && kv.second.fused[j]) return true;
+    return false;
+}
+
 // One mini-batch step on device-resident data: forward, output, backward, momentum update.
 int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, int64_t ldx, int64_t x_total, bool x_aligned,
                const float* Y, int64_t ldy, int64_t x_start, int64_t rows, int64_t global_rows, double* cost_slot) {
     StepPlan& sp = get_plan(c, rows, X, ldx, x_total, x_aligned, prec, d->act_kind);
+    bool any_fused = false;
+    for (char f : sp.fused) any_fused = any_fused || f;
+    if (any_fused) {
+        ++c->p2p_step;
+        if (c->p2p_step > 1)       // every owner's rows of the previous step have landed in this rank's weights
+            for (size_t j = 0; j < sp.fused.size(); ++j)
+                if (sp.fused[j])
+                    B2_CUDA(p2p_gate_launch(c->p2p_flags + (1 * P2P_MAX_LAYERS + int(j)) * P2P_MAX_WORLD, c->nranks, c->p2p_step - 1, c->stream));
+    }
     int rc = forward_pass(c, sp, x_start, d);
     if (rc) return rc;
     if (sp.use_tail) rc = run_tail(c, sp, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
@@ -624,14 +665,30 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
         // gradient all-reduce per layer on the communication stream, issued in the order the gradients were produced
         for (int j = nw - 1; j >= 0; --j) {
             const LayerInfo& li = c->L[j];
+            if (sp.fused[j]) {
+                // owner side of the fused exchange, on its own stream: wait for every rank's partial rows, then reduce +
+                // update + all-gather this rank's R rows and tell everyone
+                const int64_t R = li.out / c->nranks, slice = R * li.ldw, off = li.w_off + int64_t(c->rank) * slice;
+                B2_CUDA(cudaStreamWaitEvent(c->upd_stream, c->p2p_wg_ev[j], 0));
+                B2_CUDA(p2p_gate_launch(c->p2p_flags + (0 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD, c->nranks, c->p2p_step, c->upd_stream));
+                B2_CUDA(p2p_reduce_update_launch(c->peers, c->G + li.w_off, slice, c->V + off, off, slice, d->momentum, alpha, c->upd_stream));
+                B2_CUDA(p2p_signal_launch(c->peers, (1 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD + c->rank, c->p2p_step, c->upd_stream));
+                c->launches += 3;
+                continue;
+            }
             B2_CUDA(cudaStreamWaitEvent(c->comm_stream, c->grad_ready[j], 0));
             float* gptr = c->G + li.w_off;
             int r = g_nccl.AllReduce(gptr, gptr, size_t(li.ldw) * li.out, NCCL_FLOAT32, NCCL_SUM, c->comm, c->comm_stream);
             if (r != 0) { set_error(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?")); return B2NN_ERR_CUDA; }
             B2_CUDA(cudaEventRecord(c->grad_reduced[j], c->comm_stream));
         }
+        if (any_fused) {
+            B2_CUDA(cudaEventRecord(c->p2p_upd_done, c->upd_stream));
+            B2_CUDA(cudaStreamWaitEvent(c->stream, c->p2p_upd_done, 0));
+        }
         for (int j = nw - 1; j >= 0; --j) {
             const LayerInfo& li = c->L[j];
+            if (sp.fused[j]) continue;
             B2_CUDA(cudaStreamWaitEvent(c->stream, c->grad_reduced[j], 0));
             {
                 ProfScope scope(c, 4, false, 0.0, 20.0 * double(li.ldw) * li.out);
@@ -772,6 +829,11 @@ void b2nn_destroy(b2nn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* p : c->p2p_opened) cudaIpcCloseMemHandle(p);
+    cudaFree(c->p2p_flags);
+    for (auto e : c->p2p_wg_ev) cudaEventDestroy(e);
+    if (c->p2p_upd_done) cudaEventDestroy(c->p2p_upd_done);
+    if (c->upd_stream) cudaStreamDestroy(c->upd_stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     c->ws.release();
     cudaFree(c->W); cudaFree(c->V); cudaFree(c->G); cudaFree(c->W_lo);
@@ -1085,6 +1147,11 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
         rc = flush_logs(false);
         if (rc) return rc;
     }
+    if (c->p2p && c->p2p_step > 0)
+        for (int j = 0; j < int(c->L.size()) && j < P2P_MAX_LAYERS; ++j)
+            if (c->L[j].out % (256 * c->nranks) == 0)       // gate only layers that can have been fused; unfused flags stay 0
+                if (p2p_layer_was_fused(c, j))
+                    B2_CUDA(p2p_gate_launch(c->p2p_flags + (1 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD, c->nranks, c->p2p_step, c->stream));
     B2_CUDA(cudaEventRecord(ev1, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     destroy_graphs();
@@ -1457,6 +1524,50 @@ int b2nn_comm_init(b2nn_ctx* c, int rank, int nranks, const void* id128) {
     const size_t nw = c->L.size() ? c->L.size() : 16;
     while (c->grad_ready.size() < nw) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->grad_ready.push_back(e); }
     while (c->grad_reduced.size() < nw) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->grad_reduced.push_back(e); }
+    return B2NN_OK;
+}
+
+int b2nn_comm_p2p_export(b2nn_ctx* c, void* blob192) {
+    if (!c || !blob192) { set_error("p2p_export: null argument"); return B2NN_ERR_ARG; }
+    if (!c->W || !c->G) { set_error("p2p_export: set_layers must come first"); return B2NN_ERR_ARG; }
+    if (c->nranks < 2 || c->nranks > P2P_MAX_WORLD) { set_error("p2p_export: needs 2..8 ranks (b2nn_comm_init first)"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    if (!c->p2p_flags) {
+        B2_CUDA(cudaMalloc(&c->p2p_flags, sizeof(int) * 2 * P2P_MAX_LAYERS * P2P_MAX_WORLD));
+        B2_CUDA(cudaMemset(c->p2p_flags, 0, sizeof(int) * 2 * P2P_MAX_LAYERS * P2P_MAX_WORLD));
+    }
+    cudaIpcMemHandle_t h[3];
+    B2_CUDA(cudaIpcGetMemHandle(&h[0], c->W));
+    B2_CUDA(cudaIpcGetMemHandle(&h[1], c->G));
+    B2_CUDA(cudaIpcGetMemHandle(&h[2], c->p2p_flags));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(blob192, h, 192);
+    return B2NN_OK;
+}
+
+int b2nn_comm_p2p_open(b2nn_ctx* c, const void* blobs) {
+    if (!c || !blobs) { set_error("p2p_open: null argument"); return B2NN_ERR_ARG; }
+    if (!c->p2p_flags) { set_error("p2p_open: call b2nn_comm_p2p_export first"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    const char* b = static_cast<const char*>(blobs);
+    c->peers.world = c->nranks; c->peers.rank = c->rank;
+    for (int r = 0; r < c->nranks; ++r) {
+        if (r == c->rank) { c->peers.W[r] = c->W; c->peers.G[r] = c->G; c->peers.flags[r] = c->p2p_flags; continue; }
+        cudaIpcMemHandle_t h[3];
+        std::memcpy(h, b + size_t(r) * 192, 192);
+        void* ptr[3] = {nullptr, nullptr, nullptr};
+        for (int i = 0; i < 3; ++i) {
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr[i], h[i], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { set_error(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); (void)cudaGetLastError(); return B2NN_ERR_CUDA; }
+            c->p2p_opened.push_back(ptr[i]);
+        }
+        c->peers.W[r] = static_cast<float*>(ptr[0]); c->peers.G[r] = static_cast<float*>(ptr[1]); c->peers.flags[r] = static_cast<int*>(ptr[2]);
+    }
+    if (!c->upd_stream) B2_CUDA(cudaStreamCreateWithFlags(&c->upd_stream, cudaStreamNonBlocking));
+    if (!c->p2p_upd_done) B2_CUDA(cudaEventCreateWithFlags(&c->p2p_upd_done, cudaEventDisableTiming));
+    while (c->p2p_wg_ev.size() < size_t(P2P_MAX_LAYERS)) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->p2p_wg_ev.push_back(e); }
+    c->p2p = true;
+    c->plans.clear();
     return B2NN_OK;
 }
 

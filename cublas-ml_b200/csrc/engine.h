@@ -38,6 +38,10 @@ struct GemmDesc {
     // fp32-grade tensor-core mode (3xTF32): low parts x - trunc_tf32(x) of both operands, same layout and leading
     // dimension as A / B; D_lo (optional) receives the low part of the output.  Null = plain tf32.
     const float* A_lo = nullptr; const float* B_lo = nullptr; float* D_lo = nullptr;
+    // Reduce-scatter fused into the epilogue (data parallel over peer memory): output rows n in [o*R, (o+1)*R) are stored
+    // into scatter_base[o] + ((rank - o) * R + n) * ldd + m, i.e. into owner o's arena, slice `rank`.  R % tile_n == 0.
+    float* scatter_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int scatter_world = 0, scatter_rank = 0, scatter_rows = 0;
 };
 
 // fp32 FFMA backend (gemm_simt.cu)
@@ -120,6 +124,20 @@ struct TailArgs {
 };
 bool tail_supported(int K, int H, bool want_inline_g);
 cudaError_t tail_launch(const TailArgs& a, bool train, cudaStream_t s);
+
+// ---- peer-memory data parallelism (p2p.cu) ---------------------------------------------------------------------------
+constexpr int P2P_MAX_WORLD = 8;
+constexpr int P2P_MAX_LAYERS = 64;
+struct P2pPeers {
+    float* W[P2P_MAX_WORLD];       // every rank's weight arena (own entry = local pointer)
+    float* G[P2P_MAX_WORLD];       // every rank's gradient arena
+    int*   flags[P2P_MAX_WORLD];   // every rank's flag block: [0, L) wg_done per (layer, src) ... see engine.cu
+    int world, rank;
+};
+cudaError_t p2p_gate_launch(const int* flags, int count, int value, cudaStream_t s);
+cudaError_t p2p_signal_launch(const P2pPeers& peers, int index, int value, cudaStream_t s);
+cudaError_t p2p_reduce_update_launch(const P2pPeers& peers, const float* partial, int64_t slice_floats, float* vel,
+                                     int64_t w_off, int64_t count, float mu, float alpha, cudaStream_t s);
 
 void set_error(const std::string& msg);
 

@@ -63,6 +63,8 @@ struct TcArgs {
     int stages;
     uint32_t mn_lbo, mn_sbo, mn_layout;   // MN-major descriptor: 4096 / 512 / type 1 (overridable for bring-up)
     int a_3d, b_3d;                 // MN-major operand fetched with one 3-D TMA box per tile
+    float* scatter_base[8];         // fused reduce-scatter: owner arenas (peer mappings); see GemmDesc
+    int scatter_world, scatter_rank, scatter_rows;
 };
 
 // Work item -> output tile.  Tiles are walked in groups of `group_m` row-tiles: inside a group the row-tile index is
@@ -323,6 +325,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 if (m_ok) {
                     float* dst = Dp + int64_t(n0 + c0) * p.ldd + m;
+                    if (p.scatter_world > 0) {
+                        // this tile's rows belong to rank `owner`: store into its arena over NVLink, slice = my rank
+                        const int owner = n0 / p.scatter_rows;
+                        dst = p.scatter_base[owner] + (int64_t(p.scatter_rank - owner) * p.scatter_rows + n0 + c0) * p.ldd + m;
+                    }
                     if (p.atomic) {
 #pragma unroll
                         for (int j = 0; j < CH; ++j) if (n0 + c0 + j < p.N) atomicAdd(dst + int64_t(j) * p.ldd, v[j]);
@@ -474,6 +481,7 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     if (g.b_major && bn < 32) bn = 32;     // an MN-major box is 32 floats wide
     plan.x3 = g.A_lo != nullptr && g.B_lo != nullptr;
     if (plan.x3 && bn > 128) bn = 128;     // four tiles per stage: 128 x 128 keeps three stages in flight
+    if (g.scatter_world > 0 && (g.scatter_rows % bn != 0 || plan.x3)) { err = "scatter rows not a multiple of the tile"; return false; }
     plan.block_n = bn;
     plan.g = g;
 
@@ -506,7 +514,8 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     if (usable_sms < 2 * ncta) usable_sms = 2 * ncta;
     const int64_t max_workers = usable_sms / ncta;
     int splits = 1;
-    if (g.epi == EPI_STORE && g.split_k > 1) splits = g.split_k;
+    if (g.scatter_world > 0) splits = 1;        // partial tiles travel as plain stores: no split-K
+    else if (g.epi == EPI_STORE && g.split_k > 1) splits = g.split_k;
     else if (g.epi == EPI_STORE && g.split_k == 0) {
         // auto split-K: few output tiles but a long K (weight gradients, the 10-column output layer).  Model: time ~
         // waves * (K blocks per item + fixed per-item cost); items beyond one wave only pay when they shorten it.
@@ -553,6 +562,8 @@ cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream) {
     TcArgs a;
     a.D = pl.g.D; a.ldd = pl.g.ldd; a.aux = pl.g.aux; a.ldaux = pl.g.ldaux;
     a.D_lo = pl.x3 ? pl.g.D_lo : nullptr;
+    for (int i = 0; i < 8; ++i) a.scatter_base[i] = pl.g.scatter_base[i];
+    a.scatter_world = pl.g.scatter_world; a.scatter_rank = pl.g.scatter_rank; a.scatter_rows = pl.g.scatter_rows;
     a.M = pl.g.M; a.N = pl.g.N;
     a.tiles_m = pl.tiles_m; a.tiles_n = pl.tiles_n; a.splits = pl.splits;
     {

@@ -55,3 +55,16 @@ def exchange_unique_id(make_id, rank: int, world: int) -> bytes:
     if not isinstance(uid, (bytes, bytearray)) or len(uid) != 128:
         raise RuntimeError("bad NCCL unique id")
     return bytes(uid)
+
+
+def enable_peer_exchange(net, rank: int, world: int) -> bool:
+    """Switch the large layers' gradient exchange from NCCL to the fused peer-memory path (b2nn_comm_p2p_*): every rank
+    exports its three CUDA IPC handles, the blobs are all-gathered in rank order, every rank opens its peers'."""
+    import torch.distributed as dist
+    if world < 2 or world > 8:
+        return False
+    mine = net.comm_p2p_export()
+    blobs = [None] * world
+    dist.all_gather_object(blobs, mine)
+    net.comm_p2p_open(b"".join(blobs))
+    return True

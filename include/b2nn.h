@@ -166,6 +166,13 @@ int b2nn_builtin_kind(const void* fn, int family);
 int b2nn_comm_unique_id(void* id128);
 int b2nn_comm_init(b2nn_ctx* ctx, int rank, int nranks, const void* id128);
 int b2nn_comm_barrier(b2nn_ctx* ctx);
+/* Optional: exchange the gradients of the large layers over NVLink peer memory instead of NCCL.  The weight-gradient
+ * GEMM stores each output tile directly into the arena of the rank that owns those rows (reduce-scatter fused into the
+ * epilogue); the owner's update kernel sums the partial slices, applies the momentum step and stores the new rows into
+ * every rank's weights (update fused with the all-gather).  Call after b2nn_comm_init and b2nn_set_layers, on every
+ * rank: export 192 bytes (three CUDA IPC handles), all-gather them in rank order with the host's own plumbing, open. */
+int b2nn_comm_p2p_export(b2nn_ctx* ctx, void* blob192);
+int b2nn_comm_p2p_open(b2nn_ctx* ctx, const void* blobs_world_x_192);
 
 /* ---- introspection ------------------------------------------------------------------------------------------ */
 /* Raw GEMM entry used by the kernel unit tests and the roofline benchmark: D(m,n) = sum_k A(m,k) B(n,k), D stored

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, name, prec_name, q):
+def _worker(rank, world, port, name, prec_name, p2p, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -33,6 +33,8 @@ def _worker(rank, world, port, name, prec_name, q):
         net = b2nn.Net(rank)
         net.set_layers(c.layers, c.init_kind, c.seed)
         net.comm_init(rank, world, dp.exchange_unique_id(b2nn.Net.comm_unique_id, rank, world))
+        if p2p:
+            assert dp.enable_peer_exchange(net, rank, world)
         xl, yl, ml = dp.shard_training_set(x_cm, y_cm, c.m, n1, K, c.batch_num, rank, world)
         net.set_train_data(xl, yl, ml)
         d = b2nn.make_desc(momentum=c.momentum, rate=c.rate, iters=c.iters, display=c.display, batch_num=c.batch_num,
@@ -42,14 +44,17 @@ def _worker(rank, world, port, name, prec_name, q):
         out = net.train(d)
         th = net.get_weights()
         net.comm_barrier()
-        q.put((rank, th, out.log_J, out.final_cost, out.error_count))
+        q.put((rank, th, out.log_J, out.final_cost, out.error_count, out.kernel_launches))
         net.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,prec", [("clf_tanh_softmax", "fp32"), ("wide_mini", "fp32"), ("wide_mini", "tf32")])
-def test_two_gpu_run_matches_single_gpu(b2nn, name, prec):
+@pytest.mark.parametrize("name,prec,p2p", [("clf_tanh_softmax", "fp32", False), ("wide_mini", "fp32", False),
+                                           ("wide_mini", "tf32", False), ("wide_mini", "tf32", True)])
+def test_two_gpu_run_matches_single_gpu(b2nn, name, prec, p2p):
+    """p2p = True: the first layer's gradient (512 rows = 2 ranks x 256-column tiles) takes the fused peer-memory path
+    (reduce-scatter in the GEMM epilogue, update + all-gather on the owner); the others stay on NCCL."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -58,7 +63,7 @@ def test_two_gpu_run_matches_single_gpu(b2nn, name, prec):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + (os.getpid() % 300)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, prec, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, prec, p2p, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
