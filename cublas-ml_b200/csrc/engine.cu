@@ -1253,7 +1253,6 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
     if (!x || !y || m < 1) { set_error("train_host: bad arguments"); return B2NN_ERR_ARG; }
     if (n_plus_1 != c->layers[0] + 1 || k != c->layers.back()) { set_error("data shape does not match the layers"); return B2NN_ERR_ARG; }
     if (d->batch_num < 1 || int64_t(d->batch_num) > m) { set_error("batch_num must be in [1, m]"); return B2NN_ERR_ARG; }
-    if (c->comm) { set_error("train_host: data-parallel streaming is not implemented (use b2nn_train)"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
     const int prec = resolve_precision(d->precision);
     const int n = n_plus_1 - 1, nb = d->batch_num;
@@ -1296,6 +1295,21 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
     B2_CUDA(cudaStreamSynchronize(c->stream));                 // staging buffers initialised before the copy stream touches them
 
     auto batch_rows = [&](int b) { return b == nb - 1 ? last_rows : bs; };
+    // data parallel: every rank streams its own shard; the update uses the GLOBAL rows of each batch
+    std::vector<int64_t> global_rows(nb);
+    for (int b = 0; b < nb; ++b) global_rows[b] = batch_rows(b);
+    if (c->comm) {
+        int64_t* tmp = nullptr;
+        B2_CUDA(cudaMalloc(&tmp, sizeof(int64_t) * nb));
+        B2_CUDA(cudaMemcpyAsync(tmp, global_rows.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice, c->stream));
+        int r = g_nccl.AllReduce(tmp, tmp, size_t(nb), NCCL_INT64, NCCL_SUM, c->comm, c->stream);
+        if (r != 0) { cudaFree(tmp); set_error("ncclAllReduce(batch rows) failed"); return B2NN_ERR_CUDA; }
+        B2_CUDA(cudaMemcpyAsync(global_rows.data(), tmp, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(tmp);
+        while (c->grad_ready.size() < c->L.size()) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->grad_ready.push_back(e); }
+        while (c->grad_reduced.size() < c->L.size()) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->grad_reduced.push_back(e); }
+    }
     auto issue_copy = [&](int64_t s) -> int {                   // H2D of step s's batch into staging buffer s & 1
         const int buf = int(s & 1), b = int(s % nb);
         const int64_t rows = batch_rows(b), start = int64_t(b) * bs;
@@ -1320,12 +1334,16 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
         if (s + 1 < steps) { rc = issue_copy(s + 1); if (rc) return rc; }      // next batch travels while this one computes
         B2_CUDA(cudaStreamWaitEvent(c->stream, c->st_copied[buf], 0));
         if (x3) B2_CUDA(split_lo_launch(c->Xst[buf], lo_buffer(c, c->Xst[buf], c->ldst * int64_t(n_plus_1)), c->ldst * int64_t(n_plus_1), c->stream));
-        rc = train_step(c, d, prec, c->Xst[buf], c->ldst, c->ldst, true, c->Yst[buf], c->ldst, 0, batch_rows(b), batch_rows(b),
+        rc = train_step(c, d, prec, c->Xst[buf], c->ldst, c->ldst, true, c->Yst[buf], c->ldst, 0, batch_rows(b), global_rows[b],
                         c->d_jsteps + s);
         if (rc) return rc;
         B2_CUDA(cudaEventRecord(c->st_consumed[buf], c->stream));
         B2_CUDA(cudaMemcpyAsync(c->h_jsteps + s, c->d_jsteps + s, sizeof(double), cudaMemcpyDeviceToHost, c->stream));   // this step's loss
     }
+    if (c->p2p && c->p2p_step > 0)
+        for (int j = 0; j < int(c->L.size()) && j < P2P_MAX_LAYERS; ++j)
+            if (p2p_layer_was_fused(c, j))
+                B2_CUDA(p2p_gate_launch(c->p2p_flags + (1 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD, c->nranks, c->p2p_step, c->stream));
     B2_CUDA(cudaEventRecord(ev1, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     float ms = 0.f;

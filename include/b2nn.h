@@ -138,7 +138,8 @@ int b2nn_reset_velocity(b2nn_ctx* ctx);
  * the compute of batch b.  x: m x n_plus_1 (ones column first), y: m x k, column-major HOST buffers (pinned memory
  * gives the full PCIe rate).  J_steps (optional, iters*batch_num floats): the cost of EVERY step, each read back with
  * its own asynchronous D2H.  No final cost pass (the data is not resident); velocity is zeroed at entry like
- * train*Momentum (cublasNN.cpp:533-534). */
+ * train*Momentum (cublasNN.cpp:533-534).  Data parallel: every rank streams its own shard (its rows of every batch);
+ * J_steps then holds the mean cost of the rank's rows. */
 int b2nn_train_host(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x, const float* y, int64_t m, int n_plus_1,
                     int k, float* J_steps, b2nn_train_result* result);
 
