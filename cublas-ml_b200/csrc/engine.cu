@@ -152,6 +152,9 @@ struct b2nn_ctx {
     cudaEvent_t st_copied[2] = {nullptr, nullptr}, st_consumed[2] = {nullptr, nullptr};
     double* d_jsteps = nullptr; double* h_jsteps = nullptr; int64_t jsteps_cap = 0;
 
+    // staging of b2nn_predict (kept between calls: small-batch inference is otherwise dominated by cudaMalloc/cudaFree)
+    float* pr_x = nullptr; float* pr_p = nullptr; float* pr_h = nullptr; int64_t pr_ld = 0; int pr_n = 0, pr_k = 0;
+
     // host-step staging (b2nn_train_step_host)
     float* Xs = nullptr; float* Ys = nullptr; int64_t lds = 0, caps = 0;
 
@@ -354,7 +357,10 @@ void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
     }
     // tcgen05 only where tensor cores pay: below ~2^26 multiply-adds a contraction is launch / HBM bound and stays on
     // the exact fp32 FFMA kernel (the bikeshare-sized nets of config C2 never leave fp32).
-    if ((prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3) && work >= double(1 << 26) && g.M >= 32) {
+    // ... except long-K contractions with few rows (small-batch inference on a wide input, config C5): the FFMA kernel
+    // would walk K serially in a single block, the tcgen05 pipeline streams it in a few microseconds.
+    const bool long_k_few_rows = !allow_split && g.a_major == 1 && g.b_major == 0 && g.K >= 512 && work >= double(1 << 15);
+    if ((prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3) && (work >= double(1 << 26) || long_k_few_rows)) {
         std::string err;
         const int requested = g.split_k;
         if (g.epi == EPI_STORE && (allow_split || g.N <= 32)) g.split_k = 0;     // let the tcgen05 plan pick the split
@@ -840,6 +846,7 @@ void b2nn_destroy(b2nn_ctx* c) {
     for (auto& kv : c->lo_cache) cudaFree(kv.second.first);
     cudaFree(c->X); cudaFree(c->Y); cudaFree(c->Xs); cudaFree(c->Ys); cudaFree(c->Xsp); cudaFree(c->Ysp);
     cudaFree(c->d_acc);
+    cudaFree(c->pr_x); cudaFree(c->pr_p); cudaFree(c->pr_h);
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->Xst[i]); cudaFree(c->Yst[i]);
         if (c->st_copied[i]) cudaEventDestroy(c->st_copied[i]);
@@ -1407,27 +1414,32 @@ int b2nn_predict(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, int64_t 
     const int prec = resolve_precision(d->precision);
     const int n = c->layers[0], K = c->layers.back();
     const int64_t ld = round_up(rows, 32);
-    float *xd = nullptr, *pd = nullptr, *hd = nullptr;
-    B2_CUDA(cudaMalloc(&xd, sizeof(float) * ld * (n + 1)));
-    B2_CUDA(cudaMalloc(&pd, sizeof(float) * ld));
-    B2_CUDA(cudaMalloc(&hd, sizeof(float) * ld * K));
-    B2_CUDA(cudaMemsetAsync(xd, 0, sizeof(float) * ld * (n + 1), c->stream));
-    rc = stage_x_from_host(c, x, rows, 0, rows, n, xd, ld, true);
-    if (!rc) rc = evaluate_device(c, d, prec, xd, ld, nullptr, 0, nullptr, rows, d->classify ? pd : nullptr, hd, ld, nullptr, nullptr);
+    if (ld > c->pr_ld || n != c->pr_n || K != c->pr_k) {
+        drop_lo(c, c->pr_x);
+        cudaFree(c->pr_x); cudaFree(c->pr_p); cudaFree(c->pr_h); c->pr_x = c->pr_p = c->pr_h = nullptr; c->pr_ld = 0;
+        c->plans.clear();
+        B2_CUDA(cudaMalloc(&c->pr_x, sizeof(float) * ld * (n + 1)));
+        B2_CUDA(cudaMalloc(&c->pr_p, sizeof(float) * ld));
+        B2_CUDA(cudaMalloc(&c->pr_h, sizeof(float) * ld * K));
+        c->pr_ld = ld; c->pr_n = n; c->pr_k = K;
+        B2_CUDA(cudaMemsetAsync(c->pr_x, 0, sizeof(float) * ld * (n + 1), c->stream));
+        B2_CUDA(fill_launch(c->pr_x + int64_t(n) * ld, 1.0f, ld, c->stream));
+    }
+    float *xd = c->pr_x, *pd = c->pr_p, *hd = c->pr_h;
+    const int64_t ldp = c->pr_ld;
+    rc = stage_x_from_host(c, x, rows, 0, rows, n, xd, ldp, false);
+    if (!rc) rc = evaluate_device(c, d, prec, xd, ldp, nullptr, 0, nullptr, rows, d->classify ? pd : nullptr, hd, ldp, nullptr, nullptr);
     if (!rc) {
         cudaError_t e;
         if (d->classify) e = cudaMemcpyAsync(out, pd, sizeof(float) * rows, cudaMemcpyDeviceToHost, c->stream);
-        else e = cudaMemcpy2DAsync(out, sizeof(float) * rows, hd, sizeof(float) * ld, sizeof(float) * rows, size_t(K),
+        else e = cudaMemcpy2DAsync(out, sizeof(float) * rows, hd, sizeof(float) * ldp, sizeof(float) * rows, size_t(K),
                                    cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess && probs)
-            e = cudaMemcpy2DAsync(probs, sizeof(float) * rows, hd, sizeof(float) * ld, sizeof(float) * rows, size_t(K),
+            e = cudaMemcpy2DAsync(probs, sizeof(float) * rows, hd, sizeof(float) * ldp, sizeof(float) * rows, size_t(K),
                                   cudaMemcpyDeviceToHost, c->stream);
         if (e != cudaSuccess) { set_error(std::string("predict copy back: ") + cudaGetErrorString(e)); rc = B2NN_ERR_CUDA; }
     }
     cudaStreamSynchronize(c->stream);
-    c->plans.clear();
-    drop_lo(c, xd);
-    cudaFree(xd); cudaFree(pd); cudaFree(hd);
     return rc;
 }
 

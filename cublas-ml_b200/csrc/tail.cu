@@ -202,6 +202,158 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const TailArgs p) {
     }
 }
 
+
+// Small hidden layer (H+1 <= 512, K*(H+1) <= 8192 floats: configs C1, C2, C5): the whole W lives in shared memory and
+// ONE WARP owns a group of 32 samples end to end — no block-level synchronisation per group (the kernel above spends
+// its time in __syncthreads when each of its 16 warps only has three rows of a to read).  The second read of a hits L1.
+constexpr int SMALL_THREADS = 128;
+template <int KMAX, bool TRAIN>
+__global__ void __launch_bounds__(SMALL_THREADS) tail_small_kernel(const TailArgs p) {
+    extern __shared__ float smem[];
+    const int K = p.K, H1 = p.H + 1;
+    float* W_s = smem;                    // [K][H1]
+    float* G_s = W_s + K * H1;            // [K][H1] when the gradient is accumulated in-kernel
+    const bool inline_g = TRAIN && p.G_inline != nullptr;
+    for (int idx = threadIdx.x; idx < K * H1; idx += SMALL_THREADS) {
+        const int k = idx / H1, h = idx - k * H1;
+        W_s[idx] = __ldg(p.W + int64_t(k) * p.ldw + h);
+        if (inline_g) G_s[idx] = 0.f;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = int64_t(blockIdx.x) * (SMALL_THREADS / 32) + (threadIdx.x >> 5);
+    const int64_t n_warps = int64_t(gridDim.x) * (SMALL_THREADS / 32);
+    const int64_t n_groups = (p.rows + 31) / 32;
+    double cost = 0.0, err = 0.0;
+    for (int64_t grp = warp_global; grp < n_groups; grp += n_warps) {
+        const int64_t i = grp * 32 + lane;
+        const bool ok = i < p.rows;
+        const int64_t ic = ok ? i : p.rows - 1;
+        const float* ap = p.a + ic;
+        float z[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) z[k] = 0.f;
+        int h = 0;
+        for (; h + 8 <= H1; h += 8) {
+            float av[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) av[u] = __ldg(ap + int64_t(h + u) * p.lda);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) if (k < K) z[k] = fmaf(av[u], W_s[k * H1 + h + u], z[k]);
+        }
+        for (; h < H1; ++h) {
+            const float av = __ldg(ap + int64_t(h) * p.lda);
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) if (k < K) z[k] = fmaf(av, W_s[k * H1 + h], z[k]);
+        }
+        float zmax = -INFINITY, total = 0.f;
+        if (p.out_kind == B2NN_OUT_SOFTMAX) {
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) if (k < K) zmax = fmaxf(zmax, z[k]);
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) if (k < K) total += expf(z[k] - zmax);
+        }
+        float dl[KMAX];
+        float best_h = 0.f, best_y = 0.f; int arg_h = 0, arg_y = 0;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            dl[k] = 0.f;
+            if (k < K) {
+                float hv;
+                if (p.out_kind == B2NN_OUT_SOFTMAX) hv = expf(z[k] - zmax) / total;
+                else if (p.out_kind == B2NN_OUT_SIGMOID) hv = sigmoid_f(z[k]);
+                else hv = z[k];
+                if (hv > best_h) { best_h = hv; arg_h = k; }
+                float yv = 0.f;
+                if (p.Y) {
+                    yv = __ldg(p.Y + int64_t(k) * p.ldy + ic);
+                    if (yv > best_y) { best_y = yv; arg_y = k; }
+                }
+                const float dv = hv - yv;
+                if (ok) {
+                    dl[k] = dv;
+                    if (p.h_out) p.h_out[int64_t(k) * p.ldh + i] = hv;
+                    if (p.delta_last) p.delta_last[int64_t(k) * p.ldd + i] = dv;
+                    if (p.cost_sum && p.Y) {
+                        float c = 0.f;
+                        if (p.cost_kind == B2NN_COST_SQUARED) c = dv * dv;
+                        else {
+                            if (yv != 0.f) c += -yv * logf(hv);
+                            if (p.cost_kind == B2NN_COST_NEGLNMAX && yv != 1.f) c += -(1.f - yv) * logf(1.f - hv);
+                            c = fabsf(c);
+                        }
+                        cost += double(c);
+                    }
+                }
+            }
+        }
+        if (ok) {
+            if (p.pred) p.pred[i] = float(arg_h);
+            if (p.err_sum) {
+                if (p.y_labels) err += (float(arg_h) != __ldg(p.y_labels + i)) ? 1.0 : 0.0;
+                else if (p.Y) err += (arg_h != arg_y) ? 1.0 : 0.0;
+            }
+        }
+        if (TRAIN) {
+            for (int hh = 0; hh < H1; ++hh) {
+                const float av = __ldg(ap + int64_t(hh) * p.lda);          // L1 hit: read in pass 1 by the same warp
+                if (hh < p.H && p.delta_prev) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) if (k < K) s = fmaf(dl[k], W_s[k * H1 + hh], s);
+                    const float d = (p.act_kind == B2NN_ACT_SIGMOID) ? av * (1.0f - av) : 1.0f - av * av;
+                    if (ok) p.delta_prev[int64_t(hh) * p.ldp + i] = s * d;
+                }
+                if (inline_g) {
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) {
+                        if (k < K) {
+                            float v = dl[k] * av;
+                            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                            if (lane == 0) atomicAdd(&G_s[k * H1 + hh], v);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (p.cost_sum || p.err_sum) {
+        for (int o = 16; o > 0; o >>= 1) {
+            cost += __shfl_xor_sync(0xffffffffu, cost, o);
+            err += __shfl_xor_sync(0xffffffffu, err, o);
+        }
+        if (lane == 0) {
+            if (p.cost_sum && cost != 0.0) atomicAdd(p.cost_sum, cost);
+            if (p.err_sum && err != 0.0) atomicAdd(p.err_sum, err);
+        }
+    }
+    if (inline_g) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < K * H1; idx += SMALL_THREADS) {
+            const int k = idx / H1, h = idx - k * H1;
+            const float v = G_s[idx];
+            if (v != 0.f) atomicAdd(p.G_inline + int64_t(k) * p.ldw + h, v);
+        }
+    }
+}
+
+template <int KMAX>
+cudaError_t launch_small(const TailArgs& a, bool train, unsigned grid, size_t smem, cudaStream_t s) {
+    if (train) {
+        static bool set = false;
+        if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_small_kernel<KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e != cudaSuccess) return e; set = true; }
+        tail_small_kernel<KMAX, true><<<grid, SMALL_THREADS, smem, s>>>(a);
+    } else {
+        static bool set = false;
+        if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_small_kernel<KMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e != cudaSuccess) return e; set = true; }
+        tail_small_kernel<KMAX, false><<<grid, SMALL_THREADS, smem, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
 template <int KMAX>
 cudaError_t launch_k(const TailArgs& a, bool train, unsigned grid, size_t smem, cudaStream_t s) {
     if (train) {
@@ -230,6 +382,22 @@ bool tail_supported(int K, int H, bool want_inline_g) {
 cudaError_t tail_launch(const TailArgs& a, bool train, cudaStream_t s) {
     if (a.rows <= 0) return cudaSuccess;
     const int kmax = a.K <= 4 ? 4 : a.K <= 16 ? 16 : 32;
+    // Forward-only calls take the warp-per-group kernel (C5 at 2^20 rows: 1121 -> 335 us).  Training keeps the
+    // block-cooperative kernel: its in-kernel gradient reduction is spread over 16 warps instead of serialised in one
+    // (C1: 28 us against 142 us).
+    if (!train && a.H + 1 <= 512 && int64_t(a.K) * (a.H + 1) <= 8192) {
+        const bool ig = train && a.G_inline != nullptr;
+        const size_t sm = sizeof(float) * size_t(a.K) * (a.H + 1) * (ig ? 2 : 1);
+        const int64_t grp = (a.rows + 31) / 32;
+        const int64_t blocks = (grp + SMALL_THREADS / 32 - 1) / (SMALL_THREADS / 32);
+        const int64_t capb = ig ? 148 * 2 : 148 * 16;
+        const unsigned g = unsigned(blocks < capb ? blocks : capb);
+        switch (kmax) {
+            case 4:  return launch_small<4>(a, train, g, sm, s);
+            case 16: return launch_small<16>(a, train, g, sm, s);
+            default: return launch_small<32>(a, train, g, sm, s);
+        }
+    }
     size_t smem = sizeof(float) * (size_t(kmax) * (HC + 1) + size_t(TAIL_WARPS) * kmax * 32);
     const bool inline_g = train && a.G_inline != nullptr;
     if (inline_g) smem += sizeof(float) * size_t(a.K) * (a.H + 1);

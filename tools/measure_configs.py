@@ -176,6 +176,13 @@ def main():
                 us = e0.elapsed_time(e1) / reps * 1e3
                 emit(config="C5", impl="ours", mode=name, batch=Bn, us=round(us, 2), samples_per_s=round(Bn / us * 1e6),
                      hbm_gbs=round(Bn * 3144 / us / 1e3, 1))
+                if os.environ.get("B2NN_MEASURE_PROFILE") and Bn >= 65536:
+                    net.profile_enable(True)
+                    for _ in range(3):
+                        net.predict_device(d, xd.data_ptr(), Bn, ld, outd.data_ptr())
+                    prof = net.profile_read()
+                    net.profile_enable(False)
+                    print(json.dumps({"c5_profile_us": {k: round(v["ms"] * 1e3 / 3, 1) for k, v in prof.items() if v["launches"]}}), flush=True)
                 # end to end through b2nn_predict (host rows in, class ids out)
                 if name == "tf32" and Bn in (1, 1024, 65536, 1 << 20):
                     xh = np.random.default_rng(0).standard_normal((785, Bn)).astype(np.float32)
