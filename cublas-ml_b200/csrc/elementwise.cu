@@ -167,6 +167,18 @@ __global__ void __launch_bounds__(256) momentum_update_lo_kernel(float* __restri
     }
 }
 
+__global__ void __launch_bounds__(256) abs_sum_kernel(const float* __restrict__ J, int64_t ld, int64_t rows, int K, double* out) {
+    __shared__ double sh[8];
+    double s = 0.0;
+    const int64_t total = rows * K, stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int64_t k = e / rows, i = e - k * rows;
+        s += double(fabsf(J[k * ld + i]));
+    }
+    const double t = block_sum(s, sh);
+    if (threadIdx.x == 0 && t != 0.0) atomicAdd(out, t);
+}
+
 __global__ void fill_kernel(float* p, float v, int64_t count) {
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) p[i] = v;
@@ -257,6 +269,12 @@ cudaError_t momentum_update_lo_launch(float* theta, float* vel, const float* gra
     if (count <= 0) return cudaSuccess;
     const int64_t want = (count + 255) / 256;
     momentum_update_lo_kernel<<<unsigned(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(theta, vel, grad, theta_lo, count, mu, alpha);
+    return cudaGetLastError();
+}
+cudaError_t abs_sum_launch(const float* J, int64_t ld, int64_t rows, int K, double* out, cudaStream_t s) {
+    if (rows <= 0 || K <= 0) return cudaSuccess;
+    const int64_t want = (rows * K + 255) / 256;
+    abs_sum_kernel<<<unsigned(want < 296 ? want : 296), 256, 0, s>>>(J, ld, rows, K, out);
     return cudaGetLastError();
 }
 cudaError_t fill_launch(float* p, float v, int64_t count, cudaStream_t s) {

@@ -72,6 +72,7 @@ struct Workspace {
     float* z_last = nullptr;     // K rows
     float* scratch = nullptr;    // custom path: act'(z) / product
     std::vector<float*> a_lo, delta_lo;   // fp32-grade tensor-core mode: x - trunc_tf32(x) of a / delta (same shapes)
+    float *hbuf = nullptr, *ybuf = nullptr, *jbuf = nullptr;   // custom output activation / cost: h, compact y, per-element J
     void release() {
         for (float* p : a) cudaFree(p);
         for (float* p : delta) cudaFree(p);
@@ -79,7 +80,8 @@ struct Workspace {
         for (float* p : a_lo) cudaFree(p);
         for (float* p : delta_lo) cudaFree(p);
         a_lo.clear(); delta_lo.clear();
-        cudaFree(z_last); cudaFree(scratch);
+        cudaFree(z_last); cudaFree(scratch); cudaFree(hbuf); cudaFree(ybuf); cudaFree(jbuf);
+        hbuf = ybuf = jbuf = nullptr;
         a.clear(); delta.clear(); z.clear(); z_last = nullptr; scratch = nullptr; cap = ld = 0;
     }
 };
@@ -163,7 +165,7 @@ struct b2nn_ctx {
     int plans_prec = -1;
     const float* plans_x = nullptr;
     int64_t plans_ldx = 0, plans_xtotal = 0;
-    bool plans_xaligned = false;
+    bool plans_xaligned = false, plans_notail = false;
     int plans_act = -1;
 
     double* d_acc = nullptr;             // device accumulators: [0] cost, [1] errors, [2..] display slots
@@ -385,12 +387,12 @@ void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
 // every batch of the same size; the batch start only moves the TMA coordinates (run_gemm).
 // x_aligned: every batch start passed to run_gemm is a multiple of 32 samples (one 3-D TMA box per X tile).
 StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64_t x_total, bool x_aligned, int prec,
-                   int act_kind) {
+                   int act_kind, bool no_tail_arg = false) {
     if (c->plans_prec != prec || c->plans_ldx != ldx || c->plans_act != act_kind || c->plans_xtotal != x_total ||
-        c->plans_xaligned != x_aligned) {
+        c->plans_xaligned != x_aligned || c->plans_notail != no_tail_arg) {
         c->plans.clear();
         c->plans_prec = prec; c->plans_ldx = ldx; c->plans_act = act_kind; c->plans_xtotal = x_total;
-        c->plans_xaligned = x_aligned;
+        c->plans_xaligned = x_aligned; c->plans_notail = no_tail_arg;
     }
     const auto key = std::make_pair(rows, X);
     auto it = c->plans.find(key);
@@ -408,7 +410,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
     sp.fused.assign(nw, 0);
     {
         const LayerInfo& last = c->L[nw - 1];
-        const bool no_tail = std::getenv("B2NN_NO_TAIL") != nullptr;
+        const bool no_tail = no_tail_arg || std::getenv("B2NN_NO_TAIL") != nullptr;
         sp.use_tail = !custom && !no_tail && tail_supported(last.out, last.in, false);
         sp.tail_inline_g = sp.use_tail && tail_supported(last.out, last.in, true);
     }
@@ -599,6 +601,59 @@ int output_and_delta(b2nn_ctx* c, const b2nn_train_desc* d, const float* Y, int6
     return B2NN_OK;
 }
 
+bool custom_outcost(const b2nn_train_desc* d) {
+    return d->classify && (d->out_kind == B2NN_OUT_CUSTOM || d->cost_kind == B2NN_COST_CUSTOM);
+}
+
+// User-supplied output activation and / or cost (function pointers of cublasNN.h:49-50): z_last is materialised, the
+// user's host functions are called on device buffers exactly like the reference calls them (cublasNN.cpp:606, 613, 731-733;
+// legacy default stream, ordered with the blocking engine stream), the rest stays in the fused output kernel.
+// The matrices handed to the user functions have `ld` rows (>= rows, padding rows hold garbage that is never read back).
+int output_custom(b2nn_ctx* c, const b2nn_train_desc* d, const float* Y, int64_t ldy, int64_t rows, bool train,
+                  double* cost_slot, double* err_slot, const float* labels, float* pred, float* probs, int64_t ldp) {
+    const int nl = int(c->layers.size());
+    Workspace& w = c->ws;
+    const int K = c->layers[nl - 1];
+    const int64_t cnt = int64_t(K) * w.ld;
+    if (cnt > INT32_MAX) { set_error("custom output / cost: element count exceeds int"); return B2NN_ERR_ARG; }
+    if (d->out_kind == B2NN_OUT_CUSTOM && !d->out_fn) { set_error("custom output activation needs out_fn"); return B2NN_ERR_ARG; }
+    if (d->cost_kind == B2NN_COST_CUSTOM && cost_slot && !d->cost_fn) { set_error("custom cost needs cost_fn"); return B2NN_ERR_ARG; }
+    if (!w.hbuf) {
+        B2_CUDA(cudaMalloc(&w.hbuf, sizeof(float) * cnt));
+        B2_CUDA(cudaMalloc(&w.ybuf, sizeof(float) * cnt));
+        B2_CUDA(cudaMalloc(&w.jbuf, sizeof(float) * cnt));
+        B2_CUDA(cudaMemsetAsync(w.ybuf, 0, sizeof(float) * cnt, c->stream));
+    }
+    OutputArgs a{};
+    if (d->out_kind == B2NN_OUT_CUSTOM) {
+        d->out_fn(w.z_last, w.hbuf, int(w.ld), K);
+    } else {
+        a.z = w.z_last; a.ldz = w.ld; a.h = w.hbuf; a.ldh = w.ld; a.rows = rows; a.K = K;
+        a.out_kind = d->out_kind; a.cost_kind = B2NN_COST_CROSSENTROPY;
+        B2_CUDA(output_layer_launch(a, c->stream));
+        ++c->launches;
+    }
+    const bool builtin_cost = d->cost_kind != B2NN_COST_CUSTOM;
+    a = OutputArgs{};
+    a.z = w.hbuf; a.ldz = w.ld;                     // identity "activation" over the user's h
+    a.y = Y; a.ldy = ldy;
+    a.h = probs; a.ldh = ldp;
+    a.delta = train ? w.delta[nl - 2] : nullptr; a.ldd = w.ld;
+    a.cost_sum = (builtin_cost && Y) ? cost_slot : nullptr;
+    a.pred = pred; a.err_sum = err_slot; a.y_labels = labels;
+    a.rows = rows; a.K = K; a.out_kind = B2NN_OUT_LINEAR; a.cost_kind = builtin_cost ? d->cost_kind : B2NN_COST_CROSSENTROPY;
+    B2_CUDA(output_layer_launch(a, c->stream));
+    ++c->launches;
+    if (!builtin_cost && cost_slot && Y) {
+        B2_CUDA(cudaMemcpy2DAsync(w.ybuf, sizeof(float) * w.ld, Y, sizeof(float) * ldy, sizeof(float) * rows, size_t(K),
+                                  cudaMemcpyDeviceToDevice, c->stream));
+        d->cost_fn(w.hbuf, w.ybuf, w.jbuf, int(cnt));
+        B2_CUDA(abs_sum_launch(w.jbuf, w.ld, rows, K, cost_slot, c->stream));      // cublasSasum over the valid rows (:614, :734)
+        ++c->launches;
+    }
+    return B2NN_OK;
+}
+
 // The fused last layer (tail.cu).  Training: z, h, delta_last, cost, delta_prev [, G_last].  Evaluation: z, h, cost,
 // argmax, error count.
 int run_tail(b2nn_ctx* c, const StepPlan& sp, const b2nn_train_desc* d, const float* Y, int64_t ldy, int64_t rows, bool train,
@@ -642,7 +697,8 @@ bool p2p_layer_was_fused(b2nn_ctx* c, int j) {
 // One mini-batch step on device-resident data: forward, output, backward, momentum update.
 int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, int64_t ldx, int64_t x_total, bool x_aligned,
                const float* Y, int64_t ldy, int64_t x_start, int64_t rows, int64_t global_rows, double* cost_slot) {
-    StepPlan& sp = get_plan(c, rows, X, ldx, x_total, x_aligned, prec, d->act_kind);
+    const bool custom_oc = custom_outcost(d);
+    StepPlan& sp = get_plan(c, rows, X, ldx, x_total, x_aligned, prec, d->act_kind, custom_oc);
     bool any_fused = false;
     for (char f : sp.fused) any_fused = any_fused || f;
     if (any_fused) {
@@ -654,7 +710,8 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
     }
     int rc = forward_pass(c, sp, x_start, d);
     if (rc) return rc;
-    if (sp.use_tail) rc = run_tail(c, sp, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
+    if (custom_oc) rc = output_custom(c, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
+    else if (sp.use_tail) rc = run_tail(c, sp, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
     else rc = output_and_delta(c, d, Y + x_start, ldy, rows, cost_slot);
     if (rc) return rc;
     if (prec == B2NN_PREC_TF32X3 && !c->ws.delta_lo.empty()) {
@@ -741,15 +798,18 @@ int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float
     const int64_t chunk = rows <= c->ws.cap ? c->ws.cap : std::max<int64_t>(32, c->ws.cap / 32 * 32);
     const int out_kind = d->classify ? d->out_kind : B2NN_OUT_LINEAR;
     const int cost_kind = d->classify ? d->cost_kind : B2NN_COST_SQUARED;
-    if (out_kind == B2NN_OUT_CUSTOM || cost_kind == B2NN_COST_CUSTOM) {
-        set_error("custom output activation / cost function pointers are not supported by the fused output kernel yet");
-        return B2NN_ERR_ARG;
-    }
     for (int64_t s = 0; s < rows; s += chunk) {
         const int64_t r = std::min<int64_t>(chunk, rows - s);
-        StepPlan& sp = get_plan(c, r, X, ldx, rows, true, prec, d->act_kind);
+        StepPlan& sp = get_plan(c, r, X, ldx, rows, true, prec, d->act_kind, custom_outcost(d));
         rc = forward_pass(c, sp, s, d);
         if (rc) return rc;
+        if (custom_outcost(d)) {
+            rc = output_custom(c, d, Y ? Y + s : nullptr, ldy, r, false, (Y && cost) ? c->d_acc : nullptr,
+                               (d->classify && errors && (Y || labels)) ? c->d_acc + 1 : nullptr, labels ? labels + s : nullptr,
+                               pred_out ? pred_out + s : nullptr, probs_out ? probs_out + s : nullptr, ldp);
+            if (rc) return rc;
+            continue;
+        }
         if (sp.use_tail) {
             rc = run_tail(c, sp, d, Y ? Y + s : nullptr, ldy, r, false, (Y && cost) ? c->d_acc : nullptr,
                           (d->classify && errors && (Y || labels)) ? c->d_acc + 1 : nullptr, labels ? labels + s : nullptr,
@@ -1089,7 +1149,7 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
     // remaining epochs replay a captured CUDA graph of the whole epoch (one variant with, one without the cost of batch 0).
     double step_work = 0.0;
     for (const LayerInfo& li : c->L) step_work += 6.0 * double(last_rows) * double(li.in + 1) * double(li.out);
-    bool use_graph = !c->comm && d->act_kind != B2NN_ACT_CUSTOM && !c->profile && nb <= 128 && d->iters > 2 &&
+    bool use_graph = !c->comm && d->act_kind != B2NN_ACT_CUSTOM && !custom_outcost(d) && !c->profile && nb <= 128 && d->iters > 2 &&
                      step_work < 2e10;
     if (const char* e = std::getenv("B2NN_GRAPH")) use_graph = use_graph && std::atoi(e) != 0;
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};     // [0] no cost, [1] batch 0 reports its cost

@@ -96,6 +96,8 @@ cudaError_t theta_internal_to_ref_launch(const float* w, float* ref, int in, int
 cudaError_t stage_x_launch(const float* x_ref, int64_t ld_ref, float* x_int, int64_t ld_int, int64_t rows, int n,
                            cudaStream_t s);
 cudaError_t fill_launch(float* p, float v, int64_t count, cudaStream_t s);
+// *out += sum |J[k*ld + i]| over i < rows, k < K   (cublasSasum over the valid region, double accumulator)
+cudaError_t abs_sum_launch(const float* J, int64_t ld, int64_t rows, int K, double* out, cudaStream_t s);
 // lo[i] = x[i] - trunc_tf32(x[i])  (exact; what tcgen05 kind::tf32 drops from x)
 cudaError_t split_lo_launch(const float* x, float* lo, int64_t count, cudaStream_t s);
 // momentum update that also refreshes the low parts of the weights

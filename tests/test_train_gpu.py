@@ -279,3 +279,100 @@ def test_c3_full_size_one_step_against_fp64(b2nn, oracle, prec):
         # and theta itself to fp32 resolution of the update
         assert float((got - wn).abs().max()) <= rel * denom + 2e-7
     net.close()
+
+
+def test_error_paths_fail_loudly(b2nn):
+    """Call-order and argument errors are undefined behaviour in the reference (cublasNN.cpp:137, 657, main.cpp:125);
+    here every one of them returns a status and a message, and the context stays usable."""
+    net = b2nn.Net()
+    with pytest.raises(b2nn.B2nnError):
+        net.set_layers([4, 3], 1, 1)                      # no hidden layer (reference dereferences aPos[-1], :657)
+    with pytest.raises(b2nn.B2nnError):
+        net.layers = [4, 3, 2]
+        net.set_train_data(np.zeros(5 * 5, np.float32), np.zeros(5 * 2, np.float32), 5)   # set_layers never succeeded
+    net.set_layers([4, 3, 2], 1, 1)
+    with pytest.raises(b2nn.B2nnError):
+        net.train(b2nn.make_desc(iters=1, batch_num=1))   # no data yet
+    x = np.ones((5, 6), np.float32).reshape(-1)
+    y = np.zeros((2, 6), np.float32).reshape(-1)
+    net.set_train_data(x, y, 6)
+    with pytest.raises(b2nn.B2nnError):
+        net.train(b2nn.make_desc(iters=1, batch_num=7))   # more batches than rows
+    with pytest.raises(b2nn.B2nnError):
+        net.train(b2nn.make_desc(iters=1, batch_num=0))
+    with pytest.raises(b2nn.B2nnError):
+        net.set_weights(np.zeros(3, np.float32))          # wrong count
+    with pytest.raises(b2nn.B2nnError):
+        net.train(b2nn.make_desc(iters=1, batch_num=1, act=b2nn.ACT_CUSTOM))   # custom activation without pointers
+    out = net.train(b2nn.make_desc(iters=2, batch_num=2, display=1))            # still usable
+    assert out.steps == 4 and np.all(np.isfinite(out.log_J))
+    net.close()
+
+
+def test_single_row_batches_and_tiny_shapes(b2nn, oracle):
+    """Stochastic mode (batchNum = m, one row per step) and 1-unit layers: the smallest shapes every kernel must take."""
+    layers, m = [1, 1, 1], 5
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((m, 1)).astype(np.float32)
+    yv = (0.5 * x + 0.1).astype(np.float32)
+    x_cm, y_cm = oracle.with_bias_colmajor(x), oracle.colmajor(yv)
+    net = b2nn.Net()
+    net.set_layers(layers, 1, 9)
+    th0 = net.get_weights()
+    net.set_train_data(x_cm, y_cm, m)
+    for prec in ("fp32", "tf32", "tf32x3"):
+        net.set_weights(th0)
+        d = b2nn.make_desc(momentum=0.5, rate=0.1, iters=7, display=1, batch_num=m, classify=False, act=b2nn.ACT_TANH,
+                           out=b2nn.OUT_LINEAR, cost=b2nn.COST_SQUARED, precision=PREC[prec])
+        out = net.train(d)
+        ref = oracle.train(layers, x_cm, y_cm, m, batch_num=m, iters=7, display=1, momentum=0.5, rate=0.1,
+                           hidden_act=oracle.TANH, classify=False, theta0=th0, precision="f64")
+        assert np.abs(net.get_weights() - ref.theta).max() <= 2e-5
+        np.testing.assert_allclose(out.log_J, ref.log_J, rtol=1e-4, atol=1e-7)
+        assert abs(out.final_cost - ref.final_cost) <= 1e-4 * ref.final_cost + 1e-7
+    net.close()
+
+
+def _addr(b2nn, mangled):
+    import ctypes
+    return ctypes.cast(getattr(b2nn.lib(), mangled), ctypes.c_void_p).value
+
+
+@pytest.mark.parametrize("which", ["hidden", "output", "cost", "all"])
+@pytest.mark.parametrize("name", ["clf_tanh_softmax", "clf_sigmoid_sigout"])
+def test_function_pointer_path_matches_fused_builtins(b2nn, name, which):
+    """The reference's extension point: user functions passed by pointer (cublasNN.h:45-50).  Feeding the library's own
+    exported ops back in as 'unknown' pointers forces the generic path (materialised z, calls on the legacy default
+    stream, like cublasNN.cpp:606, 613, 648, 673); it must reproduce the fused built-in path."""
+    c = cases.case_by_name(name)
+    tanh_case = c.hidden_act == cases.TANH
+    act = "_Z7tanhGPUPKfPfi" if tanh_case else "_Z10sigmoidGPUPKfPfi"
+    dact = "_Z9sechSqGPUPKfPfi" if tanh_case else "_Z14sigmoidGradGPUPKfPfi"
+    outf = "_Z10softmaxGPUPKfPfii" if c.out_act == cases.OUT_SOFTMAX else "_Z16sigmoidOutputGPUPKfPfii"
+    costf = "_Z19crossEntropyCostGPUPfS_S_i" if c.cost == cases.COST_CROSSENTROPY else "_Z15negLnMaxCostGPUPfS_S_i"
+    net, th0, th, out = _engine(b2nn, c, "fp32")
+    x_cm, y_cm = cases.oracle_inputs(c)
+    net2 = b2nn.Net()
+    net2.set_layers(c.layers, c.init_kind, c.seed)
+    net2.set_train_data(x_cm, y_cm, c.m)
+    d = _desc(b2nn, c, "fp32")
+    if which in ("hidden", "all"):
+        d.act_kind = b2nn.ACT_CUSTOM
+        d.act_fn, d.act_grad_fn = _addr(b2nn, act), _addr(b2nn, dact)
+    if which in ("output", "all"):
+        d.out_kind = b2nn.OUT_CUSTOM
+        d.out_fn = _addr(b2nn, outf)
+    if which in ("cost", "all"):
+        d.cost_kind = b2nn.COST_CUSTOM
+        d.cost_fn = _addr(b2nn, costf)
+    out2 = net2.train(d)
+    th2 = net2.get_weights()
+    assert np.abs(th2 - th).max() <= 2e-5 * np.abs(th).max(), which
+    np.testing.assert_allclose(out2.log_J, out.log_J, rtol=2e-5)
+    assert abs(out2.final_cost - out.final_cost) <= 2e-5 * abs(out.final_cost) + 1e-8
+    assert out2.error_count == out.error_count
+    got, probs = net2.predict(d, x_cm, c.m)
+    want, wprobs = net.predict(_desc(b2nn, c, "fp32"), x_cm, c.m)
+    np.testing.assert_allclose(probs, wprobs, rtol=1e-4, atol=1e-6)
+    assert (got != want).mean() <= 0.005
+    net.close(); net2.close()
