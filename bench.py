@@ -188,11 +188,26 @@ def run_ours(args):
         net.comm_init(rank, world, uid[0])
         # gradient exchange of the large layers over NVLink peer memory, fused into the GEMM / update kernels
         if os.environ.get("B2NN_P2P", "1") != "0" and 2 <= world <= 8:
-            mine = net.comm_p2p_export()
+            ok = 1
+            try:
+                mine = net.comm_p2p_export()
+            except Exception:  # noqa: BLE001
+                mine, ok = b"", 0
             blobs = [None] * world
             dist.all_gather_object(blobs, mine)
-            net.comm_p2p_open(b"".join(blobs))
-            p2p_on = True
+            if ok and all(len(b) == 192 for b in blobs):
+                try:
+                    net.comm_p2p_open(b"".join(blobs))
+                except Exception:  # noqa: BLE001
+                    ok = 0
+            else:
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            p2p_on = bool(int(flag.item()))
+            if not p2p_on and ok:
+                # some rank could not map its peers (no CUDA IPC in this container): every rank stays on the NCCL path
+                net.comm_p2p_open(None)
 
     nb = K
     iters = 1

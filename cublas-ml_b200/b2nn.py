@@ -308,8 +308,9 @@ class Net:
         _check(lib().b2nn_comm_p2p_export(self._h, buf), "b2nn_comm_p2p_export")
         return buf.raw
 
-    def comm_p2p_open(self, blobs: bytes):
-        buf = C.create_string_buffer(blobs, len(blobs))
+    def comm_p2p_open(self, blobs):
+        """blobs: the world x 192 bytes gathered in rank order; None switches the peer-memory path off again."""
+        buf = C.create_string_buffer(blobs, len(blobs)) if blobs is not None else None
         _check(lib().b2nn_comm_p2p_open(self._h, buf), "b2nn_comm_p2p_open")
 
     def comm_barrier(self):

@@ -1636,7 +1636,8 @@ int b2nn_comm_p2p_export(b2nn_ctx* c, void* blob192) {
 }
 
 int b2nn_comm_p2p_open(b2nn_ctx* c, const void* blobs) {
-    if (!c || !blobs) { set_error("p2p_open: null argument"); return B2NN_ERR_ARG; }
+    if (!c) { set_error("p2p_open: null context"); return B2NN_ERR_ARG; }
+    if (!blobs) { c->p2p = false; c->plans.clear(); return B2NN_OK; }      // switch back to the NCCL path
     if (!c->p2p_flags) { set_error("p2p_open: call b2nn_comm_p2p_export first"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
     const char* b = static_cast<const char*>(blobs);

@@ -173,7 +173,7 @@ int b2nn_comm_barrier(b2nn_ctx* ctx);
  * every rank's weights (update fused with the all-gather).  Call after b2nn_comm_init and b2nn_set_layers, on every
  * rank: export 192 bytes (three CUDA IPC handles), all-gather them in rank order with the host's own plumbing, open. */
 int b2nn_comm_p2p_export(b2nn_ctx* ctx, void* blob192);
-int b2nn_comm_p2p_open(b2nn_ctx* ctx, const void* blobs_world_x_192);
+int b2nn_comm_p2p_open(b2nn_ctx* ctx, const void* blobs_world_x_192);   /* NULL: back to the NCCL path */
 
 /* ---- introspection ------------------------------------------------------------------------------------------ */
 /* Raw GEMM entry used by the kernel unit tests and the roofline benchmark: D(m,n) = sum_k A(m,k) B(n,k), D stored
