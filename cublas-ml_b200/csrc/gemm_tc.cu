@@ -148,24 +148,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
-        if (lane == 0) {
-            int it = 0;
-            for (int w = worker; w < total_work; w += n_workers) {
-                const int split = w / tiles_mn, rem = w - split * tiles_mn;
-                int tile_m, tile_n; decode_tile(rem, p.tiles_m, p.tiles_n, p.group_m, tile_m, tile_n);
-                const int m0 = (tile_m * NCTA + int(rank)) * BM;          // this CTA's 128 rows of A
-                const int n0 = tile_n * BN + int(rank) * B_ROWS;          // this CTA's share of B
-                const int kb0 = split * p.k_blocks;
-                int nkb = p.k_blocks_total - kb0;
-                if (nkb > p.k_blocks) nkb = p.k_blocks;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
-                    uint8_t* sb = sa + A_TILE_BYTES;
-                    uint64_t* bar = &full_bar[s];
-                    const int kc = (kb0 + kb) * BK;
+        // the whole warp walks the loop (warp-uniform control flow and operands); one elected lane issues
+        const bool issuer = elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        for (int w = worker; w < total_work; w += n_workers) {
+            const int split = w / tiles_mn, rem = w - split * tiles_mn;
+            int tile_m, tile_n; decode_tile(rem, p.tiles_m, p.tiles_n, p.group_m, tile_m, tile_n);
+            const int m0 = (tile_m * NCTA + int(rank)) * BM;          // this CTA's 128 rows of A
+            const int n0 = tile_n * BN + int(rank) * B_ROWS;          // this CTA's share of B
+            const int kb0 = split * p.k_blocks;
+            int nkb = p.k_blocks_total - kb0;
+            if (nkb > p.k_blocks) nkb = p.k_blocks;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
+                uint8_t* sb = sa + A_TILE_BYTES;
+                uint64_t* bar = &full_bar[s];
+                const int kc = (kb0 + kb) * BK;
+                if (issuer) {
                     if (NCTA == 1) mbar_expect_tx(bar, STAGE_BYTES);
                     auto load_pair = [&](uint8_t* ta, uint8_t* tb, const CUtensorMap* ma, const CUtensorMap* mb) {
                         if (A_MN) {
@@ -207,12 +208,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         else mbar_arrive_remote(bar, 0);
                     }
                 }
+                __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer (leader CTA only) ----------------
         if (leader) {
-            int it = 0, t = 0;
+            // Everything the issue loop needs is warp-uniform and kept in registers as (descriptor of stage 0) + offset, so
+            // the loop body is a handful of uniform adds around the four tcgen05.mma: with the descriptors rebuilt per
+            // instruction inside a lane-0 branch the issuing thread itself (~150 SASS instructions per k-block, each
+            // operand moved to the uniform file through a vote loop) was the bottleneck at ~62 % tensor-pipe activity.
+            const uint32_t smem_base = smem_u32(smem);
+            const uint64_t a_desc0 = A_MN ? umma_smem_desc(smem_base, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                          : umma_smem_desc(smem_base, 16, 1024);
+            const uint64_t b_desc0 = B_MN ? umma_smem_desc(smem_base + A_TILE_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                          : umma_smem_desc(smem_base + A_TILE_BYTES, 16, 1024);
+            constexpr uint32_t A_KSTEP = (A_MN ? 1024 : UMMA_K * 4) >> 4;      // descriptor units of 16 bytes
+            constexpr uint32_t B_KSTEP = (B_MN ? 1024 : UMMA_K * 4) >> 4;
+            constexpr uint32_t STAGE_STEP = STAGE_BYTES >> 4;
+            constexpr uint32_t LO_STEP = HALF_STAGE >> 4;
+            const bool issuer = elect_one();
+            int s = 0, t = 0;
+            uint32_t ph = 0;
             for (int w = worker; w < total_work; w += n_workers, ++t) {
                 const int split = w / tiles_mn;
                 const int kb0 = split * p.k_blocks;
@@ -223,29 +241,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait(&tmem_empty[acc], acc_ph ^ 1);          // epilogue has drained this accumulator buffer
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + uint32_t(acc) * ACC_COLS;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t sa = smem_u32(smem + size_t(s) * STAGE_BYTES);
-                        const uint32_t sb = sa + A_TILE_BYTES;
+                    if (issuer) {
+                        const uint64_t da0 = a_desc0 + uint64_t(uint32_t(s) * STAGE_STEP);
+                        const uint64_t db0 = b_desc0 + uint64_t(uint32_t(s) * STAGE_STEP);
 #pragma unroll
                         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                            auto desc_a = [&](uint32_t base) { return A_MN ? umma_smem_desc(base + kk * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout)
-                                                                           : umma_smem_desc(base + kk * UMMA_K * 4, 16, 1024); };
-                            auto desc_b = [&](uint32_t base) { return B_MN ? umma_smem_desc(base + kk * 1024, p.mn_lbo, p.mn_sbo, p.mn_layout)
-                                                                           : umma_smem_desc(base + kk * UMMA_K * 4, 16, 1024); };
                             auto mma = [&](uint64_t da, uint64_t db, uint32_t accumulate) {
                                 if (NCTA == 2) umma_tf32_pair(tmem_d, da, db, IDESC, accumulate);
                                 else umma_tf32(tmem_d, da, db, IDESC, accumulate);
                             };
-                            const uint64_t da = desc_a(sa), db = desc_b(sb);
+                            const uint64_t da = da0 + kk * A_KSTEP, db = db0 + kk * B_KSTEP;
                             mma(da, db, (kb | kk) != 0 ? 1u : 0u);
                             if (X3) {
-                                mma(da, desc_b(sb + HALF_STAGE), 1u);            // hi(A) * lo(B)
-                                mma(desc_a(sa + HALF_STAGE), db, 1u);            // lo(A) * hi(B)
+                                mma(da, db + LO_STEP, 1u);                       // hi(A) * lo(B)
+                                mma(da + LO_STEP, db, 1u);                       // lo(A) * hi(B)
                             }
                         }
                         // slot reusable (in both CTAs) once these MMAs have read it; accumulator complete after the last
@@ -253,6 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (kb == nkb - 1) { if (NCTA == 2) umma_commit_pair(&tmem_full[acc], 3); else umma_commit(&tmem_full[acc]); }
                     }
                     __syncwarp();
+                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -452,7 +465,8 @@ cudaError_t launch_majors(const TcPlan& pl, const TcArgs& a, cudaStream_t stream
 template <int BN>
 cudaError_t launch_bn(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
     if (pl.x3) {
-        // the fp32-grade mode keeps 4 tiles per stage: single CTAs, tiles up to 128 columns
+        // the fp32-grade mode keeps 4 tiles per stage: a single CTA takes tiles up to 128 columns, a pair up to 256
+        if (pl.ncta == 2) return launch_majors<BN, 2, true>(pl, a, stream);
         if constexpr (BN <= 128) return launch_majors<BN, 1, true>(pl, a, stream); else return cudaErrorInvalidValue;
     }
     return pl.ncta == 2 ? launch_majors<BN, 2, false>(pl, a, stream) : launch_majors<BN, 1, false>(pl, a, stream);
@@ -480,7 +494,13 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     if (g.N > 128) bn = 256; else if (g.N > 64) bn = 128; else if (g.N > 32) bn = 64; else if (g.N > 16) bn = 32; else bn = 16;
     if (g.b_major && bn < 32) bn = 32;     // an MN-major box is 32 floats wide
     plan.x3 = g.A_lo != nullptr && g.B_lo != nullptr;
-    if (plan.x3 && bn > 128) bn = 128;     // four tiles per stage: 128 x 128 keeps three stages in flight
+    // CTA pairs (cta_group::2, 256-row tiles, each CTA stages half of B) whenever there are two 128-row tiles to pair:
+    // 745 vs 692 TFLOP/s on 8192 x 4096 x 4097 (profiles/r1_gemm_pair.md).  B2NN_TC_NCTA=1 forces single CTAs.
+    int ncta = g.M > BM ? 2 : 1;
+    if (const char* e = std::getenv("B2NN_TC_NCTA")) { if (std::atoi(e) == 1) ncta = 1; }
+    if (g.b_major && bn < 64) ncta = 1;    // a CTA of a pair must stage whole 32-float atoms of B
+    // 3xTF32 stages four tiles per k-block: 128 x 128 alone (3 stages), 256 x 256 as a pair (3 stages)
+    if (plan.x3 && ncta == 1 && bn > 128) bn = 128;
     if (g.scatter_world > 0 && (g.scatter_rows % bn != 0 || plan.x3)) { err = "scatter rows not a multiple of the tile"; return false; }
     plan.block_n = bn;
     plan.g = g;
@@ -491,12 +511,6 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
         g_num_sms = n;
     }
-    // CTA pairs (cta_group::2, 256-row tiles) whenever there are at least two 128-row tiles to pair up
-    // CTA pairs are numerically verified but currently slower than single CTAs (profiles/): opt-in via B2NN_TC_NCTA=2
-    int ncta = 1;
-    if (const char* e = std::getenv("B2NN_TC_NCTA")) { if (std::atoi(e) == 2 && g.M > BM) ncta = 2; }
-    if (g.b_major && bn < 64) ncta = 1;
-    if (plan.x3) ncta = 1;
     plan.ncta = ncta;
 
     const int stage_bytes = (A_TILE_BYTES + b_tile_bytes(bn / ncta, g.b_major != 0)) * (plan.x3 ? 2 : 1);

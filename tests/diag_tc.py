@@ -79,6 +79,31 @@ def perf(net):
                 print(f"perf {name} {mode} EXC {ex}", flush=True)
                 return
     os.environ["B2NN_TC_NCTA"] = "1"
+    # yardstick only (never on the product path): cuBLAS TF32 on the same shapes through torch.matmul
+    torch.backends.cuda.matmul.allow_tf32 = True
+    for name, M, N, K in (("fwd1", B, H, H + 1), ("square", 8192, 8192, 8192), ("cublas-friendly", B, H, H)):
+        a = torch.randn(M, K, device="cuda") * 0.05
+        b = torch.randn(K, N, device="cuda") * 0.05
+        for _ in range(3):
+            torch.matmul(a, b)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"yardstick cuBLAS tf32 {name:16s} M,N,K=({M},{N},{K}) {ms * 1e3:8.1f} us  {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s", flush=True)
+        a16, b16 = a.bfloat16(), b.bfloat16()
+        for _ in range(3):
+            torch.matmul(a16, b16)
+        e0.record()
+        for _ in range(10):
+            torch.matmul(a16, b16)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"yardstick cuBLAS bf16 {name:16s} M,N,K=({M},{N},{K}) {ms * 1e3:8.1f} us  {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s", flush=True)
 
 
 def main():
