@@ -191,7 +191,8 @@ struct b2nn_ctx {
     // optional per-launch CUDA-event timing (b2nn_profile_*): kind 0 forward, 1 delta backprop, 2 weight gradient,
     // 3 output layer, 4 momentum update
     bool profile = false;
-    struct ProfRec { int kind; bool tc; double flops; double bytes; cudaEvent_t e0, e1; };
+    struct ProfRec { int kind; bool tc; double flops; double bytes; cudaEvent_t e0, e1; bool own_e0; };
+    bool prof_chain = false;           // the previous scope's end event can serve as this scope's start
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> prof_pool;
 };
@@ -492,11 +493,14 @@ struct ProfScope {
     b2nn_ctx* c; bool on;
     ProfScope(b2nn_ctx* ctx, int kind, bool tc, double flops, double bytes) : c(ctx), on(ctx->profile) {
         if (!on) return;
-        b2nn_ctx::ProfRec r{kind, tc, flops, bytes, prof_event(c), prof_event(c)};
-        cudaEventRecord(r.e0, c->stream);
+        // Back-to-back scopes on the engine stream share one event (end of the previous = start of this one): a timing
+        // event drains the stream, so two per launch inflated every interval by several microseconds.
+        const bool chain = c->prof_chain && !c->prof.empty();
+        b2nn_ctx::ProfRec r{kind, tc, flops, bytes, chain ? c->prof.back().e1 : prof_event(c), prof_event(c), !chain};
+        if (!chain) cudaEventRecord(r.e0, c->stream);
         c->prof.push_back(r);
     }
-    ~ProfScope() { if (on) cudaEventRecord(c->prof.back().e1, c->stream); }
+    ~ProfScope() { if (on) { cudaEventRecord(c->prof.back().e1, c->stream); c->prof_chain = true; } }
 };
 
 int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind) {
@@ -699,6 +703,7 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
                const float* Y, int64_t ldy, int64_t x_start, int64_t rows, int64_t global_rows, double* cost_slot) {
     const bool custom_oc = custom_outcost(d);
     StepPlan& sp = get_plan(c, rows, X, ldx, x_total, x_aligned, prec, d->act_kind, custom_oc);
+    if (c->comm) c->prof_chain = false;      // waits on the exchange streams sit between steps: not part of any launch
     bool any_fused = false;
     for (char f : sp.fused) any_fused = any_fused || f;
     if (any_fused) {
@@ -917,7 +922,7 @@ void b2nn_destroy(b2nn_ctx* c) {
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->h_acc) cudaFreeHost(c->h_acc);
     for (auto e : c->log_events) cudaEventDestroy(e);
-    for (auto& r : c->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto& r : c->prof) { if (r.own_e0) cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     for (auto e : c->grad_ready) cudaEventDestroy(e);
     for (auto e : c->grad_reduced) cudaEventDestroy(e);
@@ -1560,6 +1565,7 @@ void* b2nn_stream(b2nn_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int b2nn_profile_enable(b2nn_ctx* c, int on) {
     if (!c) { set_error("null ctx"); return B2NN_ERR_ARG; }
     c->profile = on != 0;
+    c->prof_chain = false;
     return B2NN_OK;
 }
 
@@ -1574,10 +1580,12 @@ int b2nn_profile_read(b2nn_ctx* c, double* ms, double* flops, double* bytes, int
             ms[r.kind] += t; flops[r.kind] += r.flops; bytes[r.kind] += r.bytes; ++launches[r.kind];
             if (r.tc) ++tc_launches[r.kind];
         }
-        c->prof_pool.push_back(r.e0); c->prof_pool.push_back(r.e1);
+        if (r.own_e0) c->prof_pool.push_back(r.e0);
+        c->prof_pool.push_back(r.e1);
     }
     (void)cudaGetLastError();
     c->prof.clear();
+    c->prof_chain = false;
     return B2NN_OK;
 }
 

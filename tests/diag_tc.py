@@ -106,9 +106,59 @@ def perf(net):
         print(f"yardstick cuBLAS bf16 {name:16s} M,N,K=({M},{N},{K}) {ms * 1e3:8.1f} us  {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s", flush=True)
 
 
+def sustained(net, seconds=3.0):
+    """Power-limited regime: the same 8192 x 4096 x 4096 contraction back to back for `seconds`, ours and the cuBLAS
+    yardsticks, with the SM clock / power seen at the end of each run (the tensor pipe is capped by board power)."""
+    import time
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+    M = 8192; N = 4096; K = 4096
+    stream = torch.cuda.ExternalStream(net.stream())
+    ld = K + 32
+    A = torch.randn(M + 1, ld, device="cuda") * 0.05          # K-major both: the wgrad form
+    Bm = torch.randn(N + 1, ld, device="cuda") * 0.05
+    D = torch.empty(N, M, device="cuda")
+    a = torch.randn(M, K, device="cuda") * 0.05
+    b = torch.randn(K, N, device="cuda") * 0.05
+    a16, b16 = a.bfloat16(), b.bfloat16()
+    torch.backends.cuda.matmul.allow_tf32 = True
+    os.environ.pop("B2NN_TC_NCTA", None)
+
+    def ours():
+        net.gemm(3, A.data_ptr(), ld, 0, Bm.data_ptr(), ld, 0, D.data_ptr(), M, M, N, K, 0, 0, M)
+    cases = (("ours tcgen05 tf32 (pair)", ours, stream), ("cuBLAS tf32", lambda: torch.matmul(a, b), None),
+             ("cuBLAS bf16", lambda: torch.matmul(a16, b16), None))
+    for name, fn, st in cases:
+        torch.cuda.synchronize()
+        time.sleep(2.0)                                         # let the board cool back to boost clocks
+        t_end = time.time() + seconds
+        total = 0
+        last_ms = None
+        while time.time() < t_end:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st) if st is not None else e0.record()
+            for _ in range(100):
+                fn()
+            e1.record(st) if st is not None else e1.record()
+            torch.cuda.synchronize()
+            last_ms = e0.elapsed_time(e1) / 100
+            total += 100
+            if total == 100:
+                first_ms = last_ms
+        mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        watts = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+        fl = 2.0 * M * N * K
+        print(f"sustained {name:26s} first 100: {fl / first_ms / 1e9:7.1f} TFLOP/s   last 100 of {total}: {fl / last_ms / 1e9:7.1f} TFLOP/s"
+              f"   {mhz} MHz {watts:.0f} W", flush=True)
+
+
 def main():
     net = b2nn.Net()
     ok_all = True
+    if "--sustained" in sys.argv:
+        sustained(net)
+        return
     if "--perf-only" not in sys.argv:
         for mode, backend, ncta in (("single/2d", 1, "1"), ("single/3d", 3, "1"), ("pair/2d", 1, "2"), ("pair/3d", 3, "2")):
             os.environ["B2NN_TC_NCTA"] = ncta
