@@ -1,6 +1,7 @@
 // elementwise.cu — the bandwidth-bound kernels around the contractions: output layer (+ cost, argmax, error count),
 // momentum update, layout conversion at the ABI edge, weight-init rescale.
 #include "engine.h"
+#include "pdl.cuh"
 #include "epilogue.cuh"
 #include "../../include/b2nn.h"
 
@@ -29,6 +30,7 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 // Softmax is max-shifted: identical to the reference whenever the reference does not overflow.
 // cost_sum / err_sum are double accumulators.
 __global__ void __launch_bounds__(OUT_THREADS) output_layer_kernel(OutputArgs a, double* cost_sum, double* err_sum) {
+    pdl_enter();
     __shared__ double sh[OUT_THREADS / 32];
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     double cost = 0.0, err = 0.0;
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(OUT_THREADS) output_layer_kernel(OutputArgs a,
 __global__ void __launch_bounds__(256) momentum_update_kernel(float4* __restrict__ theta, float4* __restrict__ vel,
                                                               const float4* __restrict__ grad, int64_t n4, float mu,
                                                               float alpha) {
+    pdl_enter();
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 v = vel[i];
@@ -95,6 +98,7 @@ __global__ void __launch_bounds__(256) momentum_update_kernel(float4* __restrict
 }
 __global__ void momentum_update_tail_kernel(float* theta, float* vel, const float* grad, int64_t from, int64_t count,
                                             float mu, float alpha) {
+    pdl_enter();
     const int64_t i = from + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < count) {
         const float v = fmaf(mu, vel[i], alpha * grad[i]);
@@ -150,6 +154,7 @@ __global__ void split_batches_kernel(const float* __restrict__ src, int64_t ld_s
 __device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 __global__ void __launch_bounds__(256) split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, int64_t count) {
+    pdl_enter();
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) lo[i] = tf32_lo(x[i]);
 }
@@ -157,6 +162,7 @@ __global__ void __launch_bounds__(256) split_lo_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) momentum_update_lo_kernel(float* __restrict__ theta, float* __restrict__ vel,
                                                                  const float* __restrict__ grad, float* __restrict__ theta_lo,
                                                                  int64_t count, float mu, float alpha) {
+    pdl_enter();
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
         const float v = fmaf(mu, vel[i], alpha * grad[i]);
@@ -209,9 +215,8 @@ inline unsigned blocks_for(int64_t n, int threads) { return unsigned((n + thread
 
 cudaError_t output_layer_launch(const OutputArgs& a, cudaStream_t stream) {
     if (a.rows <= 0) return cudaSuccess;
-    output_layer_kernel<<<blocks_for(a.rows, OUT_THREADS), OUT_THREADS, 0, stream>>>(
-        a, a.cost_sum, a.err_sum);
-    return cudaGetLastError();
+    return launch_pdl(output_layer_kernel, dim3(blocks_for(a.rows, OUT_THREADS)), dim3(OUT_THREADS), 0, stream, a, a.cost_sum,
+                      a.err_sum);
 }
 
 cudaError_t momentum_update_launch(float* theta, float* vel, const float* grad, int64_t count, float mu, float alpha,
@@ -224,14 +229,15 @@ cudaError_t momentum_update_launch(float* theta, float* vel, const float* grad, 
         // 148 SMs x 8 resident blocks of 256 threads; grid-stride covers the rest.
         const int64_t want = (n4 + 255) / 256;
         const unsigned grid = unsigned(want < 148 * 8 ? want : 148 * 8);
-        momentum_update_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<float4*>(theta), reinterpret_cast<float4*>(vel),
-                                                        reinterpret_cast<const float4*>(grad), n4, mu, alpha);
+        cudaError_t e = launch_pdl(momentum_update_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<float4*>(theta),
+                                   reinterpret_cast<float4*>(vel), reinterpret_cast<const float4*>(grad), n4, mu, alpha);
+        if (e != cudaSuccess) return e;
     }
     const int64_t done = n4 * 4;
     if (done < count)
-        momentum_update_tail_kernel<<<blocks_for(count - done, 256), 256, 0, stream>>>(theta, vel, grad, done, count, mu,
-                                                                                      alpha);
-    return cudaGetLastError();
+        return launch_pdl(momentum_update_tail_kernel, dim3(blocks_for(count - done, 256)), dim3(256), 0, stream, theta, vel, grad,
+                          done, count, mu, alpha);
+    return cudaSuccess;
 }
 
 cudaError_t theta_ref_to_internal_launch(const float* ref, float* w, int in, int out, int64_t ldw, cudaStream_t s) {
@@ -261,15 +267,14 @@ cudaError_t split_batches_launch(const float* src, int64_t ld_src, float* dst, i
 cudaError_t split_lo_launch(const float* x, float* lo, int64_t count, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
     const int64_t want = (count + 255) / 256;
-    split_lo_kernel<<<unsigned(want < 148 * 8 ? want : 148 * 8), 256, 0, s>>>(x, lo, count);
-    return cudaGetLastError();
+    return launch_pdl(split_lo_kernel, dim3(unsigned(want < 148 * 8 ? want : 148 * 8)), dim3(256), 0, s, x, lo, count);
 }
 cudaError_t momentum_update_lo_launch(float* theta, float* vel, const float* grad, float* theta_lo, int64_t count, float mu,
                                       float alpha, cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
     const int64_t want = (count + 255) / 256;
-    momentum_update_lo_kernel<<<unsigned(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(theta, vel, grad, theta_lo, count, mu, alpha);
-    return cudaGetLastError();
+    return launch_pdl(momentum_update_lo_kernel, dim3(unsigned(want < 148 * 16 ? want : 148 * 16)), dim3(256), 0, stream, theta, vel,
+                      grad, theta_lo, count, mu, alpha);
 }
 cudaError_t abs_sum_launch(const float* J, int64_t ld, int64_t rows, int K, double* out, cudaStream_t s) {
     if (rows <= 0 || K <= 0) return cudaSuccess;

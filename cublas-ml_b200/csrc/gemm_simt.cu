@@ -5,6 +5,7 @@
 // every shape (any M, N, K, any leading dimension, both operand major-nesses) and is what small or TMA-hostile
 // layers run on; large layers go to the tcgen05 kernel in gemm_tc.cu when the precision mode allows it.
 #include "engine.h"
+#include "pdl.cuh"
 #include "epilogue.cuh"
 
 namespace b2 {
@@ -44,6 +45,7 @@ __device__ __forceinline__ void store_tile(float (*s)[64 + PAD], const float (&r
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmDesc g, int k_per_split) {
+    pdl_enter();
     __shared__ __align__(16) float As[2][BK][BM + PAD];
     __shared__ __align__(16) float Bs[2][BK][BN + PAD];
 
@@ -125,11 +127,10 @@ cudaError_t gemm_simt_launch(const GemmDesc& g, cudaStream_t stream) {
     splits = (g.K + k_per - 1) / k_per;
     if (splits < 1) splits = 1;
     dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
-    if (g.a_major && g.b_major)       gemm_simt_kernel<true, true><<<grid, NT, 0, stream>>>(g, k_per);
-    else if (g.a_major && !g.b_major) gemm_simt_kernel<true, false><<<grid, NT, 0, stream>>>(g, k_per);
-    else if (!g.a_major && g.b_major) gemm_simt_kernel<false, true><<<grid, NT, 0, stream>>>(g, k_per);
-    else                              gemm_simt_kernel<false, false><<<grid, NT, 0, stream>>>(g, k_per);
-    return cudaGetLastError();
+    if (g.a_major && g.b_major)       return launch_pdl(gemm_simt_kernel<true, true>, grid, dim3(NT), 0, stream, g, k_per);
+    else if (g.a_major && !g.b_major) return launch_pdl(gemm_simt_kernel<true, false>, grid, dim3(NT), 0, stream, g, k_per);
+    else if (!g.a_major && g.b_major) return launch_pdl(gemm_simt_kernel<false, true>, grid, dim3(NT), 0, stream, g, k_per);
+    return launch_pdl(gemm_simt_kernel<false, false>, grid, dim3(NT), 0, stream, g, k_per);
 }
 
 }  // namespace b2

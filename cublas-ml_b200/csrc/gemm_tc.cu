@@ -24,6 +24,7 @@
 #include "engine.h"
 #include "epilogue.cuh"
 #include "ptx.cuh"
+#include "pdl.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -145,6 +146,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (NCTA == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above overlapped the previous kernel's tail (pdl.cuh); from here on its results are visible
+    pdl_enter();
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
@@ -441,11 +444,20 @@ cudaError_t launch_one(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
     cfg.blockDim = dim3(NUM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = pl.smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    unsigned na = 0;
+    if (NCTA == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = NCTA; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = NCTA == 2 ? 1 : 0;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, pl.map_a, pl.map_b, X3 ? pl.map_a_lo : pl.map_a, X3 ? pl.map_b_lo : pl.map_b, a);
 }
 

@@ -13,6 +13,7 @@
 // Lanes walk consecutive samples, so every global access is a 128-byte line.  Arithmetic is exact fp32 in every
 // precision mode.
 #include "engine.h"
+#include "pdl.cuh"
 #include "epilogue.cuh"
 #include "../../include/b2nn.h"
 
@@ -25,6 +26,7 @@ constexpr int HC = 512;                   // hidden units per shared-memory chun
 
 template <int KMAX, bool TRAIN>
 __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const TailArgs p) {
+    pdl_enter();
     extern __shared__ float smem[];
     float* W_s = smem;                                    // [KMAX][HC + 1]
     float* red = W_s + KMAX * (HC + 1);                   // [TAIL_WARPS][KMAX][32]
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const TailArgs p) {
 constexpr int SMALL_THREADS = 128;
 template <int KMAX, bool TRAIN>
 __global__ void __launch_bounds__(SMALL_THREADS) tail_small_kernel(const TailArgs p) {
+    pdl_enter();
     extern __shared__ float smem[];
     const int K = p.K, H1 = p.H + 1;
     float* W_s = smem;                    // [K][H1]
@@ -345,13 +348,12 @@ cudaError_t launch_small(const TailArgs& a, bool train, unsigned grid, size_t sm
     if (train) {
         static bool set = false;
         if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_small_kernel<KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e != cudaSuccess) return e; set = true; }
-        tail_small_kernel<KMAX, true><<<grid, SMALL_THREADS, smem, s>>>(a);
+        return launch_pdl(tail_small_kernel<KMAX, true>, dim3(grid), dim3(SMALL_THREADS), smem, s, a);
     } else {
         static bool set = false;
         if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_small_kernel<KMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e != cudaSuccess) return e; set = true; }
-        tail_small_kernel<KMAX, false><<<grid, SMALL_THREADS, smem, s>>>(a);
+        return launch_pdl(tail_small_kernel<KMAX, false>, dim3(grid), dim3(SMALL_THREADS), smem, s, a);
     }
-    return cudaGetLastError();
 }
 
 template <int KMAX>
@@ -359,13 +361,12 @@ cudaError_t launch_k(const TailArgs& a, bool train, unsigned grid, size_t smem, 
     if (train) {
         static bool set = false;
         if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_kernel<KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e != cudaSuccess) return e; set = true; }
-        tail_kernel<KMAX, true><<<grid, TAIL_THREADS, smem, s>>>(a);
+        return launch_pdl(tail_kernel<KMAX, true>, dim3(grid), dim3(TAIL_THREADS), smem, s, a);
     } else {
         static bool set = false;
         if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_kernel<KMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e != cudaSuccess) return e; set = true; }
-        tail_kernel<KMAX, false><<<grid, TAIL_THREADS, smem, s>>>(a);
+        return launch_pdl(tail_kernel<KMAX, false>, dim3(grid), dim3(TAIL_THREADS), smem, s, a);
     }
-    return cudaGetLastError();
 }
 
 }  // namespace
