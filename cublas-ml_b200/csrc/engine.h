@@ -32,6 +32,11 @@ struct GemmDesc {
     // Extent of A's allocation along each index when it is larger than origin + size (0 = origin + size).  Lets one
     // tensor map over the whole training matrix serve every batch.
     int64_t a_mn_end = 0, a_k_end = 0;
+    int64_t b_mn_end = 0, b_k_end = 0;     // same for B (only set by the swapped plan below)
+    // D(m,n) stored n-contiguous (D[m * ldd + n]) instead of m-contiguous.  Internal to the tcgen05 plan: a skinny
+    // forward contraction is run with the operands swapped (units on the TMEM lanes, samples on the columns) so its
+    // sample dimension spreads over many small tiles; the transposed store restores the unit-major layout.
+    bool d_trans = false;
     // The caller guarantees that reading up to 31 floats past the M/N extent of an MN-major operand (in every k row,
     // including the last) stays inside its allocation, which the one-box-per-tile 3-D TMA view relies on.
     bool mn_slack = false;
@@ -64,6 +69,7 @@ struct TcPlan {
     unsigned grid_x = 0;      // persistent grid: min(work items, SMs / ncta) * ncta
     size_t smem_bytes = 0;
     bool a_3d = false, b_3d = false;
+    bool swapped = false;     // the kernel runs D^T = B A^T (see GemmDesc::d_trans); `g` stays the caller's description
     bool valid = false;
 };
 // Returns false (and sets err) when the operands violate a TMA constraint (alignment, stride) so the caller can

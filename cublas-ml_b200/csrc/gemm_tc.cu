@@ -61,6 +61,7 @@ struct TcArgs {
     int a_mn0, a_k0, b_mn0, b_k0;
     int epi;
     int atomic;                     // split-K: accumulate with red.global.add
+    int d_trans;                    // store D[m * ldd + n] (row of this thread's TMEM lane, 32 consecutive columns)
     int stages;
     uint32_t mn_lbo, mn_sbo, mn_layout;   // MN-major descriptor: 4096 / 512 / type 1 (overridable for bring-up)
     int a_3d, b_3d;                 // MN-major operand fetched with one 3-D TMA box per tile
@@ -339,7 +340,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int j = 0; j < CH; ++j)
                         if (n0 + c0 + j < p.N) dlo[int64_t(j) * p.ldd] = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
                 }
-                if (m_ok) {
+                if (p.d_trans) {
+                    // swapped plan: lane = unit, columns = samples -> each thread owns CH consecutive floats of one row
+                    if (m_ok) {
+                        float* dst = Dp + int64_t(m) * p.ldd + n0 + c0;
+                        if (p.atomic) {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) if (n0 + c0 + j < p.N) atomicAdd(dst + j, v[j]);
+                        } else if (n0 + c0 + CH <= p.N) {
+#pragma unroll
+                            for (int j = 0; j < CH; j += 4)
+                                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j) if (n0 + c0 + j < p.N) dst[j] = v[j];
+                        }
+                    }
+                } else if (m_ok) {
                     float* dst = Dp + int64_t(n0 + c0) * p.ldd + m;
                     if (p.scatter_world > 0) {
                         // this tile's rows belong to rank `owner`: store into its arena over NVLink, slice = my rank
@@ -463,7 +480,7 @@ cudaError_t launch_one(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
 
 template <int BN, int NCTA, bool X3>
 cudaError_t launch_majors(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
-    const bool am = pl.g.a_major != 0, bm = pl.g.b_major != 0;
+    const bool am = (pl.swapped ? pl.g.b_major : pl.g.a_major) != 0, bm = (pl.swapped ? pl.g.a_major : pl.g.b_major) != 0;
     if (am && bm) {
         if constexpr (NCTA == 2 && BN < 64) return cudaErrorInvalidValue; else return launch_one<BN, true, true, NCTA, X3>(pl, a, stream);
     }
@@ -494,8 +511,40 @@ bool tc_runtime_ok(std::string& err) {
     return true;
 }
 
-bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
+// The description the kernel actually runs: the caller's, or (swapped plan) D^T = B A^T with a transposed store.
+static GemmDesc effective_desc(const GemmDesc& u, bool swapped) {
+    if (!swapped) return u;
+    GemmDesc e = u;
+    e.A = u.B; e.lda = u.ldb; e.a_major = u.b_major; e.a_mn0 = u.b_mn0; e.a_k0 = u.b_k0; e.a_mn_end = u.b_mn_end; e.a_k_end = u.b_k_end;
+    e.B = u.A; e.ldb = u.lda; e.b_major = u.a_major; e.b_mn0 = u.a_mn0; e.b_k0 = u.a_k0; e.b_mn_end = u.a_mn_end; e.b_k_end = u.a_k_end;
+    e.M = u.N; e.N = u.M;
+    e.d_trans = true;
+    return e;
+}
+
+bool tc_plan_build(TcPlan& plan, const GemmDesc& gu, std::string& err) {
     plan.valid = false;
+    plan.swapped = false;
+    if (g_num_sms == 0) {
+        int dev = 0, n = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        g_num_sms = n;
+    }
+    // Skinny forward contraction (activations MN-major x weights K-major, <= 128 output units) that would leave most of
+    // the machine idle as ceil(rows / 256) pair tiles: run it swapped, as one 128-lane tile of units x many small tiles
+    // of samples (config C1's 4200 x 50 x 785: 17 pair tiles -> 132 tiles of 32 samples).
+    // Not when split-K is available (plain store, split_k == 0): a long K then spreads over the SMs as splits, which
+    // keeps 16 KB per stage in flight instead of the swapped plan's 4 KB sample tiles (C3's 8192 x 10 x 4097 output layer:
+    // 27 us split against ~75 us swapped).  Measured gains: small-batch inference on the MNIST net 29 -> 20 us.
+    const bool may_split = gu.epi == EPI_STORE && gu.split_k == 0;
+    if (gu.a_major == 1 && gu.b_major == 0 && gu.N <= BM && gu.M > 0 && gu.epi <= EPI_TANH && !gu.A_lo && !gu.D_lo && !may_split &&
+        gu.scatter_world == 0 && gu.split_k <= 1 && !gu.d_trans && gu.ldd % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(gu.D) & 15) == 0 && !std::getenv("B2NN_TC_NO_SWAP")) {
+        const int64_t pair_tiles = (int64_t(gu.M) + 2 * BM - 1) / (2 * BM);
+        if (pair_tiles * 2 < g_num_sms) plan.swapped = true;
+    }
+    const GemmDesc g = effective_desc(gu, plan.swapped);
     if (!tc_runtime_ok(err)) return false;
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) { err = "empty contraction"; return false; }
     if (g.a_mn0 + g.M >= (int64_t(1) << 31) || g.a_k0 + g.K >= (int64_t(1) << 31) ||
@@ -505,6 +554,11 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     int bn;
     if (g.N > 128) bn = 256; else if (g.N > 64) bn = 128; else if (g.N > 32) bn = 64; else if (g.N > 16) bn = 32; else bn = 16;
     if (g.b_major && bn < 32) bn = 32;     // an MN-major box is 32 floats wide
+    if (plan.swapped) {
+        // largest sample tile that still gives every SM one: the weights are re-read per tile, so wider is cheaper
+        bn = 32;
+        for (int cand : {256, 128, 64}) if ((int64_t(g.N) + cand - 1) / cand >= g_num_sms) { bn = cand; break; }
+    }
     plan.x3 = g.A_lo != nullptr && g.B_lo != nullptr;
     // CTA pairs (cta_group::2, 256-row tiles, each CTA stages half of B) whenever there are two 128-row tiles to pair:
     // 745 vs 692 TFLOP/s on 8192 x 4096 x 4097 (profiles/r1_gemm_pair.md).  B2NN_TC_NCTA=1 forces single CTAs.
@@ -515,14 +569,7 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     if (plan.x3 && ncta == 1 && bn > 128) bn = 128;
     if (g.scatter_world > 0 && (g.scatter_rows % bn != 0 || plan.x3)) { err = "scatter rows not a multiple of the tile"; return false; }
     plan.block_n = bn;
-    plan.g = g;
-
-    if (g_num_sms == 0) {
-        int dev = 0, n = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        g_num_sms = n;
-    }
+    plan.g = gu;
     plan.ncta = ncta;
 
     const int stage_bytes = (A_TILE_BYTES + b_tile_bytes(bn / ncta, g.b_major != 0)) * (plan.x3 ? 2 : 1);
@@ -574,10 +621,12 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
     plan.a_3d = g.a_major && g.mn_slack && !no3d && (g.a_mn0 % 32 == 0);
     plan.b_3d = g.b_major && g.mn_slack && !no3d && (g.b_mn0 % 32 == 0);
     if (!encode_operand(&plan.map_a, g.A, g.lda, g.a_major != 0, a_mn_end, a_k_end, BM, plan.a_3d, err)) return false;
-    if (!encode_operand(&plan.map_b, g.B, g.ldb, g.b_major != 0, g.b_mn0 + g.N, g.b_k0 + g.K, bn / ncta, plan.b_3d, err)) return false;   // each CTA of a pair stages half of B
+    const int64_t b_mn_end = g.b_mn_end > 0 ? g.b_mn_end : g.b_mn0 + g.N;
+    const int64_t b_k_end = g.b_k_end > 0 ? g.b_k_end : g.b_k0 + g.K;
+    if (!encode_operand(&plan.map_b, g.B, g.ldb, g.b_major != 0, b_mn_end, b_k_end, bn / ncta, plan.b_3d, err)) return false;   // each CTA of a pair stages half of B
     if (plan.x3) {
         if (!encode_operand(&plan.map_a_lo, g.A_lo, g.lda, g.a_major != 0, a_mn_end, a_k_end, BM, plan.a_3d, err)) return false;
-        if (!encode_operand(&plan.map_b_lo, g.B_lo, g.ldb, g.b_major != 0, g.b_mn0 + g.N, g.b_k0 + g.K, bn / ncta, plan.b_3d, err)) return false;
+        if (!encode_operand(&plan.map_b_lo, g.B_lo, g.ldb, g.b_major != 0, b_mn_end, b_k_end, bn / ncta, plan.b_3d, err)) return false;
     }
     plan.valid = true;
     return true;
@@ -585,12 +634,13 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err) {
 
 cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream) {
     if (!pl.valid) return cudaErrorInvalidValue;
+    const GemmDesc g = effective_desc(pl.g, pl.swapped);
     TcArgs a;
-    a.D = pl.g.D; a.ldd = pl.g.ldd; a.aux = pl.g.aux; a.ldaux = pl.g.ldaux;
-    a.D_lo = pl.x3 ? pl.g.D_lo : nullptr;
-    for (int i = 0; i < 8; ++i) a.scatter_base[i] = pl.g.scatter_base[i];
-    a.scatter_world = pl.g.scatter_world; a.scatter_rank = pl.g.scatter_rank; a.scatter_rows = pl.g.scatter_rows;
-    a.M = pl.g.M; a.N = pl.g.N;
+    a.D = g.D; a.ldd = g.ldd; a.aux = g.aux; a.ldaux = g.ldaux;
+    a.D_lo = pl.x3 ? g.D_lo : nullptr;
+    for (int i = 0; i < 8; ++i) a.scatter_base[i] = g.scatter_base[i];
+    a.scatter_world = g.scatter_world; a.scatter_rank = g.scatter_rank; a.scatter_rows = g.scatter_rows;
+    a.M = g.M; a.N = g.N; a.d_trans = g.d_trans ? 1 : 0;
     a.tiles_m = pl.tiles_m; a.tiles_n = pl.tiles_n; a.splits = pl.splits;
     {
         // measured on the 8192 x 4096 x 4096 contractions: 582 (row-fastest) -> 611 TFLOP/s with groups of 8-16 row-tiles
@@ -601,8 +651,8 @@ cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream) {
         a.group_m = gm;
     }
     a.k_blocks = pl.k_blocks; a.k_blocks_total = pl.k_blocks_total;
-    a.a_mn0 = int(pl.g.a_mn0); a.a_k0 = int(pl.g.a_k0); a.b_mn0 = int(pl.g.b_mn0); a.b_k0 = int(pl.g.b_k0);
-    a.epi = pl.g.epi; a.atomic = pl.splits > 1 ? 1 : 0; a.stages = pl.stages;
+    a.a_mn0 = int(g.a_mn0); a.a_k0 = int(g.a_k0); a.b_mn0 = int(g.b_mn0); a.b_k0 = int(g.b_k0);
+    a.epi = g.epi; a.atomic = pl.splits > 1 ? 1 : 0; a.stages = pl.stages;
     a.a_3d = pl.a_3d ? 1 : 0; a.b_3d = pl.b_3d ? 1 : 0;
     a.mn_lbo = ATOM_BYTES; a.mn_sbo = 512; a.mn_layout = 1;
     if (const char* e = std::getenv("B2NN_TC_MN_LBO")) a.mn_lbo = uint32_t(std::atoi(e));   // bring-up knobs
