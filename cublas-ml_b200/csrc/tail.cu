@@ -358,7 +358,10 @@ constexpr int TILE_THREADS = 256;
 constexpr int TILE_WARPS = TILE_THREADS / 32;
 constexpr int TILE_PITCH = 33;
 constexpr int TILE_GMAX = 8;               // (k,h) outputs per thread: K*(H+1) <= 2048
-template <int KMAX>
+// Code size matters here: every warp walks the kernel once per group, so the first version (everything unrolled over
+// KMAX = 16 and 8 x 32 gradient terms, 5.7 k SASS instructions) spent its 20 us fetching instructions.  Loops over k
+// are rolled and work out of shared memory; GMAX is a template parameter (C1: 2 outputs per thread, C2: 1).
+template <int GMAX>
 __global__ void __launch_bounds__(TILE_THREADS) tail_tile_kernel(const TailArgs p) {
     pdl_enter();
     extern __shared__ float smem[];
@@ -366,6 +369,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tail_tile_kernel(const TailArgs 
     float* W_s = smem;                                 // [K][H1]
     float* a_s = W_s + K * H1;                         // [H1][33]
     float* z_s = a_s + H1 * TILE_PITCH;                // [K][33]  z, then delta
+    float* y_s = z_s + K * TILE_PITCH;                 // [K][33]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool inline_g = p.G_inline != nullptr;
 
@@ -374,10 +378,10 @@ __global__ void __launch_bounds__(TILE_THREADS) tail_tile_kernel(const TailArgs 
         W_s[idx] = __ldg(p.W + int64_t(k) * p.ldw + h);
     }
     // the (k,h) gradient outputs this thread owns, as shared-memory row offsets
-    int off_d[TILE_GMAX], off_a[TILE_GMAX];
-    float acc[TILE_GMAX];
+    int off_d[GMAX], off_a[GMAX];
+    float acc[GMAX];
 #pragma unroll
-    for (int j = 0; j < TILE_GMAX; ++j) {
+    for (int j = 0; j < GMAX; ++j) {
         const int o = threadIdx.x + j * TILE_THREADS;
         const int k = o < K * H1 ? o / H1 : 0, h = o < K * H1 ? o - k * H1 : 0;
         off_d[j] = k * TILE_PITCH; off_a[j] = h * TILE_PITCH; acc[j] = 0.f;
@@ -389,14 +393,10 @@ __global__ void __launch_bounds__(TILE_THREADS) tail_tile_kernel(const TailArgs 
         const int64_t i = grp * 32 + lane;
         const bool ok = i < p.rows;
         const int64_t ic = ok ? i : p.rows - 1;
-        // ---- stage the tile (4 rows in flight per warp), Y rows for warp 0 ----
-        float yv[KMAX];
-        if (warp == 0) {
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) yv[k] = (k < K && p.Y) ? __ldg(p.Y + int64_t(k) * p.ldy + ic) : 0.f;
-        }
+        // ---- stage the tile of a (4 rows in flight per warp) and of Y ----
         const float* ap = p.a + ic;
         int h = warp;
+#pragma unroll 1
         for (; h + 3 * TILE_WARPS < H1; h += 4 * TILE_WARPS) {
             float v[4];
 #pragma unroll
@@ -404,13 +404,18 @@ __global__ void __launch_bounds__(TILE_THREADS) tail_tile_kernel(const TailArgs 
 #pragma unroll
             for (int u = 0; u < 4; ++u) a_s[(h + u * TILE_WARPS) * TILE_PITCH + lane] = v[u];
         }
+#pragma unroll 1
         for (; h < H1; h += TILE_WARPS) a_s[h * TILE_PITCH + lane] = __ldg(ap + int64_t(h) * p.lda);
+#pragma unroll 1
+        for (int k = warp; k < K; k += TILE_WARPS) y_s[k * TILE_PITCH + lane] = p.Y ? __ldg(p.Y + int64_t(k) * p.ldy + ic) : 0.f;
         __syncthreads();
         // ---- z = [a,1] W^T ----
+#pragma unroll 1
         for (int k = warp; k < K; k += TILE_WARPS) {
             float z0 = 0.f, z1 = 0.f;
             const float* wk = W_s + k * H1;
             int hh = 0;
+#pragma unroll 4
             for (; hh + 1 < H1; hh += 2) {
                 z0 = fmaf(a_s[hh * TILE_PITCH + lane], wk[hh], z0);
                 z1 = fmaf(a_s[(hh + 1) * TILE_PITCH + lane], wk[hh + 1], z1);
@@ -419,41 +424,40 @@ __global__ void __launch_bounds__(TILE_THREADS) tail_tile_kernel(const TailArgs 
             z_s[k * TILE_PITCH + lane] = z0 + z1;
         }
         __syncthreads();
-        // ---- output activation, delta, cost, argmax: one lane per sample ----
+        // ---- output activation, delta, cost, argmax: one lane per sample, rolled over k ----
         if (warp == 0) {
-            float z[KMAX];
-            float zmax = -INFINITY, total = 0.f;
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) { z[k] = k < K ? z_s[k * TILE_PITCH + lane] : 0.f; if (k < K) zmax = fmaxf(zmax, z[k]); }
+            float zmax = -INFINITY, total = 1.f;
             if (p.out_kind == B2NN_OUT_SOFTMAX) {
-#pragma unroll
-                for (int k = 0; k < KMAX; ++k) if (k < K) { z[k] = expf(z[k] - zmax); total += z[k]; }
+#pragma unroll 1
+                for (int k = 0; k < K; ++k) zmax = fmaxf(zmax, z_s[k * TILE_PITCH + lane]);
+                total = 0.f;
+#pragma unroll 1
+                for (int k = 0; k < K; ++k) { const float e = expf(z_s[k * TILE_PITCH + lane] - zmax); z_s[k * TILE_PITCH + lane] = e; total += e; }
             }
             float best_h = 0.f, best_y = 0.f; int arg_h = 0, arg_y = 0;
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                if (k < K) {
-                    float hv;
-                    if (p.out_kind == B2NN_OUT_SOFTMAX) hv = z[k] / total;
-                    else if (p.out_kind == B2NN_OUT_SIGMOID) hv = sigmoid_f(z[k]);
-                    else hv = z[k];
-                    if (hv > best_h) { best_h = hv; arg_h = k; }
-                    if (p.Y && yv[k] > best_y) { best_y = yv[k]; arg_y = k; }
-                    const float dv = hv - yv[k];
-                    z_s[k * TILE_PITCH + lane] = ok ? dv : 0.f;
-                    if (ok) {
-                        if (p.h_out) p.h_out[int64_t(k) * p.ldh + i] = hv;
-                        if (p.delta_last) p.delta_last[int64_t(k) * p.ldd + i] = dv;
-                        if (p.cost_sum && p.Y) {
-                            float c = 0.f;
-                            if (p.cost_kind == B2NN_COST_SQUARED) c = dv * dv;
-                            else {
-                                if (yv[k] != 0.f) c += -yv[k] * logf(hv);
-                                if (p.cost_kind == B2NN_COST_NEGLNMAX && yv[k] != 1.f) c += -(1.f - yv[k]) * logf(1.f - hv);
-                                c = fabsf(c);
-                            }
-                            cost += double(c);
+#pragma unroll 1
+            for (int k = 0; k < K; ++k) {
+                const float zv = z_s[k * TILE_PITCH + lane], yv = y_s[k * TILE_PITCH + lane];
+                float hv;
+                if (p.out_kind == B2NN_OUT_SOFTMAX) hv = zv / total;
+                else if (p.out_kind == B2NN_OUT_SIGMOID) hv = sigmoid_f(zv);
+                else hv = zv;
+                if (hv > best_h) { best_h = hv; arg_h = k; }
+                if (p.Y && yv > best_y) { best_y = yv; arg_y = k; }
+                const float dv = hv - yv;
+                z_s[k * TILE_PITCH + lane] = ok ? dv : 0.f;
+                if (ok) {
+                    if (p.h_out) p.h_out[int64_t(k) * p.ldh + i] = hv;
+                    if (p.delta_last) p.delta_last[int64_t(k) * p.ldd + i] = dv;
+                    if (p.cost_sum && p.Y) {
+                        float c = 0.f;
+                        if (p.cost_kind == B2NN_COST_SQUARED) c = dv * dv;
+                        else {
+                            if (yv != 0.f) c += -yv * logf(hv);
+                            if (p.cost_kind == B2NN_COST_NEGLNMAX && yv != 1.f) c += -(1.f - yv) * logf(1.f - hv);
+                            c = fabsf(c);
                         }
+                        cost += double(c);
                     }
                 }
             }
@@ -468,16 +472,16 @@ __global__ void __launch_bounds__(TILE_THREADS) tail_tile_kernel(const TailArgs 
         __syncthreads();
         // ---- delta_prev = (delta W)[no bias] .* f'(a) ----
         if (p.delta_prev) {
-            float dl[KMAX];
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) dl[k] = k < K ? z_s[k * TILE_PITCH + lane] : 0.f;
+#pragma unroll 1
             for (int hh = warp; hh < p.H; hh += TILE_WARPS) {
                 float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                for (int k = 0; k < KMAX; k += 2) {
-                    if (k < K) s0 = fmaf(dl[k], W_s[k * H1 + hh], s0);
-                    if (k + 1 < K) s1 = fmaf(dl[k + 1], W_s[(k + 1) * H1 + hh], s1);
+                int k = 0;
+#pragma unroll 2
+                for (; k + 1 < K; k += 2) {
+                    s0 = fmaf(z_s[k * TILE_PITCH + lane], W_s[k * H1 + hh], s0);
+                    s1 = fmaf(z_s[(k + 1) * TILE_PITCH + lane], W_s[(k + 1) * H1 + hh], s1);
                 }
+                if (k < K) s0 = fmaf(z_s[k * TILE_PITCH + lane], W_s[k * H1 + hh], s0);
                 const float av = a_s[hh * TILE_PITCH + lane];
                 const float d = (p.act_kind == B2NN_ACT_SIGMOID) ? av * (1.0f - av) : 1.0f - av * av;
                 if (ok) p.delta_prev[int64_t(hh) * p.ldp + i] = (s0 + s1) * d;
@@ -486,23 +490,23 @@ __global__ void __launch_bounds__(TILE_THREADS) tail_tile_kernel(const TailArgs 
         // ---- G(k,h) += sum_s delta(k,s) a(h,s) ----
         if (inline_g) {
 #pragma unroll
-            for (int j = 0; j < TILE_GMAX; ++j) {
+            for (int j = 0; j < GMAX; ++j) {
                 if (threadIdx.x + j * TILE_THREADS < K * H1) {
                     const float* dp = z_s + off_d[j];
                     const float* aq = a_s + off_a[j];
                     float g0 = 0.f, g1 = 0.f;
-#pragma unroll
+#pragma unroll 4
                     for (int t = 0; t < 32; t += 2) { g0 = fmaf(dp[t], aq[t], g0); g1 = fmaf(dp[t + 1], aq[t + 1], g1); }
                     acc[j] += g0 + g1;
                 }
             }
         }
-        __syncthreads();                                   // the next group overwrites a_s / z_s
+        __syncthreads();                                   // the next group overwrites a_s / z_s / y_s
     }
 
     if (inline_g) {
 #pragma unroll
-        for (int j = 0; j < TILE_GMAX; ++j) {
+        for (int j = 0; j < GMAX; ++j) {
             const int o = threadIdx.x + j * TILE_THREADS;
             if (o < K * H1 && acc[j] != 0.f) {
                 const int k = o / H1, h = o - k * H1;
@@ -510,27 +514,24 @@ __global__ void __launch_bounds__(TILE_THREADS) tail_tile_kernel(const TailArgs 
             }
         }
     }
-    if (p.cost_sum || p.err_sum) {
-        if (warp == 0) {
-            for (int o = 16; o > 0; o >>= 1) {
-                cost += __shfl_xor_sync(0xffffffffu, cost, o);
-                err += __shfl_xor_sync(0xffffffffu, err, o);
-            }
-            if (lane == 0) {
-                if (p.cost_sum && cost != 0.0) atomicAdd(p.cost_sum, cost);
-                if (p.err_sum && err != 0.0) atomicAdd(p.err_sum, err);
-            }
+    if ((p.cost_sum || p.err_sum) && warp == 0) {
+        for (int o = 16; o > 0; o >>= 1) {
+            cost += __shfl_xor_sync(0xffffffffu, cost, o);
+            err += __shfl_xor_sync(0xffffffffu, err, o);
+        }
+        if (lane == 0) {
+            if (p.cost_sum && cost != 0.0) atomicAdd(p.cost_sum, cost);
+            if (p.err_sum && err != 0.0) atomicAdd(p.err_sum, err);
         }
     }
 }
 
-template <int KMAX>
+template <int GMAX>
 cudaError_t launch_tile(const TailArgs& a, unsigned grid, size_t smem, cudaStream_t s) {
     static bool set = false;
-    if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_tile_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e != cudaSuccess) return e; set = true; }
-    return launch_pdl(tail_tile_kernel<KMAX>, dim3(grid), dim3(TILE_THREADS), smem, s, a);
+    if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_tile_kernel<GMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e != cudaSuccess) return e; set = true; }
+    return launch_pdl(tail_tile_kernel<GMAX>, dim3(grid), dim3(TILE_THREADS), smem, s, a);
 }
-
 
 template <int KMAX>
 cudaError_t launch_small(const TailArgs& a, bool train, unsigned grid, size_t smem, cudaStream_t s) {
@@ -577,14 +578,14 @@ cudaError_t tail_launch(const TailArgs& a, bool train, cudaStream_t s) {
     // (C1: 28 us against 142 us).
     if (train && a.H + 1 <= 512 && int64_t(a.K) * (a.H + 1) <= TILE_GMAX * TILE_THREADS && !std::getenv("B2NN_NO_TAIL_TILE")) {
         const int H1 = a.H + 1;
-        const size_t sm = sizeof(float) * (size_t(a.K) * H1 + size_t(H1) * TILE_PITCH + size_t(a.K) * TILE_PITCH);
+        const size_t sm = sizeof(float) * (size_t(a.K) * H1 + size_t(H1) * TILE_PITCH + 2 * size_t(a.K) * TILE_PITCH);
         const int64_t grp = (a.rows + 31) / 32;
         const unsigned g = unsigned(grp < 148 * 2 ? grp : 148 * 2);
-        switch (kmax) {
-            case 4:  return launch_tile<4>(a, g, sm, s);
-            case 16: return launch_tile<16>(a, g, sm, s);
-            default: return launch_tile<32>(a, g, sm, s);
-        }
+        const int per_thread = int((int64_t(a.K) * H1 + TILE_THREADS - 1) / TILE_THREADS);
+        if (per_thread <= 1) return launch_tile<1>(a, g, sm, s);
+        if (per_thread <= 2) return launch_tile<2>(a, g, sm, s);
+        if (per_thread <= 4) return launch_tile<4>(a, g, sm, s);
+        return launch_tile<8>(a, g, sm, s);
     }
     if (!train && a.H + 1 <= 512 && int64_t(a.K) * (a.H + 1) <= 8192) {
         const bool ig = train && a.G_inline != nullptr;
