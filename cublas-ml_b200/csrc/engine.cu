@@ -792,7 +792,13 @@ int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float
     int rc = ensure_acc(c, 2);
     if (rc) return rc;
     if (cost || errors) B2_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 2, c->stream));
-    const int64_t chunk_cap = std::max<int64_t>(c->ws.cap, std::min<int64_t>(rows, 1 << 16));
+    // Chunk size: at least 2^16 rows, more while the per-chunk workspace (activations + deltas of every layer) stays
+    // under 2 GiB — small nets then evaluate 2^20 rows in one pass (full occupancy for the streaming kernels) instead of
+    // sixteen short launches.
+    int64_t row_bytes = 0;
+    for (int j = 1; j < nl; ++j) row_bytes += int64_t(sizeof(float)) * (2 * int64_t(c->layers[j]) + 1);
+    const int64_t budget_rows = ((int64_t(2) << 30) / std::max<int64_t>(row_bytes, 1)) / 32 * 32;
+    const int64_t chunk_cap = std::max<int64_t>(c->ws.cap, std::min<int64_t>(rows, std::max<int64_t>(1 << 16, budget_rows)));
     rc = ensure_workspace(c, chunk_cap, d->act_kind == B2NN_ACT_CUSTOM);
     if (rc) return rc;
     if (prec == B2NN_PREC_TF32X3 && d->act_kind != B2NN_ACT_CUSTOM) {
