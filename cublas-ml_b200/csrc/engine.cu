@@ -181,6 +181,9 @@ struct b2nn_ctx {
     P2pPeers peers{};
     int* p2p_flags = nullptr;                 // local flag block: [kind][layer][rank], kind 0 = wg_done, 1 = w_done
     int p2p_step = 0;
+    std::vector<int64_t> p2p_small_off;       // per layer: float offset of its slot block in the small-layer area, -1 = none
+    int64_t p2p_small_floats = 0;
+    std::vector<int64_t> p2p_small_cnt;       // floats per slot the area was sized for (guards against a later set_layers)
     cudaStream_t upd_stream = nullptr;
     std::vector<cudaEvent_t> p2p_wg_ev;
     cudaEvent_t p2p_upd_done = nullptr;
@@ -465,6 +468,10 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
             if (g.tc) sp.fused[j] = 1;
             else { g.g.scatter_world = 0; bind_backend(c, g, prec, true); }
         } else if (!(tail_layer && sp.tail_inline_g)) bind_backend(c, g, prec, true);
+        // ... layers whose rows do not split into whole tiles per rank (the 10-unit output layer) exchange through slot
+        // buffers in peer memory instead of NCCL: no foreign kernel competes with the persistent GEMMs for SMs
+        if (c->p2p && !sp.fused[j] && !custom && prec != B2NN_PREC_TF32X3 && nw <= P2P_MAX_LAYERS &&
+            j < int(c->p2p_small_off.size()) && c->p2p_small_off[j] >= 0 && c->p2p_small_cnt[j] == li.ldw * li.out) sp.fused[j] = 2;
 
         // delta backprop  delta_{j-1} = (delta_j W_j)[:, no bias] .* f'(z_{j-1})   (cublasNN.cpp:673-676)
         if (j > 0) {
@@ -560,6 +567,12 @@ int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_d
         if (!(tail_layer && sp.tail_inline_g)) rc = run_gemm(c, sp.wgrad[j], x_start, 2);
         if (rc) return rc;
         if (sp.fused[j]) {
+            if (sp.fused[j] == 2) {
+                const LayerInfo& li = c->L[j];
+                const int64_t cnt = li.ldw * li.out;
+                B2_CUDA(p2p_small_scatter_launch(c->peers, c->G + li.w_off, c->p2p_small_off[j] + int64_t(c->rank) * cnt, cnt, c->stream));
+                ++c->launches;
+            }
             B2_CUDA(p2p_signal_launch(c->peers, (0 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD + c->rank, c->p2p_step, c->stream));
             B2_CUDA(cudaEventRecord(c->p2p_wg_ev[j], c->stream));
         } else if (c->comm && !c->grad_ready.empty()) B2_CUDA(cudaEventRecord(c->grad_ready[j], c->stream));
@@ -708,10 +721,11 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
     for (char f : sp.fused) any_fused = any_fused || f;
     if (any_fused) {
         ++c->p2p_step;
-        if (c->p2p_step > 1)       // every owner's rows of the previous step have landed in this rank's weights
-            for (size_t j = 0; j < sp.fused.size(); ++j)
-                if (sp.fused[j])
-                    B2_CUDA(p2p_gate_launch(c->p2p_flags + (1 * P2P_MAX_LAYERS + int(j)) * P2P_MAX_WORLD, c->nranks, c->p2p_step - 1, c->stream));
+        if (c->p2p_step > 1) {     // every owner's rows of the previous step have landed in this rank's weights (and every
+            uint64_t mask = 0;     // rank has consumed the small-layer slots this step will overwrite)
+            for (size_t j = 0; j < sp.fused.size(); ++j) if (sp.fused[j]) mask |= uint64_t(1) << j;
+            B2_CUDA(p2p_gate_layers_launch(c->p2p_flags + 1 * P2P_MAX_LAYERS * P2P_MAX_WORLD, mask, c->nranks, c->p2p_step - 1, c->stream));
+        }
     }
     int rc = forward_pass(c, sp, x_start, d);
     if (rc) return rc;
@@ -733,6 +747,17 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
         // gradient all-reduce per layer on the communication stream, issued in the order the gradients were produced
         for (int j = nw - 1; j >= 0; --j) {
             const LayerInfo& li = c->L[j];
+            if (sp.fused[j] == 2) {
+                // small layer: once every rank's copy sits in this rank's slots, sum them and update the local replica
+                const int64_t cnt = li.ldw * li.out;
+                B2_CUDA(cudaStreamWaitEvent(c->upd_stream, c->p2p_wg_ev[j], 0));
+                B2_CUDA(p2p_gate_launch(c->p2p_flags + (0 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD, c->nranks, c->p2p_step, c->upd_stream));
+                B2_CUDA(p2p_small_reduce_update_launch(c->peers.S[c->rank] + c->p2p_small_off[j], cnt, c->nranks, c->W + li.w_off,
+                                                       c->V + li.w_off, cnt, d->momentum, alpha, c->upd_stream));
+                B2_CUDA(p2p_signal_launch(c->peers, (1 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD + c->rank, c->p2p_step, c->upd_stream));
+                c->launches += 3;
+                continue;
+            }
             if (sp.fused[j]) {
                 // owner side of the fused exchange, on its own stream: wait for every rank's partial rows, then reduce +
                 // update + all-gather this rank's R rows and tell everyone
@@ -1225,11 +1250,11 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
         rc = flush_logs(false);
         if (rc) return rc;
     }
-    if (c->p2p && c->p2p_step > 0)
-        for (int j = 0; j < int(c->L.size()) && j < P2P_MAX_LAYERS; ++j)
-            if (c->L[j].out % (256 * c->nranks) == 0)       // gate only layers that can have been fused; unfused flags stay 0
-                if (p2p_layer_was_fused(c, j))
-                    B2_CUDA(p2p_gate_launch(c->p2p_flags + (1 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD, c->nranks, c->p2p_step, c->stream));
+    if (c->p2p && c->p2p_step > 0) {
+        uint64_t mask = 0;       // gate only layers that went through the peer-memory exchange; other flags stay 0
+        for (int j = 0; j < int(c->L.size()) && j < P2P_MAX_LAYERS; ++j) if (p2p_layer_was_fused(c, j)) mask |= uint64_t(1) << j;
+        B2_CUDA(p2p_gate_layers_launch(c->p2p_flags + 1 * P2P_MAX_LAYERS * P2P_MAX_WORLD, mask, c->nranks, c->p2p_step, c->stream));
+    }
     B2_CUDA(cudaEventRecord(ev1, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     destroy_graphs();
@@ -1418,10 +1443,11 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
         B2_CUDA(cudaEventRecord(c->st_consumed[buf], c->stream));
         B2_CUDA(cudaMemcpyAsync(c->h_jsteps + s, c->d_jsteps + s, sizeof(double), cudaMemcpyDeviceToHost, c->stream));   // this step's loss
     }
-    if (c->p2p && c->p2p_step > 0)
-        for (int j = 0; j < int(c->L.size()) && j < P2P_MAX_LAYERS; ++j)
-            if (p2p_layer_was_fused(c, j))
-                B2_CUDA(p2p_gate_launch(c->p2p_flags + (1 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD, c->nranks, c->p2p_step, c->stream));
+    if (c->p2p && c->p2p_step > 0) {
+        uint64_t mask = 0;       // gate only layers that went through the peer-memory exchange; other flags stay 0
+        for (int j = 0; j < int(c->L.size()) && j < P2P_MAX_LAYERS; ++j) if (p2p_layer_was_fused(c, j)) mask |= uint64_t(1) << j;
+        B2_CUDA(p2p_gate_layers_launch(c->p2p_flags + 1 * P2P_MAX_LAYERS * P2P_MAX_WORLD, mask, c->nranks, c->p2p_step, c->stream));
+    }
     B2_CUDA(cudaEventRecord(ev1, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
@@ -1637,8 +1663,22 @@ int b2nn_comm_p2p_export(b2nn_ctx* c, void* blob192) {
     if (c->nranks < 2 || c->nranks > P2P_MAX_WORLD) { set_error("p2p_export: needs 2..8 ranks (b2nn_comm_init first)"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
     if (!c->p2p_flags) {
-        B2_CUDA(cudaMalloc(&c->p2p_flags, sizeof(int) * 2 * P2P_MAX_LAYERS * P2P_MAX_WORLD));
-        B2_CUDA(cudaMemset(c->p2p_flags, 0, sizeof(int) * 2 * P2P_MAX_LAYERS * P2P_MAX_WORLD));
+        // one peer-visible allocation: the flag block, then `world` slots for every small layer (a layer whose rows do
+        // not split into whole 256-column tiles per rank, up to 4 Mi floats)
+        const int nw = int(c->L.size());
+        c->p2p_small_off.assign(nw, -1);
+        c->p2p_small_cnt.assign(nw, 0);
+        c->p2p_small_floats = 0;
+        for (int j = 0; j < nw && j < P2P_MAX_LAYERS; ++j) {
+            const int64_t cnt = c->L[j].ldw * c->L[j].out;
+            if (c->L[j].out % (256 * c->nranks) == 0 || cnt > (int64_t(4) << 20) || (c->L[j].w_off & 3)) continue;
+            c->p2p_small_off[j] = c->p2p_small_floats;
+            c->p2p_small_cnt[j] = cnt;
+            c->p2p_small_floats += cnt * c->nranks;
+        }
+        const size_t bytes = sizeof(int) * P2P_FLAG_INTS + sizeof(float) * size_t(c->p2p_small_floats);
+        B2_CUDA(cudaMalloc(&c->p2p_flags, bytes));
+        B2_CUDA(cudaMemset(c->p2p_flags, 0, bytes));
     }
     cudaIpcMemHandle_t h[3];
     B2_CUDA(cudaIpcGetMemHandle(&h[0], c->W));
@@ -1657,7 +1697,11 @@ int b2nn_comm_p2p_open(b2nn_ctx* c, const void* blobs) {
     const char* b = static_cast<const char*>(blobs);
     c->peers.world = c->nranks; c->peers.rank = c->rank;
     for (int r = 0; r < c->nranks; ++r) {
-        if (r == c->rank) { c->peers.W[r] = c->W; c->peers.G[r] = c->G; c->peers.flags[r] = c->p2p_flags; continue; }
+        if (r == c->rank) {
+            c->peers.W[r] = c->W; c->peers.G[r] = c->G; c->peers.flags[r] = c->p2p_flags;
+            c->peers.S[r] = reinterpret_cast<float*>(c->p2p_flags + P2P_FLAG_INTS);
+            continue;
+        }
         cudaIpcMemHandle_t h[3];
         std::memcpy(h, b + size_t(r) * 192, 192);
         void* ptr[3] = {nullptr, nullptr, nullptr};
@@ -1667,6 +1711,7 @@ int b2nn_comm_p2p_open(b2nn_ctx* c, const void* blobs) {
             c->p2p_opened.push_back(ptr[i]);
         }
         c->peers.W[r] = static_cast<float*>(ptr[0]); c->peers.G[r] = static_cast<float*>(ptr[1]); c->peers.flags[r] = static_cast<int*>(ptr[2]);
+        c->peers.S[r] = reinterpret_cast<float*>(c->peers.flags[r] + P2P_FLAG_INTS);
     }
     if (!c->upd_stream) B2_CUDA(cudaStreamCreateWithFlags(&c->upd_stream, cudaStreamNonBlocking));
     if (!c->p2p_upd_done) B2_CUDA(cudaEventCreateWithFlags(&c->p2p_upd_done, cudaEventDisableTiming));

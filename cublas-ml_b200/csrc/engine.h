@@ -140,9 +140,18 @@ struct P2pPeers {
     float* W[P2P_MAX_WORLD];       // every rank's weight arena (own entry = local pointer)
     float* G[P2P_MAX_WORLD];       // every rank's gradient arena
     int*   flags[P2P_MAX_WORLD];   // every rank's flag block: [0, L) wg_done per (layer, src) ... see engine.cu
+    float* S[P2P_MAX_WORLD];       // every rank's slot area for small layers (behind its flag block, same allocation)
     int world, rank;
 };
+constexpr int P2P_FLAG_INTS = 2 * P2P_MAX_LAYERS * P2P_MAX_WORLD;       // [kind][layer][rank]
 cudaError_t p2p_gate_launch(const int* flags, int count, int value, cudaStream_t s);
+// one launch for several layers: flags_kind = base of a [P2P_MAX_LAYERS][P2P_MAX_WORLD] block, bit j of mask = wait for layer j
+cudaError_t p2p_gate_layers_launch(const int* flags_kind, uint64_t layer_mask, int world, int value, cudaStream_t s);
+// small layers (rows do not split into whole tiles per rank): every rank copies its whole gradient into slot `rank` of
+// every peer, then each rank sums the slots in rank order and updates its own replica (identical bits everywhere)
+cudaError_t p2p_small_scatter_launch(const P2pPeers& peers, const float* src, int64_t slot_off, int64_t count, cudaStream_t s);
+cudaError_t p2p_small_reduce_update_launch(const float* slots, int64_t slot_stride, int world, float* theta, float* vel,
+                                           int64_t count, float mu, float alpha, cudaStream_t s);
 cudaError_t p2p_signal_launch(const P2pPeers& peers, int index, int value, cudaStream_t s);
 cudaError_t p2p_reduce_update_launch(const P2pPeers& peers, const float* partial, int64_t slice_floats, float* vel,
                                      int64_t w_off, int64_t count, float mu, float alpha, cudaStream_t s);

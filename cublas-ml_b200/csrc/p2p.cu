@@ -37,6 +37,52 @@ __global__ void gate_kernel(const int* flags, int count, int value) {
     }
 }
 
+// Same for every (layer, rank) entry selected by `layer_mask` of a [P2P_MAX_LAYERS][P2P_MAX_WORLD] flag block.
+__global__ void gate_layers_kernel(const int* flags, unsigned long long layer_mask, int world, int value) {
+    const long long t0 = clock64();
+    for (int i = threadIdx.x; i < P2P_MAX_LAYERS * P2P_MAX_WORLD; i += blockDim.x) {
+        const int layer = i / P2P_MAX_WORLD, r = i - layer * P2P_MAX_WORLD;
+        if (!((layer_mask >> layer) & 1ull) || r >= world) continue;
+        while (ld_acquire_sys(flags + i) < value) {
+            __nanosleep(200);
+            if (clock64() - t0 > 20000000000LL) __trap();
+        }
+    }
+}
+
+// Small layer, source side: this rank's whole gradient into slot `rank` of every peer (NVLink stores).
+__global__ void __launch_bounds__(256) small_scatter_kernel(P2pPeers peers, const float4* __restrict__ src, int64_t slot_off4,
+                                                            int64_t n4) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = src[i];
+#pragma unroll 1
+        for (int p = 0; p < peers.world; ++p) reinterpret_cast<float4*>(peers.S[p])[slot_off4 + i] = v;
+    }
+}
+
+// Small layer, every rank: g = sum of the slots in rank order (same order everywhere => replicas stay bit-identical),
+// then the momentum update of the local replica.
+__global__ void __launch_bounds__(256) small_reduce_update_kernel(const float4* __restrict__ slots, int64_t stride4, int world,
+                                                                  float4* __restrict__ theta, float4* __restrict__ vel,
+                                                                  int64_t n4, float mu, float alpha) {
+    const int64_t step = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += step) {
+        float4 g = slots[i];
+        for (int r = 1; r < world; ++r) {
+            const float4 q = slots[r * stride4 + i];
+            g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+        }
+        float4 v = vel[i];
+        float4 t = theta[i];
+        v.x = fmaf(mu, v.x, alpha * g.x); v.y = fmaf(mu, v.y, alpha * g.y);
+        v.z = fmaf(mu, v.z, alpha * g.z); v.w = fmaf(mu, v.w, alpha * g.w);
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        vel[i] = v;
+        theta[i] = t;
+    }
+}
+
 // flags_of_peer[p][index] = value on every rank p (including this one), after everything this GPU stored before.
 __global__ void signal_kernel(P2pPeers peers, int index, int value) {
     __threadfence_system();
@@ -70,6 +116,26 @@ __global__ void __launch_bounds__(256) reduce_update_allgather_kernel(P2pPeers p
 
 cudaError_t p2p_gate_launch(const int* flags, int count, int value, cudaStream_t s) {
     gate_kernel<<<1, 32, 0, s>>>(flags, count, value);
+    return cudaGetLastError();
+}
+cudaError_t p2p_gate_layers_launch(const int* flags_kind, uint64_t layer_mask, int world, int value, cudaStream_t s) {
+    if (layer_mask == 0) return cudaSuccess;
+    gate_layers_kernel<<<1, 128, 0, s>>>(flags_kind, static_cast<unsigned long long>(layer_mask), world, value);
+    return cudaGetLastError();
+}
+cudaError_t p2p_small_scatter_launch(const P2pPeers& peers, const float* src, int64_t slot_off, int64_t count, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    const int64_t n4 = count / 4, want = (n4 + 255) / 256;
+    small_scatter_kernel<<<unsigned(want < 148 ? want : 148), 256, 0, s>>>(peers, reinterpret_cast<const float4*>(src), slot_off / 4, n4);
+    return cudaGetLastError();
+}
+cudaError_t p2p_small_reduce_update_launch(const float* slots, int64_t slot_stride, int world, float* theta, float* vel,
+                                           int64_t count, float mu, float alpha, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    const int64_t n4 = count / 4, want = (n4 + 255) / 256;
+    small_reduce_update_kernel<<<unsigned(want < 148 ? want : 148), 256, 0, s>>>(reinterpret_cast<const float4*>(slots), slot_stride / 4,
+                                                                               world, reinterpret_cast<float4*>(theta),
+                                                                               reinterpret_cast<float4*>(vel), n4, mu, alpha);
     return cudaGetLastError();
 }
 cudaError_t p2p_signal_launch(const P2pPeers& peers, int index, int value, cudaStream_t s) {
