@@ -292,21 +292,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const bool m_ok = m < p.M;
             const int acc = t & 1;
             const uint32_t acc_ph = (t >> 1) & 1;
+            // Derivative epilogues read one activation per output.  Those loads are software-pipelined one chunk ahead:
+            // the first chunk is requested before the accumulator is even complete, chunk c+1 before chunk c is stored,
+            // so reads stay in flight through the store phases (the K = 10 backprop of the output layer is all epilogue).
+            const bool deriv = p.epi >= EPI_DSIGMOID;
+            // Addressing is incremental (one 64-bit add per element) with an unpredicated path for interior chunks: with
+            // a 64-bit multiply and two predicates per access the epilogue ran ~25 instructions per output element and
+            // the K = 10 backprop of the output layer was bound by instruction issue (ncu: 26 M warp instructions).
+            auto load_aux = [&](int c0, float (&dst)[CH]) {
+                const float* ap = aux + int64_t(n0 + c0) * p.ldaux + m;
+                if (m_ok && n0 + c0 + CH <= p.N) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) { dst[j] = __ldg(ap); ap += p.ldaux; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) { dst[j] = (n0 + c0 + j < p.N && m_ok) ? __ldg(ap) : 0.f; ap += p.ldaux; }
+                }
+            };
+            float av[CH];
+            if (deriv && n0 + c_begin < p.N) load_aux(c_begin, av);
             mbar_wait(&tmem_full[acc], acc_ph);
             tc_fence_after();
             const uint32_t lane_addr = tmem_base + uint32_t(acc) * ACC_COLS + (uint32_t(q * 32) << 16);
 #pragma unroll 1
             for (int c0 = c_begin; c0 < c_end; c0 += CH) {
                 if (n0 + c0 >= p.N) break;                // warp-uniform
-                // derivative epilogues: issue the whole chunk's activation loads first so they overlap the TMEM read
-                float av[CH];
-                if (p.epi >= EPI_DSIGMOID) {
-#pragma unroll
-                    for (int j = 0; j < CH; ++j) {
-                        const int n = n0 + c0 + j;
-                        av[j] = (n < p.N && m_ok) ? __ldg(aux + int64_t(n) * p.ldaux + m) : 0.f;
-                    }
-                }
+                float av_next[CH];
+                const bool more = deriv && c0 + CH < c_end && n0 + c0 + CH < p.N;
+                if (more) load_aux(c0 + CH, av_next);
                 uint32_t r[CH];
                 if constexpr (CH == 32) tmem_ld_32x32(lane_addr + c0, r); else tmem_ld_32x16(lane_addr + c0, r);
                 tmem_ld_wait();
@@ -337,8 +350,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // low part of the output for the next contraction that consumes it: exact remainder of the truncation
                     float* dlo = p.D_lo + int64_t(n0 + c0) * p.ldd + m;
 #pragma unroll
-                    for (int j = 0; j < CH; ++j)
-                        if (n0 + c0 + j < p.N) dlo[int64_t(j) * p.ldd] = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
+                    for (int j = 0; j < CH; ++j) {
+                        if (n0 + c0 + j < p.N) *dlo = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
+                        dlo += p.ldd;
+                    }
                 }
                 if (p.d_trans) {
                     // swapped plan: lane = unit, columns = samples -> each thread owns CH consecutive floats of one row
@@ -365,11 +380,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     if (p.atomic) {
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) if (n0 + c0 + j < p.N) atomicAdd(dst + int64_t(j) * p.ldd, v[j]);
+                        for (int j = 0; j < CH; ++j) { if (n0 + c0 + j < p.N) atomicAdd(dst, v[j]); dst += p.ldd; }
+                    } else if (n0 + c0 + CH <= p.N) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) { *dst = v[j]; dst += p.ldd; }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) if (n0 + c0 + j < p.N) dst[int64_t(j) * p.ldd] = v[j];
+                        for (int j = 0; j < CH; ++j) { if (n0 + c0 + j < p.N) *dst = v[j]; dst += p.ldd; }
                     }
+                }
+                if (more) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) av[j] = av_next[j];
                 }
             }
             // this warp is done reading the accumulator buffer: hand it back to the MMA issuer (leader CTA)
