@@ -62,6 +62,7 @@ struct StepPlan {
     std::vector<char> fused;     // data parallel over peer memory: layer's gradient is scattered to its owners by the GEMM
     bool use_tail = false;       // skinny last layer: forward + output + delta backprop fused in tail.cu
     bool tail_inline_g = false;  // ... and its weight gradient too
+    bool skinny_bwd = false;     // narrow last layer behind a wide hidden layer: delta backprop + gradient in one pass (skinny.cu)
 };
 
 struct Workspace {
@@ -417,6 +418,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         const bool no_tail = no_tail_arg || std::getenv("B2NN_NO_TAIL") != nullptr;
         sp.use_tail = !custom && !no_tail && tail_supported(last.out, last.in, false);
         sp.tail_inline_g = sp.use_tail && tail_supported(last.out, last.in, true);
+        sp.skinny_bwd = !sp.use_tail && !custom && nw >= 2 && skinny_bwd_supported(last.out, last.in, w.ld);
     }
     for (int j = 0; j < nw; ++j) {
         const LayerInfo& li = c->L[j];
@@ -563,8 +565,22 @@ int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_d
         // With the peer-memory exchange an owner may overwrite W_j on this rank as soon as every rank has signalled its
         // gradient of layer j, so the delta backprop that still reads W_j goes first.
         const bool bwd_first = c->p2p;
-        if (bwd_first && j > 0 && !tail_layer) { rc = run_gemm(c, sp.bwd[j], 0, 1); if (rc) return rc; }
-        if (!(tail_layer && sp.tail_inline_g)) rc = run_gemm(c, sp.wgrad[j], x_start, 2);
+        const bool skinny = sp.skinny_bwd && j == nw - 1 && j > 0;
+        if (skinny) {
+            // narrow output layer behind a wide hidden layer: delta_{j-1} and G_j in one pass over a_{j-1} (skinny.cu)
+            const LayerInfo& li = c->L[j];
+            ProfScope scope(c, 1, false, 4.0 * double(sp.rows) * li.in * li.out, 8.0 * double(sp.rows) * li.in);
+            SkinnyArgs a{};
+            a.a = c->ws.a[j - 1]; a.delta = c->ws.delta[j]; a.W = c->W + li.w_off; a.delta_prev = c->ws.delta[j - 1];
+            a.G = c->G + li.w_off; a.ld = c->ws.ld; a.ldw = li.ldw; a.rows = sp.rows; a.H = li.in; a.K = li.out; a.act_kind = d->act_kind;
+            B2_CUDA(cudaMemsetAsync(a.G, 0, sizeof(float) * size_t(li.ldw) * li.out, c->stream));
+            B2_CUDA(skinny_bwd_launch(a, c->stream));
+            ++c->launches;
+            if (!c->ws.delta_lo.empty() && c->ws.delta_lo[j - 1])      // fp32-grade mode: the next contraction wants the low part too
+                B2_CUDA(split_lo_launch(c->ws.delta[j - 1], c->ws.delta_lo[j - 1], int64_t(li.in) * c->ws.ld, c->stream));
+        }
+        if (!skinny && bwd_first && j > 0 && !tail_layer) { rc = run_gemm(c, sp.bwd[j], 0, 1); if (rc) return rc; }
+        if (!skinny && !(tail_layer && sp.tail_inline_g)) rc = run_gemm(c, sp.wgrad[j], x_start, 2);
         if (rc) return rc;
         if (sp.fused[j]) {
             if (sp.fused[j] == 2) {
@@ -576,7 +592,7 @@ int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_d
             B2_CUDA(p2p_signal_launch(c->peers, (0 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD + c->rank, c->p2p_step, c->stream));
             B2_CUDA(cudaEventRecord(c->p2p_wg_ev[j], c->stream));
         } else if (c->comm && !c->grad_ready.empty()) B2_CUDA(cudaEventRecord(c->grad_ready[j], c->stream));
-        if (!bwd_first && j > 0 && !tail_layer) {
+        if (!skinny && !bwd_first && j > 0 && !tail_layer) {
             rc = run_gemm(c, sp.bwd[j], 0, 1);
             if (rc) return rc;
             if (custom) {

@@ -133,6 +133,20 @@ struct TailArgs {
 bool tail_supported(int K, int H, bool want_inline_g);
 cudaError_t tail_launch(const TailArgs& a, bool train, cudaStream_t s);
 
+// Backward step of a narrow layer behind a wide one (skinny.cu): delta_prev = (delta W) .* f'(a) and G = delta^T [a,1]
+// in one pass over a.  a, delta, delta_prev share the leading dimension ld (samples contiguous); the caller zeroes G.
+struct SkinnyArgs {
+    const float* a;            // (H+1) rows, ones row last
+    const float* delta;        // K rows
+    const float* W;            // K rows of ldw
+    float* delta_prev;         // H rows
+    float* G;                  // K rows of ldw
+    int64_t ld, ldw, rows;
+    int H, K, act_kind;
+};
+bool skinny_bwd_supported(int K, int H, int64_t ld);
+cudaError_t skinny_bwd_launch(const SkinnyArgs& a, cudaStream_t s);
+
 // ---- peer-memory data parallelism (p2p.cu) ---------------------------------------------------------------------------
 constexpr int P2P_MAX_WORLD = 8;
 constexpr int P2P_MAX_LAYERS = 64;

@@ -333,6 +333,33 @@ def test_single_row_batches_and_tiny_shapes(b2nn, oracle):
     net.close()
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "tf32x3"])
+@pytest.mark.parametrize("act", ["tanh", "sigmoid"])
+def test_wide_hidden_narrow_output_ragged_batches(b2nn, oracle, act, prec):
+    """A 1100-unit hidden layer in front of 7 outputs takes the fused delta-backprop + gradient kernel (skinny.cu); the
+    ragged batches (111 / 111 / 115 rows) make it run with deltas of a longer previous batch left behind the batch end."""
+    layers, m, K = [40, 1100, 7], 337, 7
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((m, 40)).astype(np.float32)
+    lab = (x @ rng.standard_normal((40, K)).astype(np.float32)).argmax(1)
+    x_cm, y_cm = oracle.with_bias_colmajor(x), oracle.one_hot_colmajor(lab, K)
+    net = b2nn.Net()
+    net.set_layers(layers, b2nn.INIT_2, 5)
+    th0 = net.get_weights()
+    net.set_train_data(x_cm, y_cm, m)
+    kw = dict(momentum=0.9, rate=0.05, iters=4, display=1, batch_num=3, classify=True)
+    d = b2nn.make_desc(act=b2nn.ACT_TANH if act == "tanh" else b2nn.ACT_SIGMOID, out=b2nn.OUT_SOFTMAX,
+                       cost=b2nn.COST_CROSSENTROPY, precision=PREC[prec], **kw)
+    out = net.train(d)
+    ref = oracle.train(layers, x_cm, y_cm, m, hidden_act=oracle.TANH if act == "tanh" else oracle.SIGMOID,
+                       out_act=oracle.OUT_SOFTMAX, cost=oracle.COST_CROSSENTROPY, theta0=th0, precision="f64", **kw)
+    tol = TOL[prec]
+    err = np.abs(net.get_weights() - ref.theta).max() / np.abs(ref.theta).max()
+    assert err <= tol["theta"], (act, prec, err)
+    np.testing.assert_allclose(out.log_J, ref.log_J, rtol=tol["J"])
+    net.close()
+
+
 def _addr(b2nn, mangled):
     import ctypes
     return ctypes.cast(getattr(b2nn.lib(), mangled), ctypes.c_void_p).value
