@@ -115,8 +115,17 @@ def small_cases() -> list[Case]:
     return cases
 
 
+def extra_cases() -> list:
+    """Cases without golden vectors of the reference (checked against the oracle / a single-GPU run only)."""
+    x, y = _clf_blobs(4096, 128, 10, seed=9)
+    return [Case("wide1024_skinny", [128, 1024, 10], x, y, True, TANH, OUT_SOFTMAX, COST_CROSSENTROPY, batch_num=2, iters=3,
+                 display=1, rate=0.02, init_kind=2, seed=7,
+                 notes="1024 hidden units in front of 10 outputs: fused delta-backprop + gradient kernel (skinny.cu); data "
+                       "parallel: layer 0 splits into 256-row tiles per rank, the output layer goes through slot buffers")]
+
+
 def case_by_name(name: str) -> Case:
-    for c in small_cases():
+    for c in small_cases() + extra_cases():
         if c.name == name:
             return c
     raise KeyError(name)

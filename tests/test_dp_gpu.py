@@ -51,7 +51,8 @@ def _worker(rank, world, port, name, prec_name, p2p, q):
 
 
 @pytest.mark.parametrize("name,prec,p2p", [("clf_tanh_softmax", "fp32", False), ("wide_mini", "fp32", False),
-                                           ("wide_mini", "tf32", False), ("wide_mini", "tf32", True)])
+                                           ("wide_mini", "tf32", False), ("wide_mini", "tf32", True),
+                                           ("wide1024_skinny", "tf32", True), ("wide1024_skinny", "tf32", False)])
 def test_two_gpu_run_matches_single_gpu(b2nn, name, prec, p2p):
     """p2p = True: the first layer's gradient (512 rows = 2 ranks x 256-column tiles) takes the fused peer-memory path
     (reduce-scatter in the GEMM epilogue, update + all-gather on the owner); the others stay on NCCL."""
