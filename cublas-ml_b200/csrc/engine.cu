@@ -164,7 +164,6 @@ struct b2nn_ctx {
     Workspace ws;
     std::map<std::pair<int64_t, const float*>, StepPlan> plans;   // keyed by (rows, X base); valid for the (ws, ldx, precision, ...) below
     int plans_prec = -1;
-    const float* plans_x = nullptr;
     int64_t plans_ldx = 0, plans_xtotal = 0;
     bool plans_xaligned = false, plans_notail = false;
     int plans_act = -1;
@@ -616,7 +615,8 @@ int output_and_delta(b2nn_ctx* c, const b2nn_train_desc* d, const float* Y, int6
     const int out_kind = d->classify ? d->out_kind : B2NN_OUT_LINEAR;
     const int cost_kind = d->classify ? d->cost_kind : B2NN_COST_SQUARED;
     if (out_kind == B2NN_OUT_CUSTOM || (cost_kind == B2NN_COST_CUSTOM && cost_slot)) {
-        set_error("custom output activation / cost function pointers are not supported by the fused output kernel yet");
+        // callers route custom function pointers through output_custom(); reaching this is an engine bug, not a user error
+        set_error("internal: custom output activation / cost reached a fused output kernel");
         return B2NN_ERR_ARG;
     }
     OutputArgs a{};
@@ -697,7 +697,8 @@ int run_tail(b2nn_ctx* c, const StepPlan& sp, const b2nn_train_desc* d, const fl
     const int out_kind = d->classify ? d->out_kind : B2NN_OUT_LINEAR;
     const int cost_kind = d->classify ? d->cost_kind : B2NN_COST_SQUARED;
     if (out_kind == B2NN_OUT_CUSTOM || (cost_kind == B2NN_COST_CUSTOM && cost_slot)) {
-        set_error("custom output activation / cost function pointers are not supported by the fused output kernel yet");
+        // callers route custom function pointers through output_custom(); reaching this is an engine bug, not a user error
+        set_error("internal: custom output activation / cost reached a fused output kernel");
         return B2NN_ERR_ARG;
     }
     TailArgs a{};

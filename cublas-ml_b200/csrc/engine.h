@@ -76,9 +76,9 @@ struct TcPlan {
 // route the contraction to the FFMA kernel instead.
 bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err);
 cudaError_t tc_plan_launch(const TcPlan& plan, cudaStream_t stream);
-bool tc_runtime_ok(std::string& err);
+bool tc_runtime_ok(std::string& err);      // driver entry point for cuTensorMapEncodeTiled available?
 // Persistent GEMM grids leave `n` SMs unoccupied so a concurrent NCCL kernel is never queued behind a whole GEMM.
-void tc_set_reserved_sms(int n);   // driver entry point for cuTensorMapEncodeTiled available?
+void tc_set_reserved_sms(int n);
 
 // element-wise / bandwidth-bound kernels (elementwise.cu)
 struct OutputArgs {
