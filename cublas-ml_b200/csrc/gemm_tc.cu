@@ -37,7 +37,8 @@ namespace {
 constexpr int BM = 128;                // rows of the output tile owned by ONE CTA (TMEM lanes)
 constexpr int BK = 32;                 // floats per K block = 128 bytes
 constexpr int UMMA_K = 8;              // tf32: 32 bytes per instruction
-constexpr int EPI_WARPS = 8;           // 2 warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int EPI_WARPS = 16;          // 4 warps per TMEM lane quarter, each takes a quarter of the tile's columns
+constexpr int EPI_PARTS = EPI_WARPS / 4;
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int A_TILE_BYTES = BM * BK * 4;
 constexpr int ATOM_BYTES = 32 * BK * 4;   // one MN-major box: 32 (mn) x 32 (k) floats
@@ -276,10 +277,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else {
         // ---------------- epilogue ----------------
         const int q = warp & 3;                          // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;                // which half of the tile's columns
-        constexpr int CH = BN < 32 ? 16 : 32;
-        constexpr int COLS_PER_WARP = (BN / 2 >= CH) ? BN / 2 : CH;
-        const int c_begin = half * COLS_PER_WARP;
+        const int part = (warp - 2) >> 2;                // which slice of the tile's columns
+        constexpr int CH = 16;                           // columns per TMEM read: 16 keeps the 576-thread kernel inside 112 registers
+        constexpr int COLS_PER_WARP = (BN / EPI_PARTS >= CH) ? BN / EPI_PARTS : CH;
+        const int c_begin = part * COLS_PER_WARP;        // >= BN for the surplus warps of narrow tiles: they only arrive
         const int c_end = (c_begin + COLS_PER_WARP < BN) ? c_begin + COLS_PER_WARP : BN;
         const float* __restrict__ aux = p.aux;
         float* __restrict__ Dp = p.D;
@@ -321,7 +322,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const bool more = deriv && c0 + CH < c_end && n0 + c0 + CH < p.N;
                 if (more) load_aux(c0 + CH, av_next);
                 uint32_t r[CH];
-                if constexpr (CH == 32) tmem_ld_32x32(lane_addr + c0, r); else tmem_ld_32x16(lane_addr + c0, r);
+                tmem_ld_32x16(lane_addr + c0, r);
                 tmem_ld_wait();
                 float v[CH];
                 switch (p.epi) {                          // warp-uniform
