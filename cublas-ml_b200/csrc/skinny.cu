@@ -35,11 +35,25 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+// Blackwell packed fp32 FMA: two independent multiply-adds per issued instruction (the kernel is issue-bound).
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;\n" : "=f"(lo), "=f"(hi) : "l"(v));
+}
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // EXACT: K == KMAX, so the per-k guards (a branch each in the unrolled loops) disappear.
 template <int KMAX, bool EXACT>
-__global__ void __launch_bounds__(SK_THREADS) skinny_bwd_kernel(const SkinnyArgs p) {
+__global__ void __launch_bounds__(SK_THREADS, 4) skinny_bwd_kernel(const SkinnyArgs p) {
     pdl_enter();
     extern __shared__ __align__(16) float sk_smem[];
     constexpr int A_FLOATS = SK_ROWS * SK_PITCH, D_FLOATS = KMAX * SK_COLS, BUF_FLOATS = A_FLOATS + D_FLOATS;
@@ -47,11 +61,12 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_bwd_kernel(const SkinnyArgs
     const int K = EXACT ? KMAX : p.K;
     const int h0 = blockIdx.x * SK_ROWS;
     const int h = h0 + lane;                       // this thread's unit; h == H is the ones row (gradient of the bias only)
-    float wreg[KMAX], g[KMAX];
+    unsigned long long wreg[KMAX], g[KMAX];        // (w, w) pairs; gradient partials of the even / odd samples
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
-        wreg[k] = ((EXACT || k < K) && h < p.H) ? __ldg(p.W + int64_t(k) * p.ldw + h) : 0.f;
-        g[k] = 0.f;
+        const float w = ((EXACT || k < K) && h < p.H) ? __ldg(p.W + int64_t(k) * p.ldw + h) : 0.f;
+        wreg[k] = pack2(w, w);
+        g[k] = 0ull;
     }
     const int64_t n_tiles = (p.rows + SK_COLS - 1) / SK_COLS;
     // the next tile streams into the other buffer (cp.async) while this one is computed and stored
@@ -92,18 +107,21 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_bwd_kernel(const SkinnyArgs
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int so = warp * 16 + q * 4;
-            float4 a4 = *reinterpret_cast<const float4*>(a_s + lane * SK_PITCH + so);
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            const ulonglong2 a2 = *reinterpret_cast<const ulonglong2*>(a_s + lane * SK_PITCH + so);   // (a0,a1), (a2,a3)
+            unsigned long long t01 = 0ull, t23 = 0ull;
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
                 if (EXACT || k < K) {
-                    const float4 d = *reinterpret_cast<const float4*>(d_s + k * SK_COLS + so);     // warp-wide broadcast
-                    t.x = fmaf(d.x, wreg[k], t.x); t.y = fmaf(d.y, wreg[k], t.y);
-                    t.z = fmaf(d.z, wreg[k], t.z); t.w = fmaf(d.w, wreg[k], t.w);
-                    g[k] = fmaf(d.x, a4.x, g[k]); g[k] = fmaf(d.y, a4.y, g[k]);
-                    g[k] = fmaf(d.z, a4.z, g[k]); g[k] = fmaf(d.w, a4.w, g[k]);
+                    const ulonglong2 d2 = *reinterpret_cast<const ulonglong2*>(d_s + k * SK_COLS + so);   // warp-wide broadcast
+                    t01 = ffma2(d2.x, wreg[k], t01);
+                    t23 = ffma2(d2.y, wreg[k], t23);
+                    g[k] = ffma2(d2.x, a2.x, g[k]);
+                    g[k] = ffma2(d2.y, a2.y, g[k]);
                 }
             }
+            float4 a4, t;
+            unpack2(a2.x, a4.x, a4.y); unpack2(a2.y, a4.z, a4.w);
+            unpack2(t01, t.x, t.y); unpack2(t23, t.z, t.w);
             if (p.act_kind == B2NN_ACT_SIGMOID) {
                 a4.x = a4.x * (1.0f - a4.x); a4.y = a4.y * (1.0f - a4.y); a4.z = a4.z * (1.0f - a4.z); a4.w = a4.w * (1.0f - a4.w);
             } else {
@@ -128,7 +146,11 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_bwd_kernel(const SkinnyArgs
     // ---- gradient: sum the 8 warps' partials, one atomic per (k, unit) ----
     float* red = sk_smem;                          // [8][KMAX][32] floats <= 32 * 132
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) red[(warp * KMAX + k) * 32 + lane] = g[k];
+    for (int k = 0; k < KMAX; ++k) {
+        float g0, g1;
+        unpack2(g[k], g0, g1);
+        red[(warp * KMAX + k) * 32 + lane] = g0 + g1;
+    }
     __syncthreads();
     for (int idx = threadIdx.x; idx < K * 32; idx += SK_THREADS) {
         const int k = idx >> 5, l = idx & 31;
