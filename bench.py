@@ -289,7 +289,7 @@ def run_ours(args):
     roofline = {
         "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::tf32) x3 contractions" if args.precision != "fp32" else "gemm_simt_kernel",
         "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-        "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read+write per launch, mean over the 8 tcgen05 launches of a step)" if traffic else None,
+        "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (profiles/r1_step.csv: ncu dram__bytes_read+write per launch, mean over the 7 tcgen05 launches of a step)" if traffic else None,
         "algorithmic_flops_per_launch_mean": round(gemm_fl / max(gemm_launches, 1)), "peak_source": peak_note,
         "regime": "sustained (power-capped)" if capped else "burst (boost clocks)", "clocks": c2,
         "launches": gemm_launches, "avg_launch_ms": round(gemm_ms / max(gemm_launches, 1), 4),
