@@ -48,6 +48,32 @@ def test_c1_full_size_against_reference_live(b2nn, oracle, prec):
     assert terr <= {"fp32": 2e-3, "tf32x3": 2e-3, "tf32": 1e-1}[prec], (prec, terr)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_c1_secondary_variant_full_batch_against_reference_live(b2nn, oracle, prec):
+    """main.cpp:156 — the same net with sigmoid hidden units, sigmoid output and the negLnMax cost, batchNum 1 (one
+    42 000-row batch per step)."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libcublasml_ref.so did not travel")
+    layers, m, iters = [784, 50, 10], 42000, 12
+    lab = cases.mnist_labels()
+    x = cases.zscore(cases.synth_digits(lab, 784, seed=1234))
+    kw = dict(batch_num=1, iters=iters, display=2, momentum=0.9, rate=0.075)
+    r = oracle.ref_train(layers, x, lab.astype(np.float32).reshape(-1, 1), hidden_act=oracle.SIGMOID, classify=True,
+                         out_act=oracle.OUT_SIGMOID, cost=oracle.COST_NEGLNMAX, init_kind=2, seed=42, **kw)
+    x_cm, y_cm = oracle.with_bias_colmajor(x), oracle.one_hot_colmajor(lab, 10)
+    d = b2nn.make_desc(classify=True, act=b2nn.ACT_SIGMOID, out=b2nn.OUT_SIGMOID, cost=b2nn.COST_NEGLNMAX,
+                       precision={"fp32": 0, "tf32": 1}[prec], **kw)
+    th0, th, out = _engine_run(b2nn, layers, x_cm, y_cm, m, d, b2nn.INIT_2, 42)
+    assert np.array_equal(th0, r.theta0)
+    assert list(out.log_iter) == list(r.log_iter)
+    jtol = {"fp32": 2e-3, "tf32": 5e-2}[prec]
+    np.testing.assert_allclose(out.log_J, r.log_J, rtol=jtol)
+    assert abs(out.final_cost - r.final_cost) <= jtol * abs(r.final_cost) + 1e-6
+    assert abs(out.error_count - r.error_count) <= 0.001 * m + 1
+    terr = float(np.abs(th - r.theta).max() / np.abs(r.theta).max())
+    assert terr <= {"fp32": 2e-3, "tf32": 1e-1}[prec], (prec, terr)
+
+
 def test_c2_full_size_against_reference_live_and_oracle(b2nn, oracle):
     """BASELINE.json config C2 (bikeshare regression, full batch).  With the reference's rate 0.003 on targets ~10^2 the
     trajectory starts to oscillate around iteration 180 and is chaotic from there: any two fp32 runs (the reference's, this
