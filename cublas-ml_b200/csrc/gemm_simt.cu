@@ -11,19 +11,19 @@
 namespace b2 {
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+constexpr int BM = 64, BN = 64, NT = 256;      // BK (16 or 32) is a template parameter of the kernel
 constexpr int PAD = 4;
 
-// Loads one BK x 64 tile of an operand into registers (4 values per thread), zero-filled outside [0,mn_ext)x[k_lo,k_hi).
-template <bool MN_MAJOR>
+// Loads one BK x 64 tile of an operand into registers (BK/4 values per thread), zero-filled outside [0,mn_ext)x[k_lo,k_hi).
+template <bool MN_MAJOR, int BK>
 __device__ __forceinline__ void load_tile(const float* __restrict__ base, int64_t ld, int mn0, int mn_ext, int kt,
-                                          int k_hi, float (&r)[4]) {
+                                          int k_hi, float (&r)[BK / 4]) {
     const int t = threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < BK / 4; ++i) {
         const int e = t + NT * i;
         int mn, k;
-        if (MN_MAJOR) { k = e >> 6; mn = e & 63; } else { mn = e >> 4; k = e & 15; }
+        if (MN_MAJOR) { k = e >> 6; mn = e & 63; } else { mn = e / BK; k = e % BK; }
         const int gm = mn0 + mn, gk = kt + k;
         float v = 0.f;
         if (gm < mn_ext && gk < k_hi)
@@ -31,19 +31,21 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ base, int64_
         r[i] = v;
     }
 }
-template <bool MN_MAJOR>
-__device__ __forceinline__ void store_tile(float (*s)[64 + PAD], const float (&r)[4]) {
+template <bool MN_MAJOR, int BK>
+__device__ __forceinline__ void store_tile(float (*s)[64 + PAD], const float (&r)[BK / 4]) {
     const int t = threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < BK / 4; ++i) {
         const int e = t + NT * i;
         int mn, k;
-        if (MN_MAJOR) { k = e >> 6; mn = e & 63; } else { mn = e >> 4; k = e & 15; }
+        if (MN_MAJOR) { k = e >> 6; mn = e & 63; } else { mn = e / BK; k = e % BK; }
         s[k][mn] = r[i];
     }
 }
 
-template <bool A_MN, bool B_MN>
+// BK = 32 halves the number of load -> sync -> compute rounds: small contractions (one block per SM or fewer) are a
+// chain of global-load latencies, not of FMAs.
+template <bool A_MN, bool B_MN, int BK>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmDesc g, int k_per_split) {
     pdl_enter();
     __shared__ __align__(16) float As[2][BK][BM + PAD];
@@ -62,20 +64,20 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmDesc g, int k_per_spl
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 
-    float ra[4], rb[4];
+    float ra[BK / 4], rb[BK / 4];
     int buf = 0;
     if (k_lo < k_hi) {
-        load_tile<A_MN>(A, g.lda, m0, g.M, k_lo, k_hi, ra);
-        load_tile<B_MN>(B, g.ldb, n0, g.N, k_lo, k_hi, rb);
-        store_tile<A_MN>(As[0], ra);
-        store_tile<B_MN>(Bs[0], rb);
+        load_tile<A_MN, BK>(A, g.lda, m0, g.M, k_lo, k_hi, ra);
+        load_tile<B_MN, BK>(B, g.ldb, n0, g.N, k_lo, k_hi, rb);
+        store_tile<A_MN, BK>(As[0], ra);
+        store_tile<B_MN, BK>(Bs[0], rb);
     }
     __syncthreads();
     for (int kt = k_lo; kt < k_hi; kt += BK) {
         const bool more = kt + BK < k_hi;
         if (more) {
-            load_tile<A_MN>(A, g.lda, m0, g.M, kt + BK, k_hi, ra);
-            load_tile<B_MN>(B, g.ldb, n0, g.N, kt + BK, k_hi, rb);
+            load_tile<A_MN, BK>(A, g.lda, m0, g.M, kt + BK, k_hi, ra);
+            load_tile<B_MN, BK>(B, g.ldb, n0, g.N, kt + BK, k_hi, rb);
         }
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
@@ -89,8 +91,8 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmDesc g, int k_per_spl
                 for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(av[i], bv[j], acc[j][i]);
         }
         if (more) {
-            store_tile<A_MN>(As[buf ^ 1], ra);
-            store_tile<B_MN>(Bs[buf ^ 1], rb);
+            store_tile<A_MN, BK>(As[buf ^ 1], ra);
+            store_tile<B_MN, BK>(Bs[buf ^ 1], rb);
         }
         __syncthreads();
         buf ^= 1;
@@ -116,21 +118,29 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmDesc g, int k_per_spl
     }
 }
 
-}  // namespace
-
-cudaError_t gemm_simt_launch(const GemmDesc& g, cudaStream_t stream) {
-    if (g.M <= 0 || g.N <= 0) return cudaSuccess;
-    int splits = g.split_k > 1 && g.epi == EPI_STORE ? g.split_k : 1;
+template <int BK>
+cudaError_t launch_bk(const GemmDesc& g, int splits, cudaStream_t stream) {
     int k_per = (g.K + splits - 1) / splits;
     k_per = ((k_per + BK - 1) / BK) * BK;
     if (k_per <= 0) k_per = BK;
     splits = (g.K + k_per - 1) / k_per;
     if (splits < 1) splits = 1;
     dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
-    if (g.a_major && g.b_major)       return launch_pdl(gemm_simt_kernel<true, true>, grid, dim3(NT), 0, stream, g, k_per);
-    else if (g.a_major && !g.b_major) return launch_pdl(gemm_simt_kernel<true, false>, grid, dim3(NT), 0, stream, g, k_per);
-    else if (!g.a_major && g.b_major) return launch_pdl(gemm_simt_kernel<false, true>, grid, dim3(NT), 0, stream, g, k_per);
-    return launch_pdl(gemm_simt_kernel<false, false>, grid, dim3(NT), 0, stream, g, k_per);
+    if (g.a_major && g.b_major)       return launch_pdl(gemm_simt_kernel<true, true, BK>, grid, dim3(NT), 0, stream, g, k_per);
+    else if (g.a_major && !g.b_major) return launch_pdl(gemm_simt_kernel<true, false, BK>, grid, dim3(NT), 0, stream, g, k_per);
+    else if (!g.a_major && g.b_major) return launch_pdl(gemm_simt_kernel<false, true, BK>, grid, dim3(NT), 0, stream, g, k_per);
+    return launch_pdl(gemm_simt_kernel<false, false, BK>, grid, dim3(NT), 0, stream, g, k_per);
+}
+
+}  // namespace
+
+cudaError_t gemm_simt_launch(const GemmDesc& g, cudaStream_t stream) {
+    if (g.M <= 0 || g.N <= 0) return cudaSuccess;
+    const int splits = g.split_k > 1 && g.epi == EPI_STORE ? g.split_k : 1;
+    const int64_t blocks = int64_t((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * splits;
+    // latency-bound regime (at most two blocks per SM): deeper K tiles; throughput regime: the 16-deep tile
+    if (blocks <= 2 * 148 && g.K / splits > 16) return launch_bk<32>(g, splits, stream);
+    return launch_bk<16>(g, splits, stream);
 }
 
 }  // namespace b2
