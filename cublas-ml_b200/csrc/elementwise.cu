@@ -80,9 +80,9 @@ __global__ void __launch_bounds__(OUT_THREADS) output_layer_kernel(OutputArgs a,
 // v <- mu*v + alpha*g ; theta <- theta + v.  20 bytes per weight (read v, g, theta; write v, theta) against the
 // reference's two cublasSgeam passes at 24 bytes per weight (cublasNN.cpp:558-566, 619-627).  The gradient is already
 // in theta's layout, so the Sgeam transpose disappears.  128-bit accesses, grid-stride, one pass.
+template <bool ZERO_G>
 __global__ void __launch_bounds__(256) momentum_update_kernel(float4* __restrict__ theta, float4* __restrict__ vel,
-                                                              const float4* __restrict__ grad, int64_t n4, float mu,
-                                                              float alpha) {
+                                                              float4* __restrict__ grad, int64_t n4, float mu, float alpha) {
     pdl_enter();
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) momentum_update_kernel(float4* __restrict
         t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
         vel[i] = v;
         theta[i] = t;
+        if (ZERO_G) grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);     // small nets: next step's split-K / in-kernel sums need no memset
     }
 }
 __global__ void momentum_update_tail_kernel(float* theta, float* vel, const float* grad, int64_t from, int64_t count,
@@ -229,8 +230,8 @@ cudaError_t momentum_update_launch(float* theta, float* vel, const float* grad, 
         // 148 SMs x 8 resident blocks of 256 threads; grid-stride covers the rest.
         const int64_t want = (n4 + 255) / 256;
         const unsigned grid = unsigned(want < 148 * 8 ? want : 148 * 8);
-        cudaError_t e = launch_pdl(momentum_update_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<float4*>(theta),
-                                   reinterpret_cast<float4*>(vel), reinterpret_cast<const float4*>(grad), n4, mu, alpha);
+        cudaError_t e = launch_pdl(momentum_update_kernel<false>, dim3(grid), dim3(256), 0, stream, reinterpret_cast<float4*>(theta),
+                                   reinterpret_cast<float4*>(vel), reinterpret_cast<float4*>(const_cast<float*>(grad)), n4, mu, alpha);
         if (e != cudaSuccess) return e;
     }
     const int64_t done = n4 * 4;
@@ -238,6 +239,18 @@ cudaError_t momentum_update_launch(float* theta, float* vel, const float* grad, 
         return launch_pdl(momentum_update_tail_kernel, dim3(blocks_for(count - done, 256)), dim3(256), 0, stream, theta, vel, grad,
                           done, count, mu, alpha);
     return cudaSuccess;
+}
+
+// Same update, and the gradient arena is left all-zero (small networks: the producers of the next step accumulate
+// atomically and would otherwise each need a memset node in front).  count % 4 == 0 and 16-byte aligned arenas.
+cudaError_t momentum_update_zero_launch(float* theta, float* vel, float* grad, int64_t count, float mu, float alpha,
+                                        cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    if ((count & 3) || ((reinterpret_cast<uintptr_t>(theta) | reinterpret_cast<uintptr_t>(vel) | reinterpret_cast<uintptr_t>(grad)) & 15))
+        return cudaErrorInvalidValue;
+    const int64_t n4 = count / 4, want = (n4 + 255) / 256;
+    return launch_pdl(momentum_update_kernel<true>, dim3(unsigned(want < 148 * 8 ? want : 148 * 8)), dim3(256), 0, stream,
+                      reinterpret_cast<float4*>(theta), reinterpret_cast<float4*>(vel), reinterpret_cast<float4*>(grad), n4, mu, alpha);
 }
 
 cudaError_t theta_ref_to_internal_launch(const float* ref, float* w, int in, int out, int64_t ldw, cudaStream_t s) {

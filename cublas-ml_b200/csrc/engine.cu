@@ -181,6 +181,7 @@ struct b2nn_ctx {
     P2pPeers peers{};
     int* p2p_flags = nullptr;                 // local flag block: [kind][layer][rank], kind 0 = wg_done, 1 = w_done
     int p2p_step = 0;
+    bool g_zero = false;                      // the whole gradient arena is known to be zero (small nets: the update leaves it so)
     std::vector<int64_t> p2p_small_off;       // per layer: float offset of its slot block in the small-layer area, -1 = none
     int64_t p2p_small_floats = 0;
     std::vector<int64_t> p2p_small_cnt;       // floats per slot the area was sized for (guards against a later set_layers)
@@ -513,7 +514,8 @@ struct ProfScope {
 
 int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind) {
     ProfScope scope(c, kind, op.tc, 2.0 * double(op.g.M) * double(op.g.N) * double(op.g.K), 0.0);
-    if (op.zero_first)
+    const bool d_is_grad = op.g.D >= c->G && op.g.D < c->G + c->total_int;
+    if (op.zero_first && !(d_is_grad && c->g_zero))
         B2_CUDA(cudaMemsetAsync(op.g.D, 0, sizeof(float) * size_t(op.g.ldd) * op.g.N, c->stream));
     if (op.tc) {
         if (op.a_is_x && x_start != 0) {
@@ -572,7 +574,7 @@ int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_d
             SkinnyArgs a{};
             a.a = c->ws.a[j - 1]; a.delta = c->ws.delta[j]; a.W = c->W + li.w_off; a.delta_prev = c->ws.delta[j - 1];
             a.G = c->G + li.w_off; a.ld = c->ws.ld; a.ldw = li.ldw; a.rows = sp.rows; a.H = li.in; a.K = li.out; a.act_kind = d->act_kind;
-            B2_CUDA(cudaMemsetAsync(a.G, 0, sizeof(float) * size_t(li.ldw) * li.out, c->stream));
+            if (!c->g_zero) B2_CUDA(cudaMemsetAsync(a.G, 0, sizeof(float) * size_t(li.ldw) * li.out, c->stream));
             B2_CUDA(skinny_bwd_launch(a, c->stream));
             ++c->launches;
             if (!c->ws.delta_lo.empty() && c->ws.delta_lo[j - 1])      // fp32-grade mode: the next contraction wants the low part too
@@ -713,7 +715,7 @@ int run_tail(b2nn_ctx* c, const StepPlan& sp, const b2nn_train_desc* d, const fl
     a.cost_sum = cost_slot; a.err_sum = err_slot;
     a.rows = rows; a.H = li.in; a.K = li.out;
     a.out_kind = out_kind; a.cost_kind = cost_kind; a.act_kind = d->act_kind;
-    if (a.G_inline) B2_CUDA(cudaMemsetAsync(a.G_inline, 0, sizeof(float) * size_t(li.ldw) * li.out, c->stream));
+    if (a.G_inline && !c->g_zero) B2_CUDA(cudaMemsetAsync(a.G_inline, 0, sizeof(float) * size_t(li.ldw) * li.out, c->stream));
     {
         ProfScope scope(c, 3, false, 2.0 * double(rows) * (li.in + 1) * li.out * (train ? 3 : 1),
                         4.0 * double(rows) * (li.in + 1) * (train ? 2 : 1));
@@ -733,6 +735,8 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
                const float* Y, int64_t ldy, int64_t x_start, int64_t rows, int64_t global_rows, double* cost_slot) {
     const bool custom_oc = custom_outcost(d);
     StepPlan& sp = get_plan(c, rows, X, ldx, x_total, x_aligned, prec, d->act_kind, custom_oc);
+    // "gradient arena is all-zero" survives this step only if it ends in the zeroing update (any other exit clears it)
+    struct GZeroGuard { b2nn_ctx* c; bool keep; ~GZeroGuard() { if (!keep) c->g_zero = false; } } gz{c, false};
     if (c->comm) c->prof_chain = false;      // waits on the exchange streams sit between steps: not part of any launch
     bool any_fused = false;
     for (char f : sp.fused) any_fused = any_fused || f;
@@ -815,9 +819,18 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
         // all layers in one pass: W, V, G share one arena layout (cublasNN.cpp:558-566 is 2 launches per layer)
         {
             ProfScope scope(c, 4, false, 0.0, 20.0 * double(c->total_int));
+            // small nets: the update also zeroes the gradient arena, so the atomically accumulating producers of the next
+            // step (split-K, in-kernel gradient sums) need no memset node in front of them — two to three fewer links in
+            // a chain of few-microsecond launches.  Large nets keep the memsets (the extra 4 B per weight would cost more).
+            const bool zeroing = !(prec == B2NN_PREC_TF32X3 && c->W_lo) && c->total_int <= (int64_t(1) << 20) &&
+                                 (c->total_int & 3) == 0 && !std::getenv("B2NN_NO_ZERO_UPDATE");
             if (prec == B2NN_PREC_TF32X3 && c->W_lo)
                 B2_CUDA(momentum_update_lo_launch(c->W, c->V, c->G, c->W_lo, c->total_int, d->momentum, alpha, c->stream));
-            else
+            else if (zeroing) {
+                B2_CUDA(momentum_update_zero_launch(c->W, c->V, c->G, c->total_int, d->momentum, alpha, c->stream));
+                c->g_zero = true;
+                gz.keep = true;
+            } else
                 B2_CUDA(momentum_update_launch(c->W, c->V, c->G, c->total_int, d->momentum, alpha, c->stream));
         }
         ++c->launches;
@@ -1015,6 +1028,7 @@ int b2nn_set_layers(b2nn_ctx* c, const int* layers, int n_layers, int init_kind,
     B2_CUDA(cudaMemsetAsync(c->W, 0, sizeof(float) * (c->total_int + 64), c->stream));
     B2_CUDA(cudaMemsetAsync(c->V, 0, sizeof(float) * c->total_int, c->stream));
     B2_CUDA(cudaMemsetAsync(c->G, 0, sizeof(float) * c->total_int, c->stream));
+    c->g_zero = false;        // a fresh arena: the first step zeroes what it accumulates into
 
     // One uniform draw over the whole reference-layout arena, then the per-layer rescale (cublasNN.cpp:314-326).
     float* ref = nullptr;

@@ -95,6 +95,8 @@ struct OutputArgs {
 cudaError_t output_layer_launch(const OutputArgs& a, cudaStream_t stream);
 cudaError_t momentum_update_launch(float* theta, float* vel, const float* grad, int64_t count, float mu, float alpha,
                                    cudaStream_t stream);
+cudaError_t momentum_update_zero_launch(float* theta, float* vel, float* grad, int64_t count, float mu, float alpha,
+                                        cudaStream_t stream);   // ... and leaves grad all-zero
 // reference arena (Theta_j (in+1) x out col-major, bias row 0)  <->  internal (out rows of ldw floats, bias at col in)
 cudaError_t theta_ref_to_internal_launch(const float* ref, float* w, int in, int out, int64_t ldw, cudaStream_t s);
 cudaError_t theta_internal_to_ref_launch(const float* w, float* ref, int in, int out, int64_t ldw, cudaStream_t s);
