@@ -473,12 +473,8 @@ int g_reserved_sms = 0;      // SMs left free for a concurrent communication ker
 template <int BN, bool A_MN, bool B_MN, int NCTA, bool X3>
 cudaError_t launch_one(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
     auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NCTA, X3>;
-    static bool attr_set = false;   // per instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> done{0};   // per instantiation, one bit per device
+    if (cudaError_t e = ensure_dyn_smem(kern, SMEM_LIMIT, done)) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pl.grid_x, 1, 1);
     cfg.blockDim = dim3(NUM_THREADS, 1, 1);

@@ -9,6 +9,7 @@
 // stream.  B2NN_PDL=0 launches everything fully serialised (for A/B measurements).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdlib>
 #include <utility>
 
@@ -17,6 +18,20 @@ namespace b2 {
 __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+}
+
+// Opt a kernel into more than 48 KB of dynamic shared memory once per DEVICE (the attribute is per device; a process
+// may hold contexts on several GPUs).  `done` is a function-local static of the launch site: one bit per device ordinal.
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kernel, int bytes, std::atomic<unsigned long long>& done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
 }
 
 inline bool pdl_enabled() {

@@ -164,12 +164,8 @@ __global__ void __launch_bounds__(SK_THREADS, 4) skinny_bwd_kernel(const SkinnyA
 template <int KMAX, bool EXACT>
 cudaError_t launch_k(const SkinnyArgs& a, dim3 grid, cudaStream_t s) {
     constexpr size_t smem = sizeof(float) * 2 * (SK_ROWS * SK_PITCH + KMAX * SK_COLS);
-    static bool set = false;
-    if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(skinny_bwd_kernel<KMAX, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        set = true;
-    }
+    static std::atomic<unsigned long long> done{0};
+    if (cudaError_t e = ensure_dyn_smem(skinny_bwd_kernel<KMAX, EXACT>, int(smem), done)) return e;
     return launch_pdl(skinny_bwd_kernel<KMAX, EXACT>, grid, dim3(SK_THREADS), smem, s, a);
 }
 

@@ -528,20 +528,20 @@ __global__ void __launch_bounds__(TILE_THREADS) tail_tile_kernel(const TailArgs 
 
 template <int GMAX>
 cudaError_t launch_tile(const TailArgs& a, unsigned grid, size_t smem, cudaStream_t s) {
-    static bool set = false;
-    if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_tile_kernel<GMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e != cudaSuccess) return e; set = true; }
+    static std::atomic<unsigned long long> done{0};
+        if (cudaError_t e = ensure_dyn_smem(tail_tile_kernel<GMAX>, 100 * 1024, done)) return e;
     return launch_pdl(tail_tile_kernel<GMAX>, dim3(grid), dim3(TILE_THREADS), smem, s, a);
 }
 
 template <int KMAX>
 cudaError_t launch_small(const TailArgs& a, bool train, unsigned grid, size_t smem, cudaStream_t s) {
     if (train) {
-        static bool set = false;
-        if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_small_kernel<KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e != cudaSuccess) return e; set = true; }
+        static std::atomic<unsigned long long> done{0};
+        if (cudaError_t e = ensure_dyn_smem(tail_small_kernel<KMAX, true>, 100 * 1024, done)) return e;
         return launch_pdl(tail_small_kernel<KMAX, true>, dim3(grid), dim3(SMALL_THREADS), smem, s, a);
     } else {
-        static bool set = false;
-        if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_small_kernel<KMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e != cudaSuccess) return e; set = true; }
+        static std::atomic<unsigned long long> done{0};
+        if (cudaError_t e = ensure_dyn_smem(tail_small_kernel<KMAX, false>, 100 * 1024, done)) return e;
         return launch_pdl(tail_small_kernel<KMAX, false>, dim3(grid), dim3(SMALL_THREADS), smem, s, a);
     }
 }
@@ -549,12 +549,12 @@ cudaError_t launch_small(const TailArgs& a, bool train, unsigned grid, size_t sm
 template <int KMAX>
 cudaError_t launch_k(const TailArgs& a, bool train, unsigned grid, size_t smem, cudaStream_t s) {
     if (train) {
-        static bool set = false;
-        if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_kernel<KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e != cudaSuccess) return e; set = true; }
+        static std::atomic<unsigned long long> done{0};
+        if (cudaError_t e = ensure_dyn_smem(tail_kernel<KMAX, true>, 200 * 1024, done)) return e;
         return launch_pdl(tail_kernel<KMAX, true>, dim3(grid), dim3(TAIL_THREADS), smem, s, a);
     } else {
-        static bool set = false;
-        if (!set) { cudaError_t e = cudaFuncSetAttribute(tail_kernel<KMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); if (e != cudaSuccess) return e; set = true; }
+        static std::atomic<unsigned long long> done{0};
+        if (cudaError_t e = ensure_dyn_smem(tail_kernel<KMAX, false>, 200 * 1024, done)) return e;
         return launch_pdl(tail_kernel<KMAX, false>, dim3(grid), dim3(TAIL_THREADS), smem, s, a);
     }
 }
