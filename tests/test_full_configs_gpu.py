@@ -74,6 +74,38 @@ def test_c1_secondary_variant_full_batch_against_reference_live(b2nn, oracle, pr
     assert terr <= {"fp32": 2e-3, "tf32": 1e-1}[prec], (prec, terr)
 
 
+def test_c3_full_size_tf32_loss_curve_tracks_fp32_grade(b2nn):
+    """Config C3 at full size for 24 momentum steps (3 epochs of 8 batches of 8192): the tf32 run's printed cost must track
+    the fp32-grade (3xTF32) run's — the size-independent form of the tf32 bound stated in test_train_gpu.py — and both
+    must learn (the cost of batch 0 falls from epoch to epoch)."""
+    layers, B, nb, K = [784, 4096, 4096, 10], 8192, 8, 10
+    rng = np.random.Generator(np.random.PCG64(7))
+    m = B * nb
+    x = rng.standard_normal((m, 784)).astype(np.float32)
+    lab = (x @ rng.standard_normal((784, K)).astype(np.float32)).argmax(1)
+    x_cm = np.empty((785, m), dtype=np.float32)          # column-major m x 785 with the ones column first
+    x_cm[0] = 1.0
+    x_cm[1:] = x.T
+    y_cm = np.zeros((K, m), dtype=np.float32)
+    y_cm[lab, np.arange(m)] = 1.0
+    curves = {}
+    for prec, code in (("tf32", 1), ("tf32x3", 3)):
+        net = b2nn.Net()
+        net.set_layers(layers, b2nn.INIT_2, 42)
+        net.set_train_data(x_cm.reshape(-1), y_cm.reshape(-1), m)
+        d = b2nn.make_desc(momentum=0.9, rate=0.02, iters=3, display=1, batch_num=nb, classify=True, act=b2nn.ACT_TANH,
+                           out=b2nn.OUT_SOFTMAX, cost=b2nn.COST_CROSSENTROPY, precision=code)
+        out = net.train(d)
+        curves[prec] = (np.array(out.log_J), out.final_cost, out.error_count)
+        net.close()
+    j32, f32, e32 = curves["tf32x3"]
+    j19, f19, e19 = curves["tf32"]
+    assert len(j32) == 3 and j32[-1] < j32[0] and j19[-1] < j19[0]
+    np.testing.assert_allclose(j19, j32, rtol=3e-2)
+    assert abs(f19 - f32) <= 3e-2 * abs(f32)
+    assert abs(e19 - e32) <= 0.01 * m
+
+
 def test_c2_full_size_against_reference_live_and_oracle(b2nn, oracle):
     """BASELINE.json config C2 (bikeshare regression, full batch).  With the reference's rate 0.003 on targets ~10^2 the
     trajectory starts to oscillate around iteration 180 and is chaotic from there: any two fp32 runs (the reference's, this
