@@ -63,6 +63,8 @@ struct StepPlan {
     bool use_tail = false;       // skinny last layer: forward + output + delta backprop fused in tail.cu
     bool tail_inline_g = false;  // ... and its weight gradient too
     bool skinny_bwd = false;     // narrow last layer behind a wide hidden layer: delta backprop + gradient in one pass (skinny.cu)
+    bool micro = false;          // the whole net fits shared memory: forward + backward + gradients in one kernel (micro.cu)
+    MicroArgs micro_args{};
 };
 
 struct Workspace {
@@ -419,6 +421,21 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         sp.use_tail = !custom && !no_tail && tail_supported(last.out, last.in, false);
         sp.tail_inline_g = sp.use_tail && tail_supported(last.out, last.in, true);
         sp.skinny_bwd = !sp.use_tail && !custom && nw >= 2 && skinny_bwd_supported(last.out, last.in, w.ld);
+        // tiny nets (every weight in shared memory, single GPU, built-in functions): one kernel for the whole step
+        if (!custom && !no_tail && !c->comm && nw <= MICRO_MAX_LAYERS && c->total_int <= 16384) {
+            MicroArgs& m = sp.micro_args;
+            m = MicroArgs{};
+            m.W = c->W; m.G = c->G; m.nw = nw; m.total = int(c->total_int);
+            int off = 0, width = 0;
+            for (int j = 0; j < nw; ++j) {
+                m.in[j] = c->L[j].in; m.out[j] = c->L[j].out; m.ldw[j] = int(c->L[j].ldw); m.w_off[j] = int(c->L[j].w_off);
+                m.act_off[j] = off;
+                off += (c->L[j].in + 1) * 33;
+                width = std::max(width, c->L[j].out);
+            }
+            m.act_total = off; m.max_width = width; m.act_kind = act_kind;
+            sp.micro = micro_supported(m);
+        }
     }
     for (int j = 0; j < nw; ++j) {
         const LayerInfo& li = c->L[j];
@@ -748,7 +765,19 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
             B2_CUDA(p2p_gate_layers_launch(c->p2p_flags + 1 * P2P_MAX_LAYERS * P2P_MAX_WORLD, mask, c->nranks, c->p2p_step - 1, c->stream));
         }
     }
-    int rc = forward_pass(c, sp, x_start, d);
+    int rc = B2NN_OK;
+    const bool micro = sp.micro && !custom_oc && !c->comm;
+    if (micro) {
+        MicroArgs a = sp.micro_args;
+        a.X = X + x_start; a.ldx = ldx; a.Y = Y + x_start; a.ldy = ldy; a.rows = rows; a.cost_sum = cost_slot;
+        a.out_kind = d->classify ? d->out_kind : B2NN_OUT_LINEAR;
+        a.cost_kind = d->classify ? d->cost_kind : B2NN_COST_SQUARED;
+        if (!c->g_zero) B2_CUDA(cudaMemsetAsync(c->G, 0, sizeof(float) * size_t(c->total_int), c->stream));
+        ProfScope scope(c, 0, false, 6.0 * double(rows) * double(c->total_int), 4.0 * double(rows) * (c->layers[0] + 1));
+        B2_CUDA(micro_launch(a, c->stream));
+        ++c->launches;
+    } else {
+    rc = forward_pass(c, sp, x_start, d);
     if (rc) return rc;
     if (custom_oc) rc = output_custom(c, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
     else if (sp.use_tail) rc = run_tail(c, sp, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
@@ -762,6 +791,7 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
     }
     rc = backward_pass(c, sp, x_start, d);
     if (rc) return rc;
+    }
     const float alpha = -d->rate / float(global_rows);      // cublasNN.cpp:544, 601
     const int nw = int(c->L.size());
     if (c->comm) {

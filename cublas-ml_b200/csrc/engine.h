@@ -149,6 +149,23 @@ struct SkinnyArgs {
 bool skinny_bwd_supported(int K, int H, int64_t ld);
 cudaError_t skinny_bwd_launch(const SkinnyArgs& a, cudaStream_t s);
 
+// A whole step (forward, output, backward, gradients of every layer) of a network whose weights fit shared memory
+// (micro.cu).  W / G are the internal arenas (layer l at w_off[l], out[l] rows of ldw[l]); X, Y point at the batch's first
+// sample; the caller zeroes G.
+constexpr int MICRO_MAX_LAYERS = 8;
+struct MicroArgs {
+    const float* W; float* G;
+    const float* X; int64_t ldx;
+    const float* Y; int64_t ldy;
+    double* cost_sum;              // may be null
+    int64_t rows;
+    int nw, total, act_total, max_width;
+    int in[MICRO_MAX_LAYERS], out[MICRO_MAX_LAYERS], ldw[MICRO_MAX_LAYERS], w_off[MICRO_MAX_LAYERS], act_off[MICRO_MAX_LAYERS];
+    int act_kind, out_kind, cost_kind;
+};
+bool micro_supported(const MicroArgs& a);
+cudaError_t micro_launch(const MicroArgs& a, cudaStream_t s);
+
 // ---- peer-memory data parallelism (p2p.cu) ---------------------------------------------------------------------------
 constexpr int P2P_MAX_WORLD = 8;
 constexpr int P2P_MAX_LAYERS = 64;
