@@ -430,7 +430,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
             for (int j = 0; j < nw; ++j) {
                 m.in[j] = c->L[j].in; m.out[j] = c->L[j].out; m.ldw[j] = int(c->L[j].ldw); m.w_off[j] = int(c->L[j].w_off);
                 m.act_off[j] = off;
-                off += (c->L[j].in + 1) * 33;
+                off += (c->L[j].in + 1) * MICRO_PITCH;
                 width = std::max(width, c->L[j].out);
             }
             m.act_total = off; m.max_width = width; m.act_kind = act_kind;

@@ -153,6 +153,7 @@ cudaError_t skinny_bwd_launch(const SkinnyArgs& a, cudaStream_t s);
 // (micro.cu).  W / G are the internal arenas (layer l at w_off[l], out[l] rows of ldw[l]); X, Y point at the batch's first
 // sample; the caller zeroes G.
 constexpr int MICRO_MAX_LAYERS = 8;
+constexpr int MICRO_PITCH = 36;        // floats per shared-memory activation row (act_off / act_total are in these units)
 struct MicroArgs {
     const float* W; float* G;
     const float* X; int64_t ldx;

@@ -11,7 +11,7 @@
 //   forward   z_j = sum_k W[j][k] a[k][s]       warps split the output units in blocks of 4 (one read of a per 4 FMA)
 //   backward  d_k = f'(a_k) sum_j W[j][k] d[j]  warps split the input units in blocks of 4 (W row chunks are one 16-byte
 //                                                broadcast read)
-//   gradient  G[j][k] += sum_s d[j][s] a[k][s]  threads own (j,k) pairs: conflict-free reads (row pitch 33), no shuffles
+//   gradient  G[j][k] += sum_s d[j][s] a[k][s]  threads own (j,k) pairs: conflict-free 16-byte reads (row pitch 36), no shuffles
 // Exact fp32.  Same arithmetic per element as the separate kernels; only the summation order over samples differs.
 #include "engine.h"
 #include <cstdlib>
@@ -22,9 +22,10 @@
 namespace b2 {
 namespace {
 
-constexpr int MC_THREADS = 256;
+constexpr int MC_THREADS = 512;
 constexpr int MC_WARPS = MC_THREADS / 32;
-constexpr int MC_PITCH = 33;
+constexpr int MC_PITCH = MICRO_PITCH;  // 36 floats per row: 16-byte aligned rows, conflict-free for lane = sample and for
+                                       // 16-byte reads with lane = row (bank = 4 row + s mod 32)
 
 __device__ __forceinline__ float act_fwd(int kind, float z) {
     return kind == B2NN_ACT_SIGMOID ? sigmoid_f(z) : tanhf(z);
@@ -135,8 +136,12 @@ __global__ void __launch_bounds__(MC_THREADS) micro_mlp_kernel(const MicroArgs p
                 const float* dp = dl + j * MC_PITCH;
                 const float* ap = al + k * MC_PITCH;
                 float g0 = 0.f, g1 = 0.f;
-#pragma unroll 8
-                for (int s = 0; s < 32; s += 2) { g0 = fmaf(dp[s], ap[s], g0); g1 = fmaf(dp[s + 1], ap[s + 1], g1); }
+#pragma unroll
+                for (int s = 0; s < 32; s += 4) {
+                    const float4 dv = *reinterpret_cast<const float4*>(dp + s);
+                    const float4 av = *reinterpret_cast<const float4*>(ap + s);
+                    g0 = fmaf(dv.x, av.x, g0); g1 = fmaf(dv.y, av.y, g1); g0 = fmaf(dv.z, av.z, g0); g1 = fmaf(dv.w, av.w, g1);
+                }
                 Gl[j * ldw + k] += g0 + g1;
             }
             if (l > 0) {
