@@ -22,7 +22,7 @@
 namespace b2 {
 namespace {
 
-constexpr int MC_THREADS = 512;
+constexpr int MC_THREADS = 512;             // measured on C2: 256 / 512 / 1024 threads -> 40.8 / 32.8 / 34.8 us per step
 constexpr int MC_WARPS = MC_THREADS / 32;
 constexpr int MC_PITCH = MICRO_PITCH;  // 36 floats per row: 16-byte aligned rows, conflict-free for lane = sample and for
                                        // 16-byte reads with lane = row (bank = 4 row + s mod 32)
