@@ -259,9 +259,11 @@ def run_ours(args):
     sampler2.join(timeout=2)
     pk, pk_src = peaks()
     # MEASURED_PEAKS.json holds a burst and a sustained (power-capped) bf16 figure.  The leg is compared with the one
-    # whose regime it ran in: sustained once NVML reports the power cap or the SM clock has left boost, burst otherwise.
+    # whose regime it ran in: sustained once the median SM clock of the leg has dropped below 0.85 x max, burst otherwise.
     c2 = sampler2.summary()
-    capped = "sw_power_cap" in c2.get("reasons", []) or (c2.get("sm_mhz") and c2.get("sm_max_mhz") and c2["sm_mhz"] < 0.93 * c2["sm_max_mhz"])
+    # (conservative: a power-cap flag alone does not switch to the lower sustained figure; the median SM clock of the leg must
+    # actually have dropped to the capped regime — MEASURED_PEAKS.json saw 0.66 x max under its sustained load)
+    capped = bool(c2.get("sm_mhz") and c2.get("sm_max_mhz") and c2["sm_mhz"] < 0.85 * c2["sm_max_mhz"])
     bf16_key = "bf16_tflops_sustained" if capped else "bf16_tflops"
     bf16_peak = pk.get(bf16_key, pk.get("bf16_tflops", 1400.0))
     gemm_ms = sum(prof[k]["ms"] for k in ("forward", "backprop", "wgrad"))
