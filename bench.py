@@ -446,12 +446,13 @@ def run_reference(args):
     secs = max(t_long - t_short, 1e-9)
     value = B * K / secs
     line = {"impl": "reference", "metric": "train_samples_per_sec", "value": round(value, 1), "unit": "samples/s",
-            "n_gpus": 1, "steps": K, "warmup": it_warm * nb, "ms_per_step": round(secs / K * 1e3, 4),
+            "n_gpus": int(getattr(args, "gpus", 1) or 1), "gpus_used": 1, "steps": K, "warmup": it_warm * nb,
+            "ms_per_step": round(secs / K * 1e3, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32" if os.environ.get("NVIDIA_TF32_OVERRIDE", "0") != "1" else "tf32(cuBLAS override)",
             "data": "synthetic",
             "config": {"workload": desc_text, "layers": layers, "batch_per_gpu": B, "global_batch": B,
-                       "parallelism": "dp1 (the reference is single-GPU)", "math": env_note,
+                       "parallelism": "dp1 (the reference is single-GPU: it runs on cuda:0 whatever --gpus says, see gpus_used)", "math": env_note,
                        "timing": "difference of two trainClassifyMomentum calls (epochs E and E+K/nb): setup and final cost cancel"},
             "tflops": round(step_flops(layers, B) * K / secs / 1e12, 2),
             "cpu_baseline": {"value": round(value, 1), "unit": "samples/s", "cores": 0, "kind": "reference",
