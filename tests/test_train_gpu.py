@@ -360,6 +360,35 @@ def test_wide_hidden_narrow_output_ragged_batches(b2nn, oracle, act, prec):
     net.close()
 
 
+@pytest.mark.parametrize("classify", [True, False])
+def test_tiny_net_whole_step_kernel_many_sample_groups(b2nn, oracle, classify):
+    """A net whose weights fit shared memory runs each step as one kernel (micro.cu).  10 007 rows per batch are 313
+    groups of 32 samples over at most 148 blocks, so every block walks several groups (and the last one is ragged)."""
+    layers, m = ([5, 8, 6, 3] if classify else [5, 8, 6, 2]), 20014
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((m, 5)).astype(np.float32)
+    x_cm = oracle.with_bias_colmajor(x)
+    if classify:
+        lab = (x @ rng.standard_normal((5, 3)).astype(np.float32)).argmax(1)
+        y_cm = oracle.one_hot_colmajor(lab, 3)
+    else:
+        y_cm = oracle.colmajor(np.tanh(x @ rng.standard_normal((5, 2)).astype(np.float32)).astype(np.float32))
+    net = b2nn.Net()
+    net.set_layers(layers, b2nn.INIT_2, 3)
+    th0 = net.get_weights()
+    net.set_train_data(x_cm, y_cm, m)
+    kw = dict(momentum=0.9, rate=0.05, iters=6, display=1, batch_num=2, classify=classify)
+    d = b2nn.make_desc(act=b2nn.ACT_TANH, out=b2nn.OUT_SOFTMAX if classify else b2nn.OUT_LINEAR,
+                       cost=b2nn.COST_CROSSENTROPY if classify else b2nn.COST_SQUARED, precision=b2nn.PREC_AUTO, **kw)
+    out = net.train(d)
+    assert out.kernel_launches == 2 * out.steps, "tiny nets take two launches per step: the whole-step kernel and the update"
+    ref = oracle.train(layers, x_cm, y_cm, m, hidden_act=oracle.TANH, theta0=th0, precision="f64", **kw)
+    assert np.abs(net.get_weights() - ref.theta).max() <= 2e-4 * np.abs(ref.theta).max()
+    np.testing.assert_allclose(out.log_J, ref.log_J, rtol=2e-4)
+    assert abs(out.final_cost - ref.final_cost) <= 2e-4 * abs(ref.final_cost)
+    net.close()
+
+
 def _addr(b2nn, mangled):
     import ctypes
     return ctypes.cast(getattr(b2nn.lib(), mangled), ctypes.c_void_p).value
