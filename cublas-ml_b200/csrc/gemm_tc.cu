@@ -9,14 +9,15 @@
 //   wgrad     G = d^T a    : A = a_{j-1}  K-major  ([m = in  ][k = sample]),  B = delta_j  K-major  ([n = out][k = sample])
 // replacing the three cublasSgemm op combinations of the reference (cublasNN.cpp:645-659 NN, :674-675 NT, :680-684 TN).
 //
-// CTA = 6 warps, one 128 x BN output tile, K streamed in blocks of 32 floats (= one 128-byte swizzle row):
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d into a STAGES-deep shared-memory ring, mbarrier complete_tx
-//   warp 1      TMEM allocator + MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::tf32 (128 x BN x 8),
-//               tcgen05.commit releases ring slots and finally signals the epilogue
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers, fused activation / derivative, coalesced
-//               stores (lane = sample index, so each warp store is one 128-byte line)
+// CTA = 18 warps (persistent, one CTA per SM, normally paired into clusters of two that share a 256 x BN tile), K
+// streamed in blocks of 32 floats (= one 128-byte swizzle row):
+//   warp 0       TMA producer: cp.async.bulk.tensor into a STAGES-deep shared-memory ring, mbarrier complete_tx
+//   warp 1       TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (128 or 256 x BN x 8),
+//                tcgen05.commit releases ring slots and finally signals the epilogue
+//   warps 2..17  epilogue: tcgen05.ld 32 lanes x 16 columns -> registers, fused activation / derivative, coalesced
+//                stores (lane = sample index, so each warp store is one 128-byte line); two TMEM accumulator buffers
 // Tails in every dimension are handled by TMA zero fill on the load side and predication on the store side.
-// Shared-memory tiles use the 128-byte swizzle; the UMMA shared-memory descriptors are built per K step:
+// Shared-memory tiles use the 128-byte swizzle; the UMMA shared-memory descriptors are "stage 0 + uniform offset":
 //   K-major  tile: rows of 128 B, 8-row groups 1024 B apart (SBO); K step of 8 floats = +32 B on the start address
 //   MN-major tile: 32-float x 32-k boxes of 4096 B written with the 32-byte-chunk 128 B swizzle (the only one
 //                  tcgen05 accepts for MN-major 4-byte operands); atoms along M/N are 4096 B apart (LBO), 4-k groups
@@ -94,7 +95,7 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f,
 // traffic per multiply-add drops by a third; the leader CTA issues the MMAs for both.
 //   warp 0      TMA producer (ring of `stages` slots, runs ahead across tiles)
 //   warp 1      TMEM allocator; in the leader CTA also the MMA issuer (one lane)
-//   warps 2..9  epilogue: TMEM -> registers -> fused activation / derivative -> coalesced global stores.  Two
+//   warps 2..17 epilogue: TMEM -> registers -> fused activation / derivative -> coalesced global stores.  Two
 //               accumulator buffers in TMEM (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // X3 = true is the fp32-grade mode ("3xTF32"): tcgen05 TRUNCATES fp32 inputs to tf32 (measured, tools/
