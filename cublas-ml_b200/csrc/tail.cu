@@ -4,8 +4,10 @@
 // contractions are "GEMMs" with N = K or K-depth = K: a tensor-core tile is >90 % padding and the work is pure memory
 // streaming of the last hidden activation a (rows x (H+1)).  The reference spends seven launches there
 // (cublasSgemm N,N :658-659; activationOutput :606; vecVecSubtract :666; cost :613-614; activationDerivative :673;
-// cublasSgemm N,T :674-675; vecVecElementMultiply :676).  This kernel does, per block of 32 samples x 8 warps:
-//   pass 1   z = [a,1] W^T           (fp32 FFMA, W chunked through shared memory, h split over the 8 warps)
+// cublasSgemm N,T :674-675; vecVecElementMultiply :676).  Three kernels share the work (tail_launch picks one):
+// tail_tile_kernel (training, small hidden layer: the 32-sample tile of a lives in shared memory), tail_small_kernel
+// (inference, one warp per 32 samples) and tail_kernel, which does, per block of 32 samples x 16 warps:
+//   pass 1   z = [a,1] W^T           (fp32 FFMA, W chunked through shared memory, h split over the 16 warps)
 //            h = softmax / sigmoid / identity (z);  delta = h - y;  cost, argmax, error count
 //   pass 2   delta_prev = (delta W)[no bias] .* f'(a)          (second read of a comes from L2)
 //            optionally G = delta^T [a,1] for small layers (warp-shuffle reduction over the 32 samples, block-local
