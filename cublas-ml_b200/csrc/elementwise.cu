@@ -29,49 +29,107 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 //   argmax (kernels.cu:74-86, with the out-of-bounds store fixed) and error count (kernels.cu:88-93).
 // Softmax is max-shifted: identical to the reference whenever the reference does not overflow.
 // cost_sum / err_sum are double accumulators.
-__global__ void __launch_bounds__(OUT_THREADS) output_layer_kernel(OutputArgs a, double* cost_sum, double* err_sum) {
-    pdl_enter();
-    __shared__ double sh[OUT_THREADS / 32];
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    double cost = 0.0, err = 0.0;
-    if (i < a.rows) {
-        const int K = a.K;
-        float zmax = -INFINITY, total = 0.f;
-        if (a.out_kind == B2NN_OUT_SOFTMAX) {
-            for (int k = 0; k < K; ++k) zmax = fmaxf(zmax, a.z[int64_t(k) * a.ldz + i]);
-            for (int k = 0; k < K; ++k) total += expf(a.z[int64_t(k) * a.ldz + i] - zmax);
-        }
-        float best_h = 0.f, best_y = 0.f; int arg_h = 0, arg_y = 0;
-        for (int k = 0; k < K; ++k) {
-            const float zv = a.z[int64_t(k) * a.ldz + i];
+// One sample (row i).  KMAX > 0: K <= KMAX, z and y are read into registers with every load in flight at once (with
+// run-time loop bounds the loads went out one per iteration: 2 K dependent L2 round trips, ~12 us for 8192 rows).
+template <int KMAX>
+__device__ __forceinline__ void output_row(const OutputArgs& a, int64_t i, bool want_cost, bool want_err, double& cost, double& err) {
+    const int K = a.K;
+    float zv[KMAX], yv[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        zv[k] = k < K ? a.z[int64_t(k) * a.ldz + i] : -INFINITY;
+        yv[k] = (k < K && a.y) ? a.y[int64_t(k) * a.ldy + i] : 0.f;
+    }
+    float zmax = -INFINITY, total = 0.f;
+    if (a.out_kind == B2NN_OUT_SOFTMAX) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) zmax = fmaxf(zmax, zv[k]);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) if (k < K) { zv[k] = expf(zv[k] - zmax); total += zv[k]; }
+    }
+    float best_h = 0.f, best_y = 0.f; int arg_h = 0, arg_y = 0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
             float h;
-            if (a.out_kind == B2NN_OUT_SOFTMAX) h = expf(zv - zmax) / total;
-            else if (a.out_kind == B2NN_OUT_SIGMOID) h = sigmoid_f(zv);
-            else h = zv;
+            if (a.out_kind == B2NN_OUT_SOFTMAX) h = zv[k] / total;
+            else if (a.out_kind == B2NN_OUT_SIGMOID) h = sigmoid_f(zv[k]);
+            else h = zv[k];
             if (a.h) a.h[int64_t(k) * a.ldh + i] = h;
             if (h > best_h) { best_h = h; arg_h = k; }
             if (a.y) {
-                const float yv = a.y[int64_t(k) * a.ldy + i];
-                if (yv > best_y) { best_y = yv; arg_y = k; }
-                const float d = h - yv;
+                if (yv[k] > best_y) { best_y = yv[k]; arg_y = k; }
+                const float d = h - yv[k];
                 if (a.delta) a.delta[int64_t(k) * a.ldd + i] = d;
-                if (cost_sum) {
+                if (want_cost) {
                     float c = 0.f;
                     if (a.cost_kind == B2NN_COST_SQUARED) c = d * d;
                     else {
-                        if (yv != 0.f) c += -yv * logf(h);
-                        if (a.cost_kind == B2NN_COST_NEGLNMAX && yv != 1.f) c += -(1.f - yv) * logf(1.f - h);
+                        if (yv[k] != 0.f) c += -yv[k] * logf(h);
+                        if (a.cost_kind == B2NN_COST_NEGLNMAX && yv[k] != 1.f) c += -(1.f - yv[k]) * logf(1.f - h);
                         c = fabsf(c);
                     }
                     cost += double(c);
                 }
             }
         }
-        if (a.pred) a.pred[i] = float(arg_h);
-        if (err_sum) {
-            if (a.y_labels) err = (float(arg_h) != a.y_labels[i]) ? 1.0 : 0.0;
-            else if (a.y)   err = (arg_h != arg_y) ? 1.0 : 0.0;
+    }
+    if (a.pred) a.pred[i] = float(arg_h);
+    if (want_err) {
+        if (a.y_labels) err = (float(arg_h) != a.y_labels[i]) ? 1.0 : 0.0;
+        else if (a.y)   err = (arg_h != arg_y) ? 1.0 : 0.0;
+    }
+}
+
+// Any K: the same row, walking memory (the generic path the register version was derived from).
+__device__ __forceinline__ void output_row_any(const OutputArgs& a, int64_t i, bool want_cost, bool want_err, double& cost, double& err) {
+    const int K = a.K;
+    float zmax = -INFINITY, total = 0.f;
+    if (a.out_kind == B2NN_OUT_SOFTMAX) {
+        for (int k = 0; k < K; ++k) zmax = fmaxf(zmax, a.z[int64_t(k) * a.ldz + i]);
+        for (int k = 0; k < K; ++k) total += expf(a.z[int64_t(k) * a.ldz + i] - zmax);
+    }
+    float best_h = 0.f, best_y = 0.f; int arg_h = 0, arg_y = 0;
+    for (int k = 0; k < K; ++k) {
+        const float zv = a.z[int64_t(k) * a.ldz + i];
+        float h;
+        if (a.out_kind == B2NN_OUT_SOFTMAX) h = expf(zv - zmax) / total;
+        else if (a.out_kind == B2NN_OUT_SIGMOID) h = sigmoid_f(zv);
+        else h = zv;
+        if (a.h) a.h[int64_t(k) * a.ldh + i] = h;
+        if (h > best_h) { best_h = h; arg_h = k; }
+        if (a.y) {
+            const float yv = a.y[int64_t(k) * a.ldy + i];
+            if (yv > best_y) { best_y = yv; arg_y = k; }
+            const float d = h - yv;
+            if (a.delta) a.delta[int64_t(k) * a.ldd + i] = d;
+            if (want_cost) {
+                float c = 0.f;
+                if (a.cost_kind == B2NN_COST_SQUARED) c = d * d;
+                else {
+                    if (yv != 0.f) c += -yv * logf(h);
+                    if (a.cost_kind == B2NN_COST_NEGLNMAX && yv != 1.f) c += -(1.f - yv) * logf(1.f - h);
+                    c = fabsf(c);
+                }
+                cost += double(c);
+            }
         }
+    }
+    if (a.pred) a.pred[i] = float(arg_h);
+    if (want_err) {
+        if (a.y_labels) err = (float(arg_h) != a.y_labels[i]) ? 1.0 : 0.0;
+        else if (a.y)   err = (arg_h != arg_y) ? 1.0 : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(OUT_THREADS) output_layer_kernel(OutputArgs a, double* cost_sum, double* err_sum) {
+    pdl_enter();
+    __shared__ double sh[OUT_THREADS / 32];
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    double cost = 0.0, err = 0.0;
+    if (i < a.rows) {
+        if (a.K <= 16) output_row<16>(a, i, cost_sum != nullptr, err_sum != nullptr, cost, err);
+        else output_row_any(a, i, cost_sum != nullptr, err_sum != nullptr, cost, err);
     }
     if (cost_sum) { const double t = block_sum(cost, sh); if (threadIdx.x == 0 && t != 0.0) atomicAdd(cost_sum, t); }
     if (err_sum)  { const double t = block_sum(err, sh);  if (threadIdx.x == 0 && t != 0.0) atomicAdd(err_sum, t); }
