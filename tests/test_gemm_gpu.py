@@ -66,6 +66,17 @@ def test_ffma_gemm_matches_fp64(net, b2nn, kind, shape):
     assert torch.all(err <= 4e-6 * bound + 1e-6), (kind, shape, float(err.max()))
 
 
+@pytest.mark.parametrize("epi", [0, 2, 4])
+@pytest.mark.parametrize("shape", [(2000, 1300, 70), (1921, 1283, 45)])
+@pytest.mark.parametrize("kind", list(MAJORS))
+def test_ffma_gemm_throughput_kernel(net, b2nn, kind, shape, epi):
+    """Shapes with at least one 128 x 128 block per SM take the 8 x 8-per-thread FFMA kernel (ragged edges in M, N, K)."""
+    M, N, K = shape
+    got, ref, bound = _run(net, b2nn, 0, M, N, K, MAJORS[kind], epi=epi, seed=epi)
+    err = (got - ref).abs()
+    assert torch.all(err <= 4e-6 * bound + 2e-6), (kind, shape, epi, float(err.max()))
+
+
 @pytest.mark.parametrize("backend", [1, 3])
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("kind", list(MAJORS))
