@@ -48,6 +48,8 @@ ABI_SYMBOLS = [
     "b2nn_train_step_host", "b2nn_train_host", "b2nn_reset_velocity", "b2nn_evaluate", "b2nn_predict", "b2nn_predict_device",
     "b2nn_builtin_kind", "b2nn_comm_unique_id", "b2nn_comm_init", "b2nn_comm_barrier", "b2nn_comm_p2p_export", "b2nn_comm_p2p_open", "b2nn_gemm",
     "b2nn_momentum_update", "b2nn_stream", "b2nn_profile_enable", "b2nn_profile_read",
+    "b2nn_save_checkpoint", "b2nn_load_checkpoint", "b2nn_set_train_data_raw", "b2nn_set_normalisation",
+    "b2nn_get_normalisation", "b2nn_evaluate_raw", "b2nn_predict_raw",
 ]
 PROFILE_KINDS = ("forward", "backprop", "wgrad", "output", "update")
 
@@ -120,6 +122,21 @@ def lib():
     L.b2nn_profile_read.restype = C.c_int
     L.b2nn_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.POINTER(i64), C.POINTER(i64)]
+    L.b2nn_save_checkpoint.restype = C.c_int
+    L.b2nn_save_checkpoint.argtypes = [vp, C.c_char_p]
+    L.b2nn_load_checkpoint.restype = C.c_int
+    L.b2nn_load_checkpoint.argtypes = [vp, C.c_char_p]
+    L.b2nn_set_train_data_raw.restype = C.c_int
+    L.b2nn_set_train_data_raw.argtypes = [vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.b2nn_set_normalisation.restype = C.c_int
+    L.b2nn_set_normalisation.argtypes = [vp, vp, vp, C.c_int]
+    L.b2nn_get_normalisation.restype = C.c_int
+    L.b2nn_get_normalisation.argtypes = [vp, vp, vp, C.c_int]
+    L.b2nn_evaluate_raw.restype = C.c_int
+    L.b2nn_evaluate_raw.argtypes = [vp, C.POINTER(TrainDesc), vp, vp, i64, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double)]
+    L.b2nn_predict_raw.restype = C.c_int
+    L.b2nn_predict_raw.argtypes = [vp, C.POINTER(TrainDesc), vp, i64, C.c_int, vp, vp]
     _lib = L
     return L
 
@@ -216,6 +233,60 @@ class Net:
         y_cm = np.ascontiguousarray(y_cm, dtype=np.float32)
         _check(lib().b2nn_set_train_data(self._h, _host_ptr(x_cm), _host_ptr(y_cm), m, self.layers[0] + 1,
                                          self.layers[-1]), "b2nn_set_train_data")
+
+    def set_train_data_raw(self, x_raw_cm: np.ndarray, y_cm: np.ndarray, m: int, normalise: bool = True):
+        """x_raw_cm: column-major m x l0 WITHOUT the ones column; normalisation + bias happen on the device.
+        Returns (mean, stddev) when normalise."""
+        x_raw_cm = np.ascontiguousarray(x_raw_cm, dtype=np.float32)
+        y_cm = np.ascontiguousarray(y_cm, dtype=np.float32)
+        n = self.layers[0]
+        mean, sd = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+        _check(lib().b2nn_set_train_data_raw(self._h, _host_ptr(x_raw_cm), _host_ptr(y_cm), m, n, self.layers[-1],
+                                             int(normalise), _host_ptr(mean), _host_ptr(sd)), "b2nn_set_train_data_raw")
+        return (mean, sd) if normalise else None
+
+    def set_normalisation(self, mean, sd):
+        if mean is None:
+            _check(lib().b2nn_set_normalisation(self._h, None, None, 0), "b2nn_set_normalisation")
+            return
+        mean = np.ascontiguousarray(mean, dtype=np.float32)
+        sd = np.ascontiguousarray(sd, dtype=np.float32)
+        _check(lib().b2nn_set_normalisation(self._h, _host_ptr(mean), _host_ptr(sd), mean.size), "b2nn_set_normalisation")
+
+    def get_normalisation(self):
+        n = self.layers[0]
+        mean, sd = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+        _check(lib().b2nn_get_normalisation(self._h, _host_ptr(mean), _host_ptr(sd), n), "b2nn_get_normalisation")
+        return mean, sd
+
+    def save_checkpoint(self, path: str):
+        _check(lib().b2nn_save_checkpoint(self._h, os.fsencode(path)), "b2nn_save_checkpoint")
+
+    def load_checkpoint(self, path: str, layers=None):
+        _check(lib().b2nn_load_checkpoint(self._h, os.fsencode(path)), "b2nn_load_checkpoint")
+        if layers is not None:
+            self.layers = list(layers)
+
+    def evaluate_raw(self, desc: TrainDesc, x_raw_cm, y, rows: int, y_is_labels=False, normalise=True):
+        x_raw_cm = np.ascontiguousarray(x_raw_cm, dtype=np.float32)
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        cost, errs = C.c_double(), C.c_double()
+        _check(lib().b2nn_evaluate_raw(self._h, C.byref(desc), _host_ptr(x_raw_cm), _host_ptr(y), rows, int(y_is_labels),
+                                       int(normalise), C.byref(cost), C.byref(errs)), "b2nn_evaluate_raw")
+        return cost.value, errs.value
+
+    def predict_raw(self, desc: TrainDesc, x_raw_cm, rows: int, normalise=True):
+        x_raw_cm = np.ascontiguousarray(x_raw_cm, dtype=np.float32)
+        K = self.layers[-1]
+        out = np.empty(rows if desc.classify else rows * K, dtype=np.float32)
+        probs = np.empty(rows * K, dtype=np.float32)
+        _check(lib().b2nn_predict_raw(self._h, C.byref(desc), _host_ptr(x_raw_cm), rows, int(normalise), _host_ptr(out),
+                                      _host_ptr(probs)), "b2nn_predict_raw")
+        return out, probs
+
+    def predict_ptr(self, desc: TrainDesc, x_ptr, rows: int, out_ptr, probs_ptr=None):
+        """b2nn_predict on raw host pointers (e.g. pinned torch tensors): no numpy copies on either side."""
+        _check(lib().b2nn_predict(self._h, C.byref(desc), x_ptr, rows, out_ptr, probs_ptr), "b2nn_predict")
 
     def train(self, desc: TrainDesc) -> TrainOut:
         its, js = [], []

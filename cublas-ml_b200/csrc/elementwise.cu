@@ -268,6 +268,37 @@ __global__ void labels_to_onehot_kernel(const float* __restrict__ labels, float*
     for (int k = 0; k < K; ++k) y[int64_t(k) * ldy + i] = (k == c) ? 1.0f : 0.0f;
 }
 
+// normaliseData (cublasNN.cpp:214-268) on the device: per-feature mean, then the (m-1)-normalised standard deviation of
+// the deviations from that mean — the reference's two passes, accumulated in double instead of its sequential float sum.
+// One block per feature row of the engine-layout matrix (samples contiguous).
+__global__ void __launch_bounds__(256) feature_stats_kernel(const float* __restrict__ x, int64_t ld, int64_t rows,
+                                                            float* __restrict__ mean, float* __restrict__ stddev) {
+    __shared__ double sh[8];
+    __shared__ float mu_sh;
+    const float* row = x + int64_t(blockIdx.x) * ld;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) s += double(row[i]);
+    const double tot = block_sum(s, sh);
+    if (threadIdx.x == 0) mu_sh = float(tot / double(rows));
+    __syncthreads();
+    const float mu = mu_sh;
+    double q = 0.0;
+    for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) { const float d = row[i] - mu; q += double(d) * double(d); }
+    const double qt = block_sum(q, sh);
+    if (threadIdx.x == 0) { mean[blockIdx.x] = mu; stddev[blockIdx.x] = float(sqrt(qt / double(rows - 1))); }
+}
+
+// normalise (cublasNN.cpp:199-212): (x - mean) / stddev with IEEE division, 0 where the feature is constant.
+__global__ void normalise_rows_kernel(float* __restrict__ x, int64_t ld, int64_t rows, const float* __restrict__ mean,
+                                      const float* __restrict__ stddev) {
+    const int f = blockIdx.y;
+    const float mu = mean[f], sd = stddev[f];
+    float* row = x + int64_t(f) * ld;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < rows; i += stride)
+        row[i] = (sd != 0.f) ? __fdiv_rn(row[i] - mu, sd) : 0.f;
+}
+
 inline unsigned blocks_for(int64_t n, int threads) { return unsigned((n + threads - 1) / threads); }
 
 }  // namespace
@@ -366,6 +397,18 @@ cudaError_t multiply_launch(const float* a, const float* b, float* out, int64_t 
 }
 cudaError_t init_scale_launch(float* theta, int in, int out, int64_t count, int kind, cudaStream_t s) {
     init_scale_kernel<<<blocks_for(count, 256), 256, 0, s>>>(theta, in, out, count, kind);
+    return cudaGetLastError();
+}
+cudaError_t feature_stats_launch(const float* x, int64_t ld, int64_t rows, int n, float* mean, float* stddev, cudaStream_t s) {
+    if (n <= 0 || rows <= 0) return cudaSuccess;
+    feature_stats_kernel<<<unsigned(n), 256, 0, s>>>(x, ld, rows, mean, stddev);
+    return cudaGetLastError();
+}
+cudaError_t normalise_rows_launch(float* x, int64_t ld, int64_t rows, int n, const float* mean, const float* stddev, cudaStream_t s) {
+    if (n <= 0 || rows <= 0) return cudaSuccess;
+    const int64_t want = (rows + 255) / 256;
+    dim3 grid(unsigned(want < 64 ? want : 64), unsigned(n));
+    normalise_rows_kernel<<<grid, 256, 0, s>>>(x, ld, rows, mean, stddev);
     return cudaGetLastError();
 }
 cudaError_t labels_to_onehot_launch(const float* labels, float* y, int64_t ldy, int64_t rows, int K, cudaStream_t s) {

@@ -25,6 +25,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace b2 {
@@ -158,10 +159,21 @@ struct b2nn_ctx {
     double* d_jsteps = nullptr; double* h_jsteps = nullptr; int64_t jsteps_cap = 0;
 
     // staging of b2nn_predict (kept between calls: small-batch inference is otherwise dominated by cudaMalloc/cudaFree)
-    float* pr_x = nullptr; float* pr_p = nullptr; float* pr_h = nullptr; int64_t pr_ld = 0; int pr_n = 0, pr_k = 0;
+    // Two of everything: chunk c+1 is packed into pinned memory and travels H2D while chunk c computes and chunk c-1's
+    // results travel back (b2nn_predict).
+    float* pr_x[2] = {nullptr, nullptr}; float* pr_p[2] = {nullptr, nullptr}; float* pr_h[2] = {nullptr, nullptr};
+    int64_t pr_ld = 0; int pr_n = 0, pr_k = 0;
+    float* pr_hx[2] = {nullptr, nullptr};      // pinned host staging of one input chunk (n rows of pr_ld floats)
+    float* pr_hout[2] = {nullptr, nullptr};    // pinned host staging of one chunk's results (pred: pr_ld, probs: K * pr_ld)
+    cudaEvent_t pr_copied[2] = {nullptr, nullptr}, pr_computed[2] = {nullptr, nullptr}, pr_out[2] = {nullptr, nullptr};
+    cudaStream_t pr_d2h_stream = nullptr;
 
     // host-step staging (b2nn_train_step_host)
     float* Xs = nullptr; float* Ys = nullptr; int64_t lds = 0, caps = 0;
+
+    // device-side normaliseData (cublasNN.cpp:191-268): per-feature mean / stddev of the training set, applied to raw rows
+    // while they are staged (b2nn_set_train_data_raw, b2nn_evaluate_raw, b2nn_predict_raw)
+    float* d_mean = nullptr; float* d_std = nullptr; int norm_n = 0;
 
     Workspace ws;
     std::map<std::pair<int64_t, const float*>, StepPlan> plans;   // keyed by (rows, X base); valid for the (ws, ldx, precision, ...) below
@@ -229,8 +241,10 @@ int resolve_precision(int prec) {
     if (prec == B2NN_PREC_FP32 || prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3) return prec;
     const char* e = std::getenv("B2NN_PRECISION");
     if (e && (std::strcmp(e, "fp32") == 0 || std::strcmp(e, "FP32") == 0)) return B2NN_PREC_FP32;
-    if (e && (std::strcmp(e, "tf32x3") == 0 || std::strcmp(e, "TF32X3") == 0)) return B2NN_PREC_TF32X3;
-    return B2NN_PREC_TF32;
+    if (e && (std::strcmp(e, "tf32") == 0 || std::strcmp(e, "TF32") == 0)) return B2NN_PREC_TF32;
+    // Default = fp32-grade (3xTF32 on the tensor cores): a drop-in for the reference's default-math cublasSgemm
+    // (cublasNN.cpp:25 never changes the math mode) must not silently narrow the arithmetic; plain tf32 is an opt-in.
+    return B2NN_PREC_TF32X3;
 }
 
 // Low-part companion buffer of an input matrix (allocated on demand, content refreshed by the caller with split_lo).
@@ -265,6 +279,22 @@ int ensure_w_lo(b2nn_ctx* c) {
     }
     return B2NN_OK;
 }
+
+// Scope guards: every error exit of the entry points below releases what it created.
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+struct GraphExecs {
+    cudaGraphExec_t g[2] = {nullptr, nullptr};
+    void destroy() { for (auto& e : g) if (e) { cudaGraphExecDestroy(e); e = nullptr; } }
+    ~GraphExecs() { destroy(); }
+};
 
 int epi_forward(int act_kind) { return act_kind == B2NN_ACT_SIGMOID ? EPI_SIGMOID : act_kind == B2NN_ACT_TANH ? EPI_TANH : EPI_STORE; }
 int epi_backward(int act_kind) { return act_kind == B2NN_ACT_SIGMOID ? EPI_DSIGMOID : act_kind == B2NN_ACT_TANH ? EPI_DTANH : EPI_STORE; }
@@ -597,7 +627,23 @@ int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_d
             if (!c->ws.delta_lo.empty() && c->ws.delta_lo[j - 1])      // fp32-grade mode: the next contraction wants the low part too
                 B2_CUDA(split_lo_launch(c->ws.delta[j - 1], c->ws.delta_lo[j - 1], int64_t(li.in) * c->ws.ld, c->stream));
         }
-        if (!skinny && bwd_first && j > 0 && !tail_layer) { rc = run_gemm(c, sp.bwd[j], 0, 1); if (rc) return rc; }
+        // user activation: sigGrad = f'(z_{j-1}) by the user's function, then delta = product .* sigGrad (cublasNN.cpp:673, 676);
+        // runs after the delta-backprop contraction wherever that sits in the order
+        auto custom_derivative = [&]() -> int {
+            if (!custom) return B2NN_OK;
+            const int64_t cnt = int64_t(c->layers[j]) * c->ws.ld;
+            if (cnt > INT32_MAX) { set_error("custom activation: element count exceeds int"); return B2NN_ERR_ARG; }
+            float* tmp = c->ws.delta[j - 1];
+            d->act_grad_fn(c->ws.z[j - 1], tmp, int(cnt));
+            B2_CUDA(multiply_launch(c->ws.scratch, tmp, tmp, cnt, c->stream));
+            ++c->launches;
+            return B2NN_OK;
+        };
+        if (!skinny && bwd_first && j > 0 && !tail_layer) {
+            rc = run_gemm(c, sp.bwd[j], 0, 1);
+            if (!rc) rc = custom_derivative();
+            if (rc) return rc;
+        }
         if (!skinny && !(tail_layer && sp.tail_inline_g)) rc = run_gemm(c, sp.wgrad[j], x_start, 2);
         if (rc) return rc;
         if (sp.fused[j]) {
@@ -612,16 +658,8 @@ int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_d
         } else if (c->comm && !c->grad_ready.empty()) B2_CUDA(cudaEventRecord(c->grad_ready[j], c->stream));
         if (!skinny && !bwd_first && j > 0 && !tail_layer) {
             rc = run_gemm(c, sp.bwd[j], 0, 1);
+            if (!rc) rc = custom_derivative();
             if (rc) return rc;
-            if (custom) {
-                const int64_t cnt = int64_t(c->layers[j]) * c->ws.ld;
-                if (cnt > INT32_MAX) { set_error("custom activation: element count exceeds int"); return B2NN_ERR_ARG; }
-                // sigGrad = f'(z_{j-1}) by the user's function, then delta = product .* sigGrad (cublasNN.cpp:673, 676)
-                float* tmp = c->ws.delta[j - 1];
-                d->act_grad_fn(c->ws.z[j - 1], tmp, int(cnt));
-                B2_CUDA(multiply_launch(c->ws.scratch, tmp, tmp, cnt, c->stream));
-                ++c->launches;
-            }
         }
     }
     return B2NN_OK;
@@ -871,7 +909,7 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
 // calcFinalCost / validate (cublasNN.cpp:687-881) over device-resident rows, chunked through the workspace.
 int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, int64_t ldx, const float* Y, int64_t ldy,
                     const float* labels, int64_t rows, float* pred_out, float* probs_out, int64_t ldp, double* cost,
-                    double* errors) {
+                    double* errors, int64_t x_extent = 0) {
     const int nl = int(c->layers.size());
     const int K = c->layers[nl - 1];
     int rc = ensure_acc(c, 2);
@@ -896,7 +934,9 @@ int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float
     const int cost_kind = d->classify ? d->cost_kind : B2NN_COST_SQUARED;
     for (int64_t s = 0; s < rows; s += chunk) {
         const int64_t r = std::min<int64_t>(chunk, rows - s);
-        StepPlan& sp = get_plan(c, r, X, ldx, rows, true, prec, d->act_kind, custom_outcost(d));
+        // x_extent: sample columns of X the tensor maps may span (staging buffers: the whole padded buffer, so plans stay
+        // valid from call to call; rows past `r` only feed accumulator rows that are never stored)
+        StepPlan& sp = get_plan(c, r, X, ldx, x_extent > 0 ? x_extent : rows, true, prec, d->act_kind, custom_outcost(d));
         rc = forward_pass(c, sp, s, d);
         if (rc) return rc;
         if (custom_outcost(d)) {
@@ -937,20 +977,77 @@ int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float
 
 // Stage a reference-layout host matrix (rows x (n+1) col-major, ones column FIRST, ld = ld_host) into engine layout.
 int stage_x_from_host(b2nn_ctx* c, const float* x_host, int64_t ld_host, int64_t row0, int64_t rows, int n, float* x_dev,
-                      int64_t ld_dev, bool fill_ones) {
-    // feature f of the engine matrix is column f+1 of the reference matrix: one strided 2-D copy, no temp buffer
-    B2_CUDA(cudaMemcpy2DAsync(x_dev, sizeof(float) * ld_dev, x_host + ld_host + row0, sizeof(float) * ld_host,
+                      int64_t ld_dev, bool fill_ones, bool raw = false) {
+    // feature f of the engine matrix is column f+1 of the reference matrix (column f of a RAW matrix, which has no ones
+    // column yet): one strided 2-D copy, no temp buffer
+    B2_CUDA(cudaMemcpy2DAsync(x_dev, sizeof(float) * ld_dev, x_host + (raw ? 0 : ld_host) + row0, sizeof(float) * ld_host,
                               sizeof(float) * rows, size_t(n), cudaMemcpyHostToDevice, c->stream));
     if (fill_ones) B2_CUDA(fill_launch(x_dev + int64_t(n) * ld_dev, 1.0f, ld_dev, c->stream));
     return B2NN_OK;
 }
 
-int validate_desc(const b2nn_ctx* c, const b2nn_train_desc* d) {
+// `training`: the entry point back-propagates, so a custom hidden activation needs its derivative too; forward-only entry
+// points (evaluate / predict, which the reference calls with activationHidden alone: cublasNN.h:51-69) need act_fn only.
+int validate_desc(const b2nn_ctx* c, const b2nn_train_desc* d, bool training) {
     if (!c || !d) { set_error("null context or descriptor"); return B2NN_ERR_ARG; }
     if (c->layers.size() < 3) { set_error("set_layers must be called first with >= 3 layers (cublasNN.cpp:657 needs a hidden layer)"); return B2NN_ERR_ARG; }
     if (d->act_kind < 0 || d->act_kind > B2NN_ACT_CUSTOM) { set_error("bad act_kind"); return B2NN_ERR_ARG; }
-    if (d->act_kind == B2NN_ACT_CUSTOM && (!d->act_fn || !d->act_grad_fn)) { set_error("custom activation needs act_fn and act_grad_fn"); return B2NN_ERR_ARG; }
+    if (d->act_kind == B2NN_ACT_CUSTOM && !d->act_fn) { set_error("custom activation needs act_fn"); return B2NN_ERR_ARG; }
+    if (d->act_kind == B2NN_ACT_CUSTOM && training && !d->act_grad_fn) { set_error("custom activation needs act_fn and act_grad_fn"); return B2NN_ERR_ARG; }
     if (d->classify && (d->out_kind < 0 || d->out_kind > B2NN_OUT_CUSTOM)) { set_error("bad out_kind"); return B2NN_ERR_ARG; }
+    return B2NN_OK;
+}
+
+// Host-streaming staging buffers (b2nn_train_step_host, b2nn_train_host, b2nn_predict) are sized for one (n, K); drop
+// them whenever the layer widths may have changed.
+void release_staging(b2nn_ctx* c) {
+    drop_lo(c, c->Xs);
+    cudaFree(c->Xs); cudaFree(c->Ys); c->Xs = c->Ys = nullptr; c->caps = 0; c->lds = 0;
+    for (int i = 0; i < 2; ++i) {
+        drop_lo(c, c->Xst[i]);
+        cudaFree(c->Xst[i]); cudaFree(c->Yst[i]); c->Xst[i] = c->Yst[i] = nullptr;
+    }
+    c->capst = 0; c->ldst = 0;
+    for (int i = 0; i < 2; ++i) {
+        drop_lo(c, c->pr_x[i]);
+        cudaFree(c->pr_x[i]); cudaFree(c->pr_p[i]); cudaFree(c->pr_h[i]);
+        c->pr_x[i] = c->pr_p[i] = c->pr_h[i] = nullptr;
+        if (c->pr_hx[i]) cudaFreeHost(c->pr_hx[i]);
+        if (c->pr_hout[i]) cudaFreeHost(c->pr_hout[i]);
+        c->pr_hx[i] = c->pr_hout[i] = nullptr;
+    }
+    c->pr_ld = 0; c->pr_n = c->pr_k = 0;
+}
+
+int comm_barrier_impl(b2nn_ctx* c);
+
+// Undo b2nn_comm_p2p_export / _open.  Collective when a communicator exists: the barrier separates "every rank has
+// closed its imports" from "the exporter frees the memory" (freeing exported memory under a live import is undefined).
+int p2p_teardown(b2nn_ctx* c) {
+    if (!c->p2p && !c->p2p_flags && c->p2p_opened.empty()) return B2NN_OK;
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->upd_stream) cudaStreamSynchronize(c->upd_stream);
+    for (void* p : c->p2p_opened) cudaIpcCloseMemHandle(p);
+    c->p2p_opened.clear();
+    c->p2p = false;
+    c->peers = P2pPeers{};
+    if (c->comm) { int rc = comm_barrier_impl(c); if (rc) return rc; }
+    cudaFree(c->p2p_flags); c->p2p_flags = nullptr;
+    c->p2p_step = 0;
+    c->p2p_small_off.clear(); c->p2p_small_cnt.clear(); c->p2p_small_floats = 0;
+    c->plans.clear();
+    return B2NN_OK;
+}
+
+int comm_barrier_impl(b2nn_ctx* c) {
+    B2_CUDA(cudaSetDevice(c->device));
+    if (c->comm) {
+        int rc = ensure_acc(c, 3);
+        if (rc) return rc;
+        int r = g_nccl.AllReduce(c->d_acc, c->d_acc, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+        if (r != 0) { set_error("ncclAllReduce(barrier) failed"); return B2NN_ERR_CUDA; }
+    }
+    B2_CUDA(cudaStreamSynchronize(c->stream));
     return B2NN_OK;
 }
 
@@ -1002,7 +1099,16 @@ void b2nn_destroy(b2nn_ctx* c) {
     for (auto& kv : c->lo_cache) cudaFree(kv.second.first);
     cudaFree(c->X); cudaFree(c->Y); cudaFree(c->Xs); cudaFree(c->Ys); cudaFree(c->Xsp); cudaFree(c->Ysp);
     cudaFree(c->d_acc);
-    cudaFree(c->pr_x); cudaFree(c->pr_p); cudaFree(c->pr_h);
+    cudaFree(c->d_mean); cudaFree(c->d_std);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->pr_x[i]); cudaFree(c->pr_p[i]); cudaFree(c->pr_h[i]);
+        if (c->pr_hx[i]) cudaFreeHost(c->pr_hx[i]);
+        if (c->pr_hout[i]) cudaFreeHost(c->pr_hout[i]);
+        if (c->pr_copied[i]) cudaEventDestroy(c->pr_copied[i]);
+        if (c->pr_computed[i]) cudaEventDestroy(c->pr_computed[i]);
+        if (c->pr_out[i]) cudaEventDestroy(c->pr_out[i]);
+    }
+    if (c->pr_d2h_stream) cudaStreamDestroy(c->pr_d2h_stream);
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->Xst[i]); cudaFree(c->Yst[i]);
         if (c->st_copied[i]) cudaEventDestroy(c->st_copied[i]);
@@ -1044,6 +1150,10 @@ int b2nn_set_layers(b2nn_ctx* c, const int* layers, int n_layers, int init_kind,
         c->total_ref += li.ref_size;
         c->total_int += li.ldw * li.out;      // multiple of 4 floats: every layer block starts 16-byte aligned
     }
+    // Peer-memory exchange: peers hold IPC mappings of the arenas about to be freed.  Collective teardown (every rank
+    // calls set_layers): close what this rank imported, meet at a barrier, only then free what it exported.
+    if (int rc = p2p_teardown(c)) return rc;
+    release_staging(c);       // sized for the old input / output widths (their ones row sits at the old index n)
     cudaFree(c->W); cudaFree(c->V); cudaFree(c->G); cudaFree(c->W_lo);
     c->W = c->V = c->G = c->W_lo = nullptr; c->w_lo_valid = false;
     c->plans.clear(); c->ws.release();
@@ -1090,35 +1200,158 @@ int b2nn_set_layers(b2nn_ctx* c, const int* layers, int n_layers, int init_kind,
 
 int64_t b2nn_num_weights(const b2nn_ctx* c) { return c ? c->total_ref : 0; }
 
+// One arena (weights or velocity) between the engine layout and the reference arena layout on the host.
+static int arena_to_host(b2nn_ctx* c, const float* arena, float* host) {
+    DevBuf ref;
+    B2_CUDA(cudaMalloc(&ref.p, sizeof(float) * c->total_ref));
+    for (const LayerInfo& li : c->L)
+        B2_CUDA(theta_internal_to_ref_launch(arena + li.w_off, ref.as<float>() + li.ref_off, li.in, li.out, li.ldw, c->stream));
+    B2_CUDA(cudaMemcpyAsync(host, ref.p, sizeof(float) * c->total_ref, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2NN_OK;
+}
+static int arena_from_host(b2nn_ctx* c, float* arena, const float* host) {
+    DevBuf ref;
+    B2_CUDA(cudaMalloc(&ref.p, sizeof(float) * c->total_ref));
+    B2_CUDA(cudaMemcpyAsync(ref.p, host, sizeof(float) * c->total_ref, cudaMemcpyHostToDevice, c->stream));
+    for (const LayerInfo& li : c->L)
+        B2_CUDA(theta_ref_to_internal_launch(ref.as<float>() + li.ref_off, arena + li.w_off, li.in, li.out, li.ldw, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2NN_OK;
+}
+
 int b2nn_get_weights(b2nn_ctx* c, float* host, int64_t count) {
     if (!c || !host || count != c->total_ref || !c->W) { set_error("get_weights: bad arguments"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
-    float* ref = nullptr;
-    B2_CUDA(cudaMalloc(&ref, sizeof(float) * c->total_ref));
-    for (const LayerInfo& li : c->L)
-        B2_CUDA(theta_internal_to_ref_launch(c->W + li.w_off, ref + li.ref_off, li.in, li.out, li.ldw, c->stream));
-    B2_CUDA(cudaMemcpyAsync(host, ref, sizeof(float) * c->total_ref, cudaMemcpyDeviceToHost, c->stream));
-    B2_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(ref);
-    return B2NN_OK;
+    return arena_to_host(c, c->W, host);
 }
 
 int b2nn_set_weights(b2nn_ctx* c, const float* host, int64_t count) {
     if (!c || !host || count != c->total_ref || !c->W) { set_error("set_weights: bad arguments"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
-    float* ref = nullptr;
-    B2_CUDA(cudaMalloc(&ref, sizeof(float) * c->total_ref));
-    B2_CUDA(cudaMemcpyAsync(ref, host, sizeof(float) * c->total_ref, cudaMemcpyHostToDevice, c->stream));
-    for (const LayerInfo& li : c->L)
-        B2_CUDA(theta_ref_to_internal_launch(ref + li.ref_off, c->W + li.w_off, li.in, li.out, li.ldw, c->stream));
     c->w_lo_valid = false;
-    B2_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(ref);
+    return arena_from_host(c, c->W, host);
+}
+
+// ---- checkpoint (not in the reference: its weights die with the process) ---------------------------------------------
+// File: "B2NNCKP1" | int32 n_layers | int32 layers[] | int32 has_velocity | int32 norm_n | int64 n_weights |
+//       float theta[] (reference arena layout) | float velocity[] | float mean[norm_n] | float stddev[norm_n] |
+//       uint64 FNV-1a of everything before it.  Little-endian, no padding.
+static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+int b2nn_save_checkpoint(b2nn_ctx* c, const char* path) {
+    if (!c || !path || !c->W) { set_error("save_checkpoint: no network"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    std::vector<float> th(static_cast<size_t>(c->total_ref)), vel(static_cast<size_t>(c->total_ref)), mean(static_cast<size_t>(c->norm_n)),
+        sd(static_cast<size_t>(c->norm_n));
+    int rc = arena_to_host(c, c->W, th.data());
+    if (!rc) rc = arena_to_host(c, c->V, vel.data());
+    if (rc) return rc;
+    if (c->norm_n > 0) {
+        B2_CUDA(cudaMemcpy(mean.data(), c->d_mean, sizeof(float) * c->norm_n, cudaMemcpyDeviceToHost));
+        B2_CUDA(cudaMemcpy(sd.data(), c->d_std, sizeof(float) * c->norm_n, cudaMemcpyDeviceToHost));
+    }
+    FILE* f = std::fopen(path, "wb");
+    if (!f) { set_error(std::string("save_checkpoint: cannot open ") + path); return B2NN_ERR_ARG; }
+    uint64_t h = 1469598103934665603ull;
+    bool ok = true;
+    auto put = [&](const void* p, size_t n) { if (n && std::fwrite(p, 1, n, f) != n) ok = false; h = fnv1a(h, p, n); };
+    const int32_t nl = int32_t(c->layers.size()), has_v = 1, nn = int32_t(c->norm_n);
+    const int64_t nw = c->total_ref;
+    put("B2NNCKP1", 8); put(&nl, 4);
+    for (int v : c->layers) { const int32_t w = v; put(&w, 4); }
+    put(&has_v, 4); put(&nn, 4); put(&nw, 8);
+    put(th.data(), sizeof(float) * th.size()); put(vel.data(), sizeof(float) * vel.size());
+    put(mean.data(), sizeof(float) * mean.size()); put(sd.data(), sizeof(float) * sd.size());
+    const uint64_t sum = h;
+    if (std::fwrite(&sum, 1, 8, f) != 8) ok = false;
+    if (std::fclose(f) != 0) ok = false;
+    if (!ok) { set_error(std::string("save_checkpoint: write failed: ") + path); return B2NN_ERR_ARG; }
     return B2NN_OK;
 }
 
+int b2nn_load_checkpoint(b2nn_ctx* c, const char* path) {
+    if (!c || !path) { set_error("load_checkpoint: null argument"); return B2NN_ERR_ARG; }
+    FILE* f = std::fopen(path, "rb");
+    if (!f) { set_error(std::string("load_checkpoint: cannot open ") + path); return B2NN_ERR_ARG; }
+    struct Closer { FILE* f; ~Closer() { std::fclose(f); } } closer{f};
+    uint64_t h = 1469598103934665603ull;
+    bool ok = true;
+    auto get = [&](void* p, size_t n) { if (n && std::fread(p, 1, n, f) != n) ok = false; else h = fnv1a(h, p, n); };
+    char magic[8]; int32_t nl = 0, has_v = 0, nn = 0; int64_t nw = 0;
+    get(magic, 8); get(&nl, 4);
+    if (!ok || std::memcmp(magic, "B2NNCKP1", 8) != 0 || nl < 3 || nl > 4096) { set_error("load_checkpoint: not a b2nn checkpoint"); return B2NN_ERR_ARG; }
+    std::vector<int> layers(size_t(nl), 0);
+    for (int i = 0; i < nl; ++i) { int32_t w = 0; get(&w, 4); layers[size_t(i)] = w; }
+    get(&has_v, 4); get(&nn, 4); get(&nw, 8);
+    int64_t expect = 0;
+    for (int i = 0; ok && i + 1 < nl; ++i) {
+        if (layers[size_t(i)] < 1 || layers[size_t(i + 1)] < 1) ok = false;
+        expect += (int64_t(layers[size_t(i)]) + 1) * layers[size_t(i + 1)];
+    }
+    if (!ok || nw != expect || nn < 0 || (nn != 0 && nn != layers[0])) { set_error("load_checkpoint: inconsistent header"); return B2NN_ERR_ARG; }
+    std::vector<float> th(static_cast<size_t>(nw)), vel(has_v ? static_cast<size_t>(nw) : 0), mean(static_cast<size_t>(nn)), sd(static_cast<size_t>(nn));
+    get(th.data(), sizeof(float) * th.size()); get(vel.data(), sizeof(float) * vel.size());
+    get(mean.data(), sizeof(float) * mean.size()); get(sd.data(), sizeof(float) * sd.size());
+    const uint64_t sum = h;
+    uint64_t stored = 0;
+    if (!ok || std::fread(&stored, 1, 8, f) != 8 || stored != sum) { set_error("load_checkpoint: truncated file or checksum mismatch"); return B2NN_ERR_ARG; }
+    const bool same = c->W && c->layers == layers;
+    if (!same) {        // (re)build the arenas for the stored architecture; the random draw is overwritten below
+        int rc = b2nn_set_layers(c, layers.data(), nl, B2NN_INIT_1, nullptr, 0, 0);
+        if (rc) return rc;
+    }
+    B2_CUDA(cudaSetDevice(c->device));
+    c->w_lo_valid = false;
+    int rc = arena_from_host(c, c->W, th.data());
+    if (!rc && has_v) rc = arena_from_host(c, c->V, vel.data());
+    if (!rc) rc = b2nn_set_normalisation(c, mean.data(), sd.data(), nn);
+    return rc;
+}
+
+static int set_train_data_impl(b2nn_ctx* c, const float* x, const float* y, int64_t m, int n_plus_1, int k, bool raw, bool normalise,
+                               float* mean_out, float* std_out);
+
 int b2nn_set_train_data(b2nn_ctx* c, const float* x, const float* y, int64_t m, int n_plus_1, int k) {
+    return set_train_data_impl(c, x, y, m, n_plus_1, k, false, false, nullptr, nullptr);
+}
+
+int b2nn_set_train_data_raw(b2nn_ctx* c, const float* x_raw, const float* y, int64_t m, int n, int k, int normalise, float* mean_out,
+                            float* std_out) {
+    return set_train_data_impl(c, x_raw, y, m, n + 1, k, true, normalise != 0, mean_out, std_out);
+}
+
+int b2nn_set_normalisation(b2nn_ctx* c, const float* mean, const float* stddev, int n) {
+    if (!c || n < 0 || (n > 0 && (!mean || !stddev))) { set_error("set_normalisation: bad arguments"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_mean); cudaFree(c->d_std); c->d_mean = c->d_std = nullptr; c->norm_n = 0;
+    if (n == 0) return B2NN_OK;
+    B2_CUDA(cudaMalloc(&c->d_mean, sizeof(float) * n));
+    B2_CUDA(cudaMalloc(&c->d_std, sizeof(float) * n));
+    B2_CUDA(cudaMemcpy(c->d_mean, mean, sizeof(float) * n, cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(c->d_std, stddev, sizeof(float) * n, cudaMemcpyHostToDevice));
+    c->norm_n = n;
+    return B2NN_OK;
+}
+
+int b2nn_get_normalisation(b2nn_ctx* c, float* mean, float* stddev, int n) {
+    if (!c || !mean || !stddev || n != c->norm_n || n == 0) { set_error("get_normalisation: no statistics of that width"); return B2NN_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    B2_CUDA(cudaMemcpy(mean, c->d_mean, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    B2_CUDA(cudaMemcpy(stddev, c->d_std, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return B2NN_OK;
+}
+
+static int set_train_data_impl(b2nn_ctx* c, const float* x, const float* y, int64_t m, int n_plus_1, int k, bool raw, bool normalise,
+                               float* mean_out, float* std_out) {
     if (!c || !x || !y || m < 1) { set_error("set_train_data: bad arguments"); return B2NN_ERR_ARG; }
+    if (normalise && m < 2) { set_error("set_train_data_raw: normalisation needs at least 2 rows"); return B2NN_ERR_ARG; }
     if (c->layers.empty()) { set_error("set_layers must precede set_train_data (main.cpp:125)"); return B2NN_ERR_ARG; }
     if (n_plus_1 != c->layers[0] + 1 || k != c->layers.back()) { set_error("data shape does not match the layers"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
@@ -1136,8 +1369,21 @@ int b2nn_set_train_data(b2nn_ctx* c, const float* x, const float* y, int64_t m, 
     }
     B2_CUDA(cudaMemsetAsync(c->X, 0, sizeof(float) * c->ldx * n_plus_1, c->stream));
     B2_CUDA(cudaMemsetAsync(c->Y, 0, sizeof(float) * c->ldy * k, c->stream));
-    int rc = stage_x_from_host(c, x, m, 0, m, c->n, c->X, c->ldx, true);
+    int rc = stage_x_from_host(c, x, m, 0, m, c->n, c->X, c->ldx, true, raw);
     if (rc) return rc;
+    if (normalise) {
+        // normaliseData on the device (cublasNN.cpp:214-268): statistics of the training set, kept for validate / predict
+        if (c->norm_n != c->n) {
+            cudaFree(c->d_mean); cudaFree(c->d_std); c->d_mean = c->d_std = nullptr; c->norm_n = 0;
+            B2_CUDA(cudaMalloc(&c->d_mean, sizeof(float) * c->n));
+            B2_CUDA(cudaMalloc(&c->d_std, sizeof(float) * c->n));
+            c->norm_n = c->n;
+        }
+        B2_CUDA(feature_stats_launch(c->X, c->ldx, m, c->n, c->d_mean, c->d_std, c->stream));
+        B2_CUDA(normalise_rows_launch(c->X, c->ldx, m, c->n, c->d_mean, c->d_std, c->stream));
+        if (mean_out) B2_CUDA(cudaMemcpyAsync(mean_out, c->d_mean, sizeof(float) * c->n, cudaMemcpyDeviceToHost, c->stream));
+        if (std_out) B2_CUDA(cudaMemcpyAsync(std_out, c->d_std, sizeof(float) * c->n, cudaMemcpyDeviceToHost, c->stream));
+    }
     B2_CUDA(cudaMemcpy2DAsync(c->Y, sizeof(float) * c->ldy, y, sizeof(float) * m, sizeof(float) * m, size_t(k),
                               cudaMemcpyHostToDevice, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
@@ -1153,7 +1399,7 @@ int b2nn_reset_velocity(b2nn_ctx* c) {
 
 int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log_user, b2nn_train_result* result) {
     auto t_call0 = std::chrono::steady_clock::now();                    // cublasNN.cpp:529, 586
-    int rc = validate_desc(c, d);
+    int rc = validate_desc(c, d, true);
     if (rc) return rc;
     if (!c->X || !c->Y) { set_error("set_train_data must precede train (copyDataGPU, main.cpp:87)"); return B2NN_ERR_ARG; }
     if (d->batch_num < 1 || int64_t(d->batch_num) > c->m) { set_error("batch_num must be in [1, m]"); return B2NN_ERR_ARG; }
@@ -1177,14 +1423,13 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
     std::vector<int64_t> global_rows(nb);
     for (int b = 0; b < nb; ++b) global_rows[b] = (b == nb - 1) ? last_rows : bs;
     if (c->comm) {
-        int64_t* tmp = nullptr;
-        B2_CUDA(cudaMalloc(&tmp, sizeof(int64_t) * nb));
-        B2_CUDA(cudaMemcpyAsync(tmp, global_rows.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice, c->stream));
-        int r = g_nccl.AllReduce(tmp, tmp, size_t(nb), NCCL_INT64, NCCL_SUM, c->comm, c->stream);
-        if (r != 0) { cudaFree(tmp); set_error("ncclAllReduce(batch rows) failed"); return B2NN_ERR_CUDA; }
-        B2_CUDA(cudaMemcpyAsync(global_rows.data(), tmp, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, c->stream));
+        DevBuf tmp;
+        B2_CUDA(cudaMalloc(&tmp.p, sizeof(int64_t) * nb));
+        B2_CUDA(cudaMemcpyAsync(tmp.p, global_rows.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice, c->stream));
+        int r = g_nccl.AllReduce(tmp.p, tmp.p, size_t(nb), NCCL_INT64, NCCL_SUM, c->comm, c->stream);
+        if (r != 0) { set_error("ncclAllReduce(batch rows) failed"); return B2NN_ERR_CUDA; }
+        B2_CUDA(cudaMemcpyAsync(global_rows.data(), tmp.p, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, c->stream));
         B2_CUDA(cudaStreamSynchronize(c->stream));
-        cudaFree(tmp);
     }
 
     if (c->comm) {
@@ -1221,8 +1466,9 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
     }
 
     const int64_t launches0 = c->launches, tc0 = c->tc_launches;
-    cudaEvent_t ev0, ev1;
-    B2_CUDA(cudaEventCreate(&ev0)); B2_CUDA(cudaEventCreate(&ev1));
+    EventPair evs;
+    B2_CUDA(cudaEventCreate(&evs.a)); B2_CUDA(cudaEventCreate(&evs.b));
+    cudaEvent_t const ev0 = evs.a, ev1 = evs.b;
     B2_CUDA(cudaEventRecord(ev0, c->stream));
 
     int issued = 0, reported = 0;
@@ -1249,9 +1495,10 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
     bool use_graph = !c->comm && d->act_kind != B2NN_ACT_CUSTOM && !custom_outcost(d) && !c->profile && nb <= 128 && d->iters > 2 &&
                      step_work < 2e10;
     if (const char* e = std::getenv("B2NN_GRAPH")) use_graph = use_graph && std::atoi(e) != 0;
-    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};     // [0] no cost, [1] batch 0 reports its cost
+    GraphExecs graphs;                                      // [0] no cost, [1] batch 0 reports its cost
+    cudaGraphExec_t (&graph_exec)[2] = graphs.g;
     int64_t graph_launches[2] = {0, 0}, graph_tc[2] = {0, 0};
-    auto destroy_graphs = [&]() { for (auto& g : graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; } };
+    auto destroy_graphs = [&]() { graphs.destroy(); };
     double* const graph_slot = c->d_acc + 1;                // fixed accumulator the captured batch-0 step writes
     auto run_epoch = [&](double* slot0) -> int {
         for (int b = 0; b < nb; ++b) {
@@ -1279,7 +1526,6 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
                     if (graph) cudaGraphDestroy(graph);
                     destroy_graphs();
                     if (!rc) { set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); rc = B2NN_ERR_CUDA; }
-                    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
                     return rc;
                 }
                 ce = cudaGraphInstantiate(&graph_exec[v], graph, 0);
@@ -1294,7 +1540,7 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
         } else {
             slot = show ? c->d_acc + 2 + issued : nullptr;
             rc = run_epoch(slot);
-            if (rc) { destroy_graphs(); cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
+            if (rc) return rc;
         }
         if (show) {
             if (issued - reported >= int(c->log_events.size())) { rc = flush_logs(true); if (rc) return rc; }
@@ -1323,7 +1569,6 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
     if (rc) return rc;
     float ms = 0.f;
     B2_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     const int64_t loop_launches = c->launches - launches0, loop_tc = c->tc_launches - tc0;
 
     double final_cost = 0.0, errors = 0.0;
@@ -1334,14 +1579,13 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
         if (c->comm) {
             // data-parallel: rank-local sums -> global cost / error count
             double loc[3] = {d->classify ? final_cost * double(c->m) : final_cost * 2.0 * double(c->m), errors, double(c->m)};
-            double* t = nullptr;
-            B2_CUDA(cudaMalloc(&t, sizeof(double) * 3));
-            B2_CUDA(cudaMemcpyAsync(t, loc, sizeof(loc), cudaMemcpyHostToDevice, c->stream));
-            int r = g_nccl.AllReduce(t, t, 3, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
-            if (r != 0) { cudaFree(t); set_error("ncclAllReduce(final cost) failed"); return B2NN_ERR_CUDA; }
-            B2_CUDA(cudaMemcpyAsync(loc, t, sizeof(loc), cudaMemcpyDeviceToHost, c->stream));
+            DevBuf t;
+            B2_CUDA(cudaMalloc(&t.p, sizeof(double) * 3));
+            B2_CUDA(cudaMemcpyAsync(t.p, loc, sizeof(loc), cudaMemcpyHostToDevice, c->stream));
+            int r = g_nccl.AllReduce(t.p, t.p, 3, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+            if (r != 0) { set_error("ncclAllReduce(final cost) failed"); return B2NN_ERR_CUDA; }
+            B2_CUDA(cudaMemcpyAsync(loc, t.p, sizeof(loc), cudaMemcpyDeviceToHost, c->stream));
             B2_CUDA(cudaStreamSynchronize(c->stream));
-            cudaFree(t);
             final_cost = d->classify ? loc[0] / loc[2] : loc[0] / (2.0 * loc[2]);
             errors = loc[1];
         }
@@ -1361,7 +1605,7 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
 
 int b2nn_train_step_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const float* y, int64_t rows,
                          int64_t global_rows, float* J_out) {
-    int rc = validate_desc(c, d);
+    int rc = validate_desc(c, d, true);
     if (rc) return rc;
     if (!x || !y || rows < 1) { set_error("train_step_host: bad arguments"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
@@ -1412,7 +1656,7 @@ int b2nn_train_step_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, 
 int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const float* y, int64_t m, int n_plus_1, int k,
                     float* J_steps, b2nn_train_result* result) {
     auto t_call0 = std::chrono::steady_clock::now();
-    int rc = validate_desc(c, d);
+    int rc = validate_desc(c, d, true);
     if (rc) return rc;
     if (!x || !y || m < 1) { set_error("train_host: bad arguments"); return B2NN_ERR_ARG; }
     if (n_plus_1 != c->layers[0] + 1 || k != c->layers.back()) { set_error("data shape does not match the layers"); return B2NN_ERR_ARG; }
@@ -1463,14 +1707,13 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
     std::vector<int64_t> global_rows(nb);
     for (int b = 0; b < nb; ++b) global_rows[b] = batch_rows(b);
     if (c->comm) {
-        int64_t* tmp = nullptr;
-        B2_CUDA(cudaMalloc(&tmp, sizeof(int64_t) * nb));
-        B2_CUDA(cudaMemcpyAsync(tmp, global_rows.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice, c->stream));
-        int r = g_nccl.AllReduce(tmp, tmp, size_t(nb), NCCL_INT64, NCCL_SUM, c->comm, c->stream);
-        if (r != 0) { cudaFree(tmp); set_error("ncclAllReduce(batch rows) failed"); return B2NN_ERR_CUDA; }
-        B2_CUDA(cudaMemcpyAsync(global_rows.data(), tmp, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, c->stream));
+        DevBuf tmp;
+        B2_CUDA(cudaMalloc(&tmp.p, sizeof(int64_t) * nb));
+        B2_CUDA(cudaMemcpyAsync(tmp.p, global_rows.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice, c->stream));
+        int r = g_nccl.AllReduce(tmp.p, tmp.p, size_t(nb), NCCL_INT64, NCCL_SUM, c->comm, c->stream);
+        if (r != 0) { set_error("ncclAllReduce(batch rows) failed"); return B2NN_ERR_CUDA; }
+        B2_CUDA(cudaMemcpyAsync(global_rows.data(), tmp.p, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, c->stream));
         B2_CUDA(cudaStreamSynchronize(c->stream));
-        cudaFree(tmp);
         while (c->grad_ready.size() < c->L.size()) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->grad_ready.push_back(e); }
         while (c->grad_reduced.size() < c->L.size()) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->grad_reduced.push_back(e); }
     }
@@ -1488,8 +1731,9 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
     };
 
     const int64_t launches0 = c->launches, tc0 = c->tc_launches;
-    cudaEvent_t ev0, ev1;
-    B2_CUDA(cudaEventCreate(&ev0)); B2_CUDA(cudaEventCreate(&ev1));
+    EventPair evs;
+    B2_CUDA(cudaEventCreate(&evs.a)); B2_CUDA(cudaEventCreate(&evs.b));
+    cudaEvent_t const ev0 = evs.a, ev1 = evs.b;
     B2_CUDA(cudaEventRecord(ev0, c->stream));
     rc = issue_copy(0);
     if (rc) return rc;
@@ -1513,7 +1757,6 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
     B2_CUDA(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     B2_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (J_steps)
         for (int64_t s = 0; s < steps; ++s) {
             const double rows = double(batch_rows(int(s % nb)));
@@ -1531,24 +1774,40 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
     return B2NN_OK;
 }
 
+static int evaluate_impl(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const float* y, int64_t rows, int y_is_labels,
+                         double* cost_out, double* errors_out, bool raw, bool normalise);
+
 int b2nn_evaluate(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const float* y, int64_t rows, int y_is_labels,
                   double* cost_out, double* errors_out) {
-    int rc = validate_desc(c, d);
+    return evaluate_impl(c, d, x, y, rows, y_is_labels, cost_out, errors_out, false, false);
+}
+int b2nn_evaluate_raw(b2nn_ctx* c, const b2nn_train_desc* d, const float* x_raw, const float* y, int64_t rows, int y_is_labels,
+                      int normalise, double* cost_out, double* errors_out) {
+    return evaluate_impl(c, d, x_raw, y, rows, y_is_labels, cost_out, errors_out, true, normalise != 0);
+}
+
+static int evaluate_impl(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const float* y, int64_t rows, int y_is_labels,
+                         double* cost_out, double* errors_out, bool raw, bool normalise) {
+    int rc = validate_desc(c, d, false);
     if (rc) return rc;
     if (!x || !y || rows < 1) { set_error("evaluate: bad arguments"); return B2NN_ERR_ARG; }
+    if (normalise && c->norm_n != c->layers[0]) { set_error("evaluate_raw: no normalisation statistics (b2nn_set_train_data_raw / b2nn_set_normalisation first)"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
     const int prec = resolve_precision(d->precision);
     const int n = c->layers[0], K = c->layers.back();
     const int64_t ld = round_up(rows, 32);
-    float *xd = nullptr, *yd = nullptr, *lab = nullptr;
-    B2_CUDA(cudaMalloc(&xd, sizeof(float) * ld * (n + 1)));
-    B2_CUDA(cudaMalloc(&yd, sizeof(float) * ld * K));
+    DevBuf xbuf, ybuf, labbuf;
+    B2_CUDA(cudaMalloc(&xbuf.p, sizeof(float) * ld * (n + 1)));
+    B2_CUDA(cudaMalloc(&ybuf.p, sizeof(float) * ld * K));
+    float *xd = xbuf.as<float>(), *yd = ybuf.as<float>(), *lab = nullptr;
     B2_CUDA(cudaMemsetAsync(xd, 0, sizeof(float) * ld * (n + 1), c->stream));
-    rc = stage_x_from_host(c, x, rows, 0, rows, n, xd, ld, true);
+    rc = stage_x_from_host(c, x, rows, 0, rows, n, xd, ld, true, raw);
+    if (!rc && normalise) rc = normalise_rows_launch(xd, ld, rows, n, c->d_mean, c->d_std, c->stream) == cudaSuccess ? 0 : B2NN_ERR_CUDA;
     if (!rc) {
         if (y_is_labels && d->classify) {
             // validate(): labels -> one-hot for the cost, raw labels for the error count (cublasNN.cpp:788-790, 859)
-            rc = cudaMalloc(&lab, sizeof(float) * rows) == cudaSuccess ? 0 : B2NN_ERR_ALLOC;
+            rc = cudaMalloc(&labbuf.p, sizeof(float) * rows) == cudaSuccess ? 0 : B2NN_ERR_ALLOC;
+            lab = labbuf.as<float>();
             if (!rc) rc = cudaMemcpyAsync(lab, y, sizeof(float) * rows, cudaMemcpyHostToDevice, c->stream) == cudaSuccess ? 0 : B2NN_ERR_CUDA;
             if (!rc) rc = labels_to_onehot_launch(lab, yd, ld, rows, K, c->stream) == cudaSuccess ? 0 : B2NN_ERR_CUDA;
         } else {
@@ -1560,49 +1819,147 @@ int b2nn_evaluate(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const f
     cudaStreamSynchronize(c->stream);
     c->plans.clear();      // plans reference xd
     drop_lo(c, xd);
-    cudaFree(xd); cudaFree(yd); cudaFree(lab);
     return rc;
 }
 
+// Copy a [rows x cols] block of floats between two pitched host matrices, split over a few threads when it is large
+// (one thread packs ~10 GB/s; PCIe gen5 moves ~50).
+static void host_copy_2d(float* dst, int64_t dst_pitch, const float* src, int64_t src_pitch, int64_t rows, int64_t cols) {
+    auto work = [=](int64_t c0, int64_t c1) {
+        for (int64_t j = c0; j < c1; ++j) std::memcpy(dst + j * dst_pitch, src + j * src_pitch, sizeof(float) * size_t(rows));
+    };
+    const int64_t bytes = rows * cols * int64_t(sizeof(float));
+    int nt = int(std::min<int64_t>(std::min<int64_t>(8, std::max(1u, std::thread::hardware_concurrency())), cols));
+    if (bytes < (int64_t(2) << 20) || nt <= 1) { work(0, cols); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, cols * t / nt, cols * (t + 1) / nt);
+    work(0, cols / nt);
+    for (auto& t : th) t.join();
+}
+
+// predict (cublasNN.cpp:906-977: cudaMalloc, one pageable H2D of the whole matrix, forward, one D2H).  Here the rows
+// travel in chunks through two pinned staging buffers and two device buffers: chunk c+1 is packed and copied H2D while
+// chunk c computes and chunk c-1's results come back, so a large batch runs at the PCIe rate and never needs more than
+// two chunks of device memory.  A source that is already pinned (cudaMallocHost / cudaHostRegister) is DMA'd directly.
+static int predict_impl(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, int64_t rows, float* out, float* probs, bool raw,
+                        bool normalise);
+
 int b2nn_predict(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, int64_t rows, float* out, float* probs) {
-    int rc = validate_desc(c, d);
+    return predict_impl(c, d, x, rows, out, probs, false, false);
+}
+int b2nn_predict_raw(b2nn_ctx* c, const b2nn_train_desc* d, const float* x_raw, int64_t rows, int normalise, float* out, float* probs) {
+    return predict_impl(c, d, x_raw, rows, out, probs, true, normalise != 0);
+}
+
+static int predict_impl(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, int64_t rows, float* out, float* probs, bool raw,
+                        bool normalise) {
+    int rc = validate_desc(c, d, false);
     if (rc) return rc;
     if (!x || !out || rows < 1) { set_error("predict: bad arguments"); return B2NN_ERR_ARG; }
+    if (normalise && c->norm_n != c->layers[0]) { set_error("predict_raw: no normalisation statistics (b2nn_set_train_data_raw / b2nn_set_normalisation first)"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
     const int prec = resolve_precision(d->precision);
     const int n = c->layers[0], K = c->layers.back();
-    const int64_t ld = round_up(rows, 32);
+    // ~48 MB of input per chunk: long enough for the full PCIe rate, short enough that the pipeline fills quickly
+    int64_t chunk = std::min<int64_t>(int64_t(1) << 17, std::max<int64_t>(1024, ((int64_t(48) << 20) / (4 * int64_t(n))) / 32 * 32));
+    if (const char* e = std::getenv("B2NN_PREDICT_CHUNK")) chunk = std::max<int64_t>(32, std::atoll(e) / 32 * 32);
+    if (rows <= chunk + chunk / 4) chunk = round_up(rows, 32);
+    const int64_t ld = chunk;
+    cudaPointerAttributes pa{};
+    const bool src_pinned = cudaPointerGetAttributes(&pa, x) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
     if (ld > c->pr_ld || n != c->pr_n || K != c->pr_k) {
-        drop_lo(c, c->pr_x);
-        cudaFree(c->pr_x); cudaFree(c->pr_p); cudaFree(c->pr_h); c->pr_x = c->pr_p = c->pr_h = nullptr; c->pr_ld = 0;
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 2; ++i) {
+            drop_lo(c, c->pr_x[i]);
+            cudaFree(c->pr_x[i]); cudaFree(c->pr_p[i]); cudaFree(c->pr_h[i]); c->pr_x[i] = c->pr_p[i] = c->pr_h[i] = nullptr;
+            if (c->pr_hx[i]) cudaFreeHost(c->pr_hx[i]);
+            if (c->pr_hout[i]) cudaFreeHost(c->pr_hout[i]);
+            c->pr_hx[i] = c->pr_hout[i] = nullptr;
+        }
+        c->pr_ld = 0;
         c->plans.clear();
-        B2_CUDA(cudaMalloc(&c->pr_x, sizeof(float) * ld * (n + 1)));
-        B2_CUDA(cudaMalloc(&c->pr_p, sizeof(float) * ld));
-        B2_CUDA(cudaMalloc(&c->pr_h, sizeof(float) * ld * K));
+        const int nbuf = rows > chunk ? 2 : 1;
+        for (int i = 0; i < nbuf; ++i) {
+            B2_CUDA(cudaMalloc(&c->pr_x[i], sizeof(float) * ld * (n + 1)));
+            B2_CUDA(cudaMalloc(&c->pr_p[i], sizeof(float) * ld));
+            B2_CUDA(cudaMalloc(&c->pr_h[i], sizeof(float) * ld * K));
+            B2_CUDA(cudaMallocHost(&c->pr_hout[i], sizeof(float) * ld * (K + 1)));
+            B2_CUDA(cudaMemsetAsync(c->pr_x[i], 0, sizeof(float) * ld * (n + 1), c->stream));
+            B2_CUDA(fill_launch(c->pr_x[i] + int64_t(n) * ld, 1.0f, ld, c->stream));
+        }
         c->pr_ld = ld; c->pr_n = n; c->pr_k = K;
-        B2_CUDA(cudaMemsetAsync(c->pr_x, 0, sizeof(float) * ld * (n + 1), c->stream));
-        B2_CUDA(fill_launch(c->pr_x + int64_t(n) * ld, 1.0f, ld, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));           // the copy stream may touch the buffers next
     }
-    float *xd = c->pr_x, *pd = c->pr_p, *hd = c->pr_h;
     const int64_t ldp = c->pr_ld;
-    rc = stage_x_from_host(c, x, rows, 0, rows, n, xd, ldp, false);
-    if (!rc) rc = evaluate_device(c, d, prec, xd, ldp, nullptr, 0, nullptr, rows, d->classify ? pd : nullptr, hd, ldp, nullptr, nullptr);
-    if (!rc) {
-        cudaError_t e;
-        if (d->classify) e = cudaMemcpyAsync(out, pd, sizeof(float) * rows, cudaMemcpyDeviceToHost, c->stream);
-        else e = cudaMemcpy2DAsync(out, sizeof(float) * rows, hd, sizeof(float) * ldp, sizeof(float) * rows, size_t(K),
-                                   cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess && probs)
-            e = cudaMemcpy2DAsync(probs, sizeof(float) * rows, hd, sizeof(float) * ldp, sizeof(float) * rows, size_t(K),
-                                  cudaMemcpyDeviceToHost, c->stream);
-        if (e != cudaSuccess) { set_error(std::string("predict copy back: ") + cudaGetErrorString(e)); rc = B2NN_ERR_CUDA; }
+    const int64_t nchunks = (rows + chunk - 1) / chunk;
+    if (nchunks > 1 && !c->pr_x[1]) {                         // the buffers were sized by a single-chunk call
+        B2_CUDA(cudaMalloc(&c->pr_x[1], sizeof(float) * ldp * (n + 1)));
+        B2_CUDA(cudaMalloc(&c->pr_p[1], sizeof(float) * ldp));
+        B2_CUDA(cudaMalloc(&c->pr_h[1], sizeof(float) * ldp * K));
+        B2_CUDA(cudaMallocHost(&c->pr_hout[1], sizeof(float) * ldp * (K + 1)));
+        B2_CUDA(cudaMemsetAsync(c->pr_x[1], 0, sizeof(float) * ldp * (n + 1), c->stream));
+        B2_CUDA(fill_launch(c->pr_x[1] + int64_t(n) * ldp, 1.0f, ldp, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));
     }
-    cudaStreamSynchronize(c->stream);
-    return rc;
+    if (!src_pinned)
+        for (int i = 0; i < (nchunks > 1 ? 2 : 1); ++i)
+            if (!c->pr_hx[i]) B2_CUDA(cudaMallocHost(&c->pr_hx[i], sizeof(float) * ldp * n));
+    if (!c->copy_stream) B2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->pr_d2h_stream) B2_CUDA(cudaStreamCreateWithFlags(&c->pr_d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        if (!c->pr_copied[i]) B2_CUDA(cudaEventCreateWithFlags(&c->pr_copied[i], cudaEventDisableTiming));
+        if (!c->pr_computed[i]) B2_CUDA(cudaEventCreateWithFlags(&c->pr_computed[i], cudaEventDisableTiming));
+        if (!c->pr_out[i]) B2_CUDA(cudaEventCreateWithFlags(&c->pr_out[i], cudaEventDisableTiming));
+    }
+    const bool want_h = !d->classify || probs != nullptr;
+    auto drain = [&](int64_t ci) -> int {                     // chunk ci's results: pinned staging -> the caller's arrays
+        const int buf = int(ci & 1);
+        const int64_t s0 = ci * chunk, r = std::min<int64_t>(chunk, rows - s0);
+        B2_CUDA(cudaEventSynchronize(c->pr_out[buf]));
+        const float* ho = c->pr_hout[buf];
+        if (d->classify) std::memcpy(out + s0, ho, sizeof(float) * size_t(r));
+        else host_copy_2d(out + s0, rows, ho + ldp, ldp, r, K);
+        if (probs) host_copy_2d(probs + s0, rows, ho + ldp, ldp, r, K);
+        return B2NN_OK;
+    };
+    for (int64_t ci = 0; ci < nchunks; ++ci) {
+        const int buf = int(ci & 1);
+        const int64_t s0 = ci * chunk, r = std::min<int64_t>(chunk, rows - s0);
+        // column f+1 of the reference matrix (its ones column is skipped) is feature row f of the engine matrix
+        const float* src = x + (raw ? 0 : rows) + s0;
+        if (ci >= 2) B2_CUDA(cudaStreamWaitEvent(c->copy_stream, c->pr_computed[buf], 0));    // device buffer free again
+        if (src_pinned) {
+            B2_CUDA(cudaMemcpy2DAsync(c->pr_x[buf], sizeof(float) * ldp, src, sizeof(float) * rows, sizeof(float) * r, size_t(n),
+                                      cudaMemcpyHostToDevice, c->copy_stream));
+        } else {
+            if (ci >= 2) B2_CUDA(cudaEventSynchronize(c->pr_copied[buf]));                      // pinned staging free again
+            host_copy_2d(c->pr_hx[buf], r, src, rows, r, n);
+            B2_CUDA(cudaMemcpy2DAsync(c->pr_x[buf], sizeof(float) * ldp, c->pr_hx[buf], sizeof(float) * r, sizeof(float) * r, size_t(n),
+                                      cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        B2_CUDA(cudaEventRecord(c->pr_copied[buf], c->copy_stream));
+        B2_CUDA(cudaStreamWaitEvent(c->stream, c->pr_copied[buf], 0));
+        if (ci >= 2) B2_CUDA(cudaStreamWaitEvent(c->stream, c->pr_out[buf], 0));               // previous results have left
+        if (normalise) B2_CUDA(normalise_rows_launch(c->pr_x[buf], ldp, r, n, c->d_mean, c->d_std, c->stream));
+        rc = evaluate_device(c, d, prec, c->pr_x[buf], ldp, nullptr, 0, nullptr, r, d->classify ? c->pr_p[buf] : nullptr,
+                             want_h ? c->pr_h[buf] : nullptr, ldp, nullptr, nullptr, ldp);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        B2_CUDA(cudaEventRecord(c->pr_computed[buf], c->stream));
+        B2_CUDA(cudaStreamWaitEvent(c->pr_d2h_stream, c->pr_computed[buf], 0));
+        if (d->classify)
+            B2_CUDA(cudaMemcpyAsync(c->pr_hout[buf], c->pr_p[buf], sizeof(float) * r, cudaMemcpyDeviceToHost, c->pr_d2h_stream));
+        if (want_h)
+            B2_CUDA(cudaMemcpy2DAsync(c->pr_hout[buf] + ldp, sizeof(float) * ldp, c->pr_h[buf], sizeof(float) * ldp, sizeof(float) * r,
+                                      size_t(K), cudaMemcpyDeviceToHost, c->pr_d2h_stream));
+        B2_CUDA(cudaEventRecord(c->pr_out[buf], c->pr_d2h_stream));
+        if (ci >= 1) { rc = drain(ci - 1); if (rc) return rc; }
+    }
+    return drain(nchunks - 1);
 }
 
 int b2nn_predict_device(b2nn_ctx* c, const b2nn_train_desc* d, const float* x_dev, int64_t rows, int64_t ld, float* out_dev) {
-    int rc = validate_desc(c, d);
+    int rc = validate_desc(c, d, false);
     if (rc) return rc;
     if (!x_dev || !out_dev || rows < 1 || ld < rows) { set_error("predict_device: bad arguments"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
@@ -1621,21 +1978,21 @@ int b2nn_gemm(b2nn_ctx* c, int backend, const float* A, int64_t lda, int a_major
     g.D = D; g.ldd = ldd; g.M = M; g.N = N; g.K = K; g.epi = epi; g.aux = aux; g.ldaux = ldaux;
     if (backend == 1 || backend == 3 || backend == 5 || backend == 7) {
         g.mn_slack = (backend & 2) != 0;
-        float *alo = nullptr, *blo = nullptr;
+        DevBuf alo, blo;
         if (backend & 4) {          // fp32-grade mode: split the operands into temporaries first
             const int64_t na = (a_major ? int64_t(K) : int64_t(M)) * lda + (g.mn_slack ? 32 : 0);
             const int64_t nbb = (b_major ? int64_t(K) : int64_t(N)) * ldb + (g.mn_slack ? 32 : 0);
-            B2_CUDA(cudaMalloc(&alo, sizeof(float) * na));
-            B2_CUDA(cudaMalloc(&blo, sizeof(float) * nbb));
-            B2_CUDA(split_lo_launch(A, alo, na, c->stream));
-            B2_CUDA(split_lo_launch(B, blo, nbb, c->stream));
-            g.A_lo = alo; g.B_lo = blo;
+            B2_CUDA(cudaMalloc(&alo.p, sizeof(float) * na));
+            B2_CUDA(cudaMalloc(&blo.p, sizeof(float) * nbb));
+            B2_CUDA(split_lo_launch(A, alo.as<float>(), na, c->stream));
+            B2_CUDA(split_lo_launch(B, blo.as<float>(), nbb, c->stream));
+            g.A_lo = alo.as<float>(); g.B_lo = blo.as<float>();
         }
         TcPlan plan;
         std::string err;
-        if (!tc_plan_build(plan, g, err)) { cudaFree(alo); cudaFree(blo); set_error("tcgen05 plan: " + err); return B2NN_ERR_ARG; }
+        if (!tc_plan_build(plan, g, err)) { set_error("tcgen05 plan: " + err); return B2NN_ERR_ARG; }
         cudaError_t le = tc_plan_launch(plan, c->stream);
-        if (backend & 4) { cudaStreamSynchronize(c->stream); cudaFree(alo); cudaFree(blo); }
+        if (backend & 4) cudaStreamSynchronize(c->stream);      // the temporaries are freed when this scope ends
         B2_CUDA(le);
         ++c->tc_launches;
     } else {
@@ -1784,15 +2141,7 @@ int b2nn_comm_p2p_open(b2nn_ctx* c, const void* blobs) {
 
 int b2nn_comm_barrier(b2nn_ctx* c) {
     if (!c) { set_error("null ctx"); return B2NN_ERR_ARG; }
-    B2_CUDA(cudaSetDevice(c->device));
-    if (c->comm) {
-        int rc = ensure_acc(c, 3);
-        if (rc) return rc;
-        int r = g_nccl.AllReduce(c->d_acc, c->d_acc, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
-        if (r != 0) { set_error("ncclAllReduce(barrier) failed"); return B2NN_ERR_CUDA; }
-    }
-    B2_CUDA(cudaStreamSynchronize(c->stream));
-    return B2NN_OK;
+    return comm_barrier_impl(c);
 }
 
 }  // extern "C"

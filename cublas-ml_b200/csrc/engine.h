@@ -116,6 +116,9 @@ cudaError_t split_batches_launch(const float* src, int64_t ld_src, float* dst, i
                                  int64_t bs_pad, int nb, int n_rows, cudaStream_t s);
 cudaError_t multiply_launch(const float* a, const float* b, float* out, int64_t count, cudaStream_t s);  // out may alias b
 cudaError_t init_scale_launch(float* theta, int in, int out, int64_t count, int kind, cudaStream_t s);
+// device-side normaliseData: per-feature mean / (m-1) standard deviation of an engine-layout matrix, and its application
+cudaError_t feature_stats_launch(const float* x, int64_t ld, int64_t rows, int n, float* mean, float* stddev, cudaStream_t s);
+cudaError_t normalise_rows_launch(float* x, int64_t ld, int64_t rows, int n, const float* mean, const float* stddev, cudaStream_t s);
 cudaError_t labels_to_onehot_launch(const float* labels, float* y, int64_t ldy, int64_t rows, int K, cudaStream_t s);
 
 // Fused skinny last layer (tail.cu): forward + output activation + delta + cost/argmax [+ delta backprop + gradient].

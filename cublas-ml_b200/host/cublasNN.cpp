@@ -1,8 +1,10 @@
 // cublasNN.cpp — host-side mirror of the reference's class cublasNN over the C ABI of include/b2nn.h.
 //
-// Host work kept here (one-shot, not on the hot path): CSV I/O, vector -> column-major conversion, one-hot encoding,
-// z-score normalisation, the bias column.  Everything that touches the GPU goes through b2nn_* calls; this file does
-// not include a CUDA header.  Printed text follows the reference byte for byte where the reference prints
+// Host work kept here (one-shot, not on the hot path): CSV I/O, vector -> column-major conversion, one-hot encoding.
+// normalise*Data and addBias* only record what was asked for: the z-score statistics, their application and the ones
+// row happen on the device while the rows are staged (b2nn_set_train_data_raw / b2nn_evaluate_raw / b2nn_predict_raw;
+// reference: host loops, cublasNN.cpp:191-268, 330-346).  Everything that touches the GPU goes through b2nn_* calls;
+// this file does not include a CUDA header.  Printed text follows the reference byte for byte where the reference prints
 // (cublasNN.cpp:555, 616, 745, 760, 849, 861-862); failures print the reference's messages and return early.
 #include "cublasNN.h"
 #include "b2nn.h"
@@ -56,16 +58,6 @@ HostMat one_hot(const HostMat& labels, int K) {
     return y;
 }
 
-// addBias (cublasNN.cpp:330-346): prepend a column of ones.
-void add_bias(HostMat& m) {
-    HostMat r;
-    r.rows = m.rows; r.cols = m.cols + 1;
-    r.v.resize(size_t(r.rows) * size_t(r.cols));
-    std::fill(r.v.begin(), r.v.begin() + r.rows, 1.0f);
-    std::memcpy(r.v.data() + r.rows, m.v.data(), sizeof(float) * m.v.size());
-    m = std::move(r);
-}
-
 void print_log(void*, int iter, float J) { std::cout << "Iteration: " << iter << "\t" << "Cost: " << J << std::endl; }
 
 }  // namespace
@@ -84,8 +76,8 @@ struct cublasNN::Impl {
     HostMat x, y, xValidate, yValidate, xPredict;
     bool classify_data = false;
     int n = 0;                   // features without bias (cublasNN.cpp:151)
-    bool x_has_bias = false, xv_has_bias = false, xp_has_bias = false;
-    std::vector<float> mean, stddev;
+    bool x_has_bias = false, xv_has_bias = false, xp_has_bias = false;      // addBias* was called (the ones row is the engine's)
+    bool x_norm = false, xv_norm = false, xp_norm = false;                  // normalise*Data was called
     b2nn_train_result last{};
 
     bool ensure_ctx() {
@@ -114,15 +106,6 @@ struct cublasNN::Impl {
         } else {
             d.out_kind = B2NN_OUT_LINEAR; d.cost_kind = B2NN_COST_SQUARED;
         }
-    }
-
-    void normalise(HostMat& m) const {          // cublasNN.cpp:199-212
-        if (m.empty() || mean.empty()) return;
-        for (int j = 0; j < m.cols && j < int(mean.size()); ++j)
-            for (long long i = 0; i < m.rows; ++i) {
-                float v = m.at(i, j) - mean[size_t(j)];
-                m.at(i, j) = (stddev[size_t(j)] != 0.f) ? v / stddev[size_t(j)] : 0.f;
-            }
     }
 
     double train(bool classify, float momentum, float rate, HiddenFn act, HiddenFn grad, OutputFn out, CostFn cost,
@@ -217,7 +200,7 @@ void cublasNN::setData(vector<vector<float>> xVec, vector<vector<float>> yVec, b
     if (xVec.empty() || yVec.empty()) { std::cout << "setData: empty input" << std::endl; return; }
     impl->x = to_colmajor(xVec);
     impl->n = impl->x.cols;
-    impl->x_has_bias = false;
+    impl->x_has_bias = false; impl->x_norm = false;
     impl->classify_data = classify;
     HostMat yRaw = to_colmajor(yVec);
     if (classify) {
@@ -231,12 +214,12 @@ void cublasNN::setData(vector<vector<float>> xVec, vector<vector<float>> yVec, b
 void cublasNN::setValidateData(vector<vector<float>> xVec, vector<vector<float>> yVec, bool) {
     impl->xValidate = to_colmajor(xVec);
     impl->yValidate = to_colmajor(yVec);          // kept raw: labels for classification (cublasNN.cpp:177-178)
-    impl->xv_has_bias = false;
+    impl->xv_has_bias = false; impl->xv_norm = false;
 }
 
 void cublasNN::setPredictData(vector<vector<float>> xVec) {
     impl->xPredict = to_colmajor(xVec);
-    impl->xp_has_bias = false;
+    impl->xp_has_bias = false; impl->xp_norm = false;
 }
 
 void cublasNN::setLayers(int* l, int lNum, InitFn randInitWeights) {
@@ -256,31 +239,16 @@ void cublasNN::setIters(int i) { impl->iters = i; }
 void cublasNN::setDisplay(int i) { impl->display = i; }
 void cublasNN::setLambda(int l) { impl->lambda = float(l); }
 
-// mean / stddev (cublasNN.cpp:214-268): float accumulation in row order, n-1 normalisation, then normalise().
-void cublasNN::normaliseData() {
-    HostMat& x = impl->x;
-    if (x.empty()) return;
-    impl->mean.assign(size_t(x.cols), 0.f);
-    impl->stddev.assign(size_t(x.cols), 0.f);
-    for (int j = 0; j < x.cols; ++j) {
-        float s = 0.f;
-        for (long long i = 0; i < x.rows; ++i) s += x.at(i, j);
-        impl->mean[size_t(j)] = s / float(x.rows);
-    }
-    for (int j = 0; j < x.cols; ++j) {
-        float s = 0.f;
-        const float mu = impl->mean[size_t(j)];
-        for (long long i = 0; i < x.rows; ++i) { const float d = x.at(i, j) - mu; s += d * d; }
-        impl->stddev[size_t(j)] = std::sqrt(s / float(x.rows - 1));
-    }
-    impl->normalise(x);
-}
-void cublasNN::normaliseValidateData() { impl->normalise(impl->xValidate); }
-void cublasNN::normalisePredictData() { impl->normalise(impl->xPredict); }
+// normaliseData (cublasNN.cpp:191-268): mean / (m-1) standard deviation of the training features, then (x - mean) / stddev.
+// Recorded here, done on the device in copyDataGPU (statistics) and while validate / predict rows are staged.
+void cublasNN::normaliseData() { if (!impl->x.empty()) impl->x_norm = true; }
+void cublasNN::normaliseValidateData() { if (!impl->xValidate.empty()) impl->xv_norm = true; }
+void cublasNN::normalisePredictData() { if (!impl->xPredict.empty()) impl->xp_norm = true; }
 
-void cublasNN::addBiasData() { if (!impl->x.empty() && !impl->x_has_bias) { add_bias(impl->x); impl->x_has_bias = true; } }
-void cublasNN::addBiasDataValidate() { if (!impl->xValidate.empty() && !impl->xv_has_bias) { add_bias(impl->xValidate); impl->xv_has_bias = true; } }
-void cublasNN::addBiasDataPredict() { if (!impl->xPredict.empty() && !impl->xp_has_bias) { add_bias(impl->xPredict); impl->xp_has_bias = true; } }
+// addBias (cublasNN.cpp:330-346): the ones column.  The engine keeps its own ones row; the call is only recorded.
+void cublasNN::addBiasData() { if (!impl->x.empty()) impl->x_has_bias = true; }
+void cublasNN::addBiasDataValidate() { if (!impl->xValidate.empty()) impl->xv_has_bias = true; }
+void cublasNN::addBiasDataPredict() { if (!impl->xPredict.empty()) impl->xp_has_bias = true; }
 
 void cublasNN::copyDataGPU() {
     if (!impl->ensure_ctx()) return;
@@ -288,7 +256,8 @@ void cublasNN::copyDataGPU() {
         std::cout << "copyDataGPU: setData and addBiasData must be called first" << std::endl;
         return;
     }
-    if (b2nn_set_train_data(impl->ctx, impl->x.v.data(), impl->y.v.data(), impl->x.rows, impl->x.cols, impl->y.cols) != B2NN_OK) {
+    if (b2nn_set_train_data_raw(impl->ctx, impl->x.v.data(), impl->y.v.data(), impl->x.rows, impl->x.cols, impl->y.cols,
+                                impl->x_norm ? 1 : 0, nullptr, nullptr) != B2NN_OK) {
         const char* e = b2nn_last_error();
         std::cout << e << std::endl;            // "cudaMalloc Failed" / "cudaMemcpy Failed" in the reference (cublasNN.cpp:366, 373)
     }
@@ -311,7 +280,8 @@ void cublasNN::validateFuncApprox(HiddenFn activationHidden) {
     b2nn_train_desc d;
     impl->fill_desc(d, false, activationHidden, nullptr, nullptr, nullptr);
     double J = 0, errs = 0;
-    if (b2nn_evaluate(impl->ctx, &d, impl->xValidate.v.data(), impl->yValidate.v.data(), impl->xValidate.rows, 0, &J, &errs) != B2NN_OK) {
+    if (b2nn_evaluate_raw(impl->ctx, &d, impl->xValidate.v.data(), impl->yValidate.v.data(), impl->xValidate.rows, 0,
+                          impl->xv_norm ? 1 : 0, &J, &errs) != B2NN_OK) {
         std::cout << "b2nn_evaluate failed: " << b2nn_last_error() << std::endl;
         return;
     }
@@ -323,7 +293,8 @@ void cublasNN::validateClassify(HiddenFn activationHidden, OutputFn activationOu
     b2nn_train_desc d;
     impl->fill_desc(d, true, activationHidden, nullptr, activationOutput, costFunction);
     double J = 0, errs = 0;
-    if (b2nn_evaluate(impl->ctx, &d, impl->xValidate.v.data(), impl->yValidate.v.data(), impl->xValidate.rows, 1, &J, &errs) != B2NN_OK) {
+    if (b2nn_evaluate_raw(impl->ctx, &d, impl->xValidate.v.data(), impl->yValidate.v.data(), impl->xValidate.rows, 1,
+                          impl->xv_norm ? 1 : 0, &J, &errs) != B2NN_OK) {
         std::cout << "b2nn_evaluate failed: " << b2nn_last_error() << std::endl;
         return;
     }
@@ -332,11 +303,12 @@ void cublasNN::validateClassify(HiddenFn activationHidden, OutputFn activationOu
     std::cout << "Validation error frequency" << '\t' << (float(errs) / float(impl->xValidate.rows)) << std::endl;
 }
 
-static vector<vector<float>> run_predict(b2nn_ctx* ctx, const b2nn_train_desc& d, const std::vector<float>& x, long long rows, int K) {
+static vector<vector<float>> run_predict(b2nn_ctx* ctx, const b2nn_train_desc& d, const std::vector<float>& x, long long rows, int K,
+                                         bool normalise) {
     vector<vector<float>> result;
     const int outputs = d.classify ? 1 : K;                                                           // cublasNN.cpp:968
     std::vector<float> out(size_t(rows) * size_t(outputs));
-    if (b2nn_predict(ctx, &d, x.data(), rows, out.data(), nullptr) != B2NN_OK) {
+    if (b2nn_predict_raw(ctx, &d, x.data(), rows, normalise ? 1 : 0, out.data(), nullptr) != B2NN_OK) {
         std::cout << "b2nn_predict failed: " << b2nn_last_error() << std::endl;
         return result;
     }
@@ -352,14 +324,14 @@ vector<vector<float>> cublasNN::predictFuncApprox(HiddenFn activationHidden) {
     if (!impl->ctx || impl->xPredict.empty() || !impl->xp_has_bias) { std::cout << "predict: no prediction data" << std::endl; return {}; }
     b2nn_train_desc d;
     impl->fill_desc(d, false, activationHidden, nullptr, nullptr, nullptr);
-    return run_predict(impl->ctx, d, impl->xPredict.v, impl->xPredict.rows, impl->layers.back());
+    return run_predict(impl->ctx, d, impl->xPredict.v, impl->xPredict.rows, impl->layers.back(), impl->xp_norm);
 }
 
 vector<vector<float>> cublasNN::predictClassify(HiddenFn activationHidden, OutputFn activationOutput) {
     if (!impl->ctx || impl->xPredict.empty() || !impl->xp_has_bias) { std::cout << "predict: no prediction data" << std::endl; return {}; }
     b2nn_train_desc d;
     impl->fill_desc(d, true, activationHidden, nullptr, activationOutput, nullptr);
-    return run_predict(impl->ctx, d, impl->xPredict.v, impl->xPredict.rows, impl->layers.back());
+    return run_predict(impl->ctx, d, impl->xPredict.v, impl->xPredict.rows, impl->layers.back(), impl->xp_norm);
 }
 
 void cublasNN::setSeed(unsigned long long seed) { impl->seed = seed; impl->seed_set = true; }
@@ -375,6 +347,21 @@ vector<float> cublasNN::getWeights() {
 void cublasNN::setWeights(const vector<float>& theta) {
     if (impl->ctx && b2nn_set_weights(impl->ctx, theta.data(), (long long)theta.size()) != B2NN_OK)
         std::cout << "b2nn_set_weights failed: " << b2nn_last_error() << std::endl;
+}
+bool cublasNN::saveCheckpoint(const string& path) {
+    if (!impl->ctx || b2nn_save_checkpoint(impl->ctx, path.c_str()) != B2NN_OK) {
+        std::cout << "b2nn_save_checkpoint failed: " << b2nn_last_error() << std::endl;
+        return false;
+    }
+    return true;
+}
+bool cublasNN::loadCheckpoint(const string& path) {
+    if (!impl->ensure_ctx()) return false;
+    if (b2nn_load_checkpoint(impl->ctx, path.c_str()) != B2NN_OK) {
+        std::cout << "b2nn_load_checkpoint failed: " << b2nn_last_error() << std::endl;
+        return false;
+    }
+    return true;
 }
 double cublasNN::lastFinalCost() const { return impl->last.final_cost; }
 double cublasNN::lastErrorCount() const { return impl->last.error_count; }

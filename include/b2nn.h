@@ -53,8 +53,10 @@ enum { B2NN_INIT_1 = 1 /* eps = 1/sqrt(in)          */, B2NN_INIT_2 = 2 /* eps =
        B2NN_INIT_CUSTOM = 3 };
 /* Arithmetic of the three contractions (forward, delta backprop, weight gradient). */
 enum { B2NN_PREC_FP32 = 0 /* fp32 FFMA, matches cublasSgemm default math up to summation order          */,
-       B2NN_PREC_TF32 = 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM; small layers stay on fp32 FFMA   */,
-       B2NN_PREC_AUTO = 2 /* B2NN_PRECISION env var ("fp32" | "tf32" | "tf32x3"), default tf32              */,
+       B2NN_PREC_TF32 = 1 /* tcgen05 kind::tf32 (inputs truncated to 10 mantissa bits), fp32 accumulate in TMEM; small layers
+                             stay on fp32 FFMA.  OPT-IN: narrower than the reference's arithmetic (stated bound 2e-2)  */,
+       B2NN_PREC_AUTO = 2 /* B2NN_PRECISION env var ("fp32" | "tf32" | "tf32x3" | "bf16"); default tf32x3 = fp32-grade, so a
+                             drop-in caller keeps the reference's fp32 tolerance without asking                        */,
        B2NN_PREC_TF32X3 = 3 /* fp32-grade on tensor cores: every operand carries its tf32 remainder and each K step
                                issues hi*hi + hi*lo + lo*hi (3 tcgen05.mma) into the fp32 TMEM accumulator            */ };
 
@@ -116,10 +118,26 @@ int64_t b2nn_num_weights(const b2nn_ctx* ctx);
 int b2nn_get_weights(b2nn_ctx* ctx, float* host_theta, int64_t count);
 int b2nn_set_weights(b2nn_ctx* ctx, const float* host_theta, int64_t count);
 
+/* Checkpoint file (not in the reference: its weights die with the process): layer widths, weights and velocity in the
+ * reference arena layout, the normalisation statistics when present, and a checksum.  load (re)creates the layers. */
+int b2nn_save_checkpoint(b2nn_ctx* ctx, const char* path);
+int b2nn_load_checkpoint(b2nn_ctx* ctx, const char* path);
+
 /* ---- data --------------------------------------------------------------------------------------------------- */
 /* replaces cublasNN::copyDataGPU + splitData (cublasNN.cpp:348-358, 498-524).  x: m x n_plus_1 (ones column first),
  * y: m x k, both column-major HOST buffers; the engine keeps its own device copy. */
 int b2nn_set_train_data(b2nn_ctx* ctx, const float* x, const float* y, int64_t m, int n_plus_1, int k);
+
+/* Device-side data staging: replaces normaliseData + addBiasData + copyDataGPU (cublasNN.cpp:191-268, 330-358) in one
+ * call.  x_raw: m x n column-major HOST matrix WITHOUT the ones column.  normalise != 0: the per-feature mean and (m-1)
+ * standard deviation are computed on the device (the reference's two passes, cublasNN.cpp:214-268, accumulated in double),
+ * applied in place ((x - mean) / stddev, 0 where the feature is constant, cublasNN.cpp:199-212) and kept in the context
+ * for b2nn_evaluate_raw / b2nn_predict_raw; mean_out / std_out (optional, n floats) receive them. */
+int b2nn_set_train_data_raw(b2nn_ctx* ctx, const float* x_raw, const float* y, int64_t m, int n, int k, int normalise,
+                            float* mean_out, float* std_out);
+/* Install / read the statistics directly (n = 0 clears them). */
+int b2nn_set_normalisation(b2nn_ctx* ctx, const float* mean, const float* stddev, int n);
+int b2nn_get_normalisation(b2nn_ctx* ctx, float* mean, float* stddev, int n);
 
 /* ---- the hot path ------------------------------------------------------------------------------------------- */
 /* replaces trainFuncApproxMomentum / trainClassifyMomentum (cublasNN.cpp:526-640). */
@@ -149,8 +167,15 @@ int b2nn_train_host(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x, 
 int b2nn_evaluate(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x, const float* y, int64_t rows,
                   int y_is_labels, double* cost_out, double* errors_out);
 /* replaces predict (cublasNN.cpp:906-977).  out: rows x 1 class ids when classify, rows x k column-major otherwise.
- * probs (optional): rows x k column-major activations of the last layer. */
+ * probs (optional): rows x k column-major activations of the last layer.  Large batches travel in chunks through two
+ * pinned staging buffers (H2D of chunk c+1, compute of chunk c and D2H of chunk c-1 overlap); a pinned x is DMA'd directly. */
 int b2nn_predict(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x, int64_t rows, float* out, float* probs);
+/* b2nn_evaluate / b2nn_predict on RAW rows (rows x n column-major, no ones column): normalise*Data + addBias* of the
+ * reference happen on the device while the rows are staged (normalise != 0 applies the stored statistics). */
+int b2nn_evaluate_raw(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x_raw, const float* y, int64_t rows,
+                      int y_is_labels, int normalise, double* cost_out, double* errors_out);
+int b2nn_predict_raw(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x_raw, int64_t rows, int normalise, float* out,
+                     float* probs);
 /* Same forward with x ALREADY on the device (config 5's data-resident inference sweep). */
 int b2nn_predict_device(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x_dev, int64_t rows, int64_t ld,
                         float* out_dev);

@@ -7,7 +7,7 @@
 // leaks `using namespace std;` because main.cpp relies on it (cublasNN.h:20).  Everything private is gone: the device
 // state lives behind the opaque engine handle, host state behind a pimpl.  No CUDA headers are needed to include this.
 //
-// Additions (not in the reference): setSeed / setPrecision / getWeights / setWeights / lastResult.
+// Additions (not in the reference): setSeed / setPrecision / getWeights / setWeights / save/loadCheckpoint / last*.
 #ifndef CUBLASNN_B200_H
 #define CUBLASNN_B200_H
 
@@ -72,9 +72,11 @@ public:
 
     // ---- additions -------------------------------------------------------------------------------------------------
     void setSeed(unsigned long long seed);      // pin the cuRAND seed (default: clock(), cublasNN.cpp:27); call before setLayers
-    void setPrecision(int b2nn_prec);           // B2NN_PREC_FP32 / B2NN_PREC_TF32 / B2NN_PREC_AUTO (default)
+    void setPrecision(int b2nn_prec);           // B2NN_PREC_AUTO (default: fp32-grade tf32x3) / _FP32 / _TF32X3 / _TF32 (opt-in, 10-bit inputs)
     vector<float> getWeights();                 // reference arena layout
     void setWeights(const vector<float>& theta);
+    bool saveCheckpoint(const string& path);    // layers + weights + velocity + normalisation statistics (b2nn_save_checkpoint)
+    bool loadCheckpoint(const string& path);    // call after setLayers (or instead of it: the file carries the layer widths)
     double lastFinalCost() const;
     double lastErrorCount() const;
     double lastLoopSeconds() const;
