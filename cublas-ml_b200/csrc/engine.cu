@@ -376,6 +376,20 @@ int prepare_x3(b2nn_ctx* c, const float* X, int64_t count, int64_t rows, bool cu
     return B2NN_OK;
 }
 
+constexpr double kTcMinWork = double(1 << 26);     // multiply-adds below which a contraction stays on the fp32 FFMA kernel
+
+// A tensor-core mode on a network none of whose contractions would reach the tensor cores (config C2's bikeshare net) is
+// plain fp32: skip the low-part bookkeeping of the fp32-grade mode altogether.
+int effective_precision(const b2nn_ctx* c, int prec, int64_t rows) {
+    if (prec != B2NN_PREC_TF32 && prec != B2NN_PREC_TF32X3) return prec;
+    for (size_t j = 0; j < c->L.size(); ++j) {
+        const LayerInfo& li = c->L[j];
+        const double work = double(rows) * double(li.in + 1) * double(li.out);
+        if (work >= kTcMinWork || (li.in + 1 >= 512 && work >= double(1 << 15))) return prec;
+    }
+    return B2NN_PREC_FP32;
+}
+
 // Decide the backend of one contraction and, for tcgen05, build its tensor maps.
 void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
     GemmDesc& g = op.g;
@@ -399,7 +413,7 @@ void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
     // ... except long-K contractions with few rows (small-batch inference on a wide input, config C5): the FFMA kernel
     // would walk K serially in a single block, the tcgen05 pipeline streams it in a few microseconds.
     const bool long_k_few_rows = !allow_split && g.a_major == 1 && g.b_major == 0 && g.K >= 512 && work >= double(1 << 15);
-    if ((prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3) && (work >= double(1 << 26) || long_k_few_rows)) {
+    if ((prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3) && (work >= kTcMinWork || long_k_few_rows)) {
         std::string err;
         const int requested = g.split_k;
         if (g.epi == EPI_STORE && (allow_split || g.N <= 32)) g.split_k = 0;     // let the tcgen05 plan pick the split
@@ -1404,11 +1418,11 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
     if (!c->X || !c->Y) { set_error("set_train_data must precede train (copyDataGPU, main.cpp:87)"); return B2NN_ERR_ARG; }
     if (d->batch_num < 1 || int64_t(d->batch_num) > c->m) { set_error("batch_num must be in [1, m]"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
-    const int prec = resolve_precision(d->precision);
     const int display = d->display > 0 ? d->display : 1;               // Q5
     const int nb = d->batch_num;
     const int64_t bs = c->m / nb;                                      // cublasNN.cpp:401
     const int64_t last_rows = c->m - int64_t(nb - 1) * bs;             // last batch absorbs the remainder (:429)
+    const int prec = effective_precision(c, resolve_precision(d->precision), last_rows);
 
     B2_CUDA(cudaMemsetAsync(c->V, 0, sizeof(float) * c->total_int, c->stream));   // :533-534, :590-591
     rc = ensure_workspace(c, last_rows, d->act_kind == B2NN_ACT_CUSTOM);
@@ -1609,7 +1623,7 @@ int b2nn_train_step_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, 
     if (rc) return rc;
     if (!x || !y || rows < 1) { set_error("train_step_host: bad arguments"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
-    const int prec = resolve_precision(d->precision);
+    const int prec = effective_precision(c, resolve_precision(d->precision), rows);
     const int n = c->layers[0], K = c->layers.back();
     if (rows > c->caps) {
         cudaFree(c->Xs); cudaFree(c->Ys); c->Xs = c->Ys = nullptr;
@@ -1662,9 +1676,9 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
     if (n_plus_1 != c->layers[0] + 1 || k != c->layers.back()) { set_error("data shape does not match the layers"); return B2NN_ERR_ARG; }
     if (d->batch_num < 1 || int64_t(d->batch_num) > m) { set_error("batch_num must be in [1, m]"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
-    const int prec = resolve_precision(d->precision);
     const int n = n_plus_1 - 1, nb = d->batch_num;
     const int64_t bs = m / nb, last_rows = m - int64_t(nb - 1) * bs;
+    const int prec = effective_precision(c, resolve_precision(d->precision), last_rows);
     const int64_t steps = int64_t(d->iters) * nb;
 
     if (!c->copy_stream) B2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -1793,7 +1807,7 @@ static int evaluate_impl(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, 
     if (!x || !y || rows < 1) { set_error("evaluate: bad arguments"); return B2NN_ERR_ARG; }
     if (normalise && c->norm_n != c->layers[0]) { set_error("evaluate_raw: no normalisation statistics (b2nn_set_train_data_raw / b2nn_set_normalisation first)"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
-    const int prec = resolve_precision(d->precision);
+    const int prec = effective_precision(c, resolve_precision(d->precision), rows);
     const int n = c->layers[0], K = c->layers.back();
     const int64_t ld = round_up(rows, 32);
     DevBuf xbuf, ybuf, labbuf;
@@ -1858,7 +1872,7 @@ static int predict_impl(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, i
     if (!x || !out || rows < 1) { set_error("predict: bad arguments"); return B2NN_ERR_ARG; }
     if (normalise && c->norm_n != c->layers[0]) { set_error("predict_raw: no normalisation statistics (b2nn_set_train_data_raw / b2nn_set_normalisation first)"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
-    const int prec = resolve_precision(d->precision);
+    const int prec = effective_precision(c, resolve_precision(d->precision), rows);
     const int n = c->layers[0], K = c->layers.back();
     // ~48 MB of input per chunk: long enough for the full PCIe rate, short enough that the pipeline fills quickly
     int64_t chunk = std::min<int64_t>(int64_t(1) << 17, std::max<int64_t>(1024, ((int64_t(48) << 20) / (4 * int64_t(n))) / 32 * 32));
@@ -1963,7 +1977,7 @@ int b2nn_predict_device(b2nn_ctx* c, const b2nn_train_desc* d, const float* x_de
     if (rc) return rc;
     if (!x_dev || !out_dev || rows < 1 || ld < rows) { set_error("predict_device: bad arguments"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
-    const int prec = resolve_precision(d->precision);
+    const int prec = effective_precision(c, resolve_precision(d->precision), rows);
     // x_dev is already in ENGINE layout: (l_0+1) rows of ld floats, ones row last.
     if (d->classify) return evaluate_device(c, d, prec, x_dev, ld, nullptr, 0, nullptr, rows, out_dev, nullptr, 0, nullptr, nullptr);
     return evaluate_device(c, d, prec, x_dev, ld, nullptr, 0, nullptr, rows, nullptr, out_dev, ld, nullptr, nullptr);

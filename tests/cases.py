@@ -124,7 +124,20 @@ def extra_cases() -> list:
                        "parallel: layer 0 splits into 256-row tiles per rank, the output layer goes through slot buffers")]
 
 
+@functools.lru_cache(maxsize=1)
+def c4_mini() -> Case:
+    """Scaled-down config C4 (784 - 8 x 8192 - 10): nine weight layers, widths chosen so that with 2, 4 and 8 ranks some
+    layers split into whole 256-column tiles per rank (fused peer-memory exchange inside the gradient GEMM) and others
+    do not (slot buffers); 4096-row batches keep every rank's contractions on the tcgen05 path up to 8 ranks."""
+    layers = [64, 512, 256, 1024, 512, 2048, 256, 512, 1024, 10]
+    x, y = _clf_blobs(8192, 64, 10, seed=13)
+    return Case("c4_mini", layers, x, y, True, TANH, OUT_SOFTMAX, COST_CROSSENTROPY, batch_num=2, iters=2, display=1,
+                rate=0.02, init_kind=2, seed=5, notes="config C4 in miniature: 9 weight layers, data-parallel schedule")
+
+
 def case_by_name(name: str) -> Case:
+    if name == "c4_mini":
+        return c4_mini()
     for c in small_cases() + extra_cases():
         if c.name == name:
             return c

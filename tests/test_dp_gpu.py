@@ -1,6 +1,8 @@
-"""Data-parallel engine parity on real GPUs (needs >= 2; skipped otherwise): a 2-rank run, each rank holding its row
-slice of every batch with gradients all-reduced by NCCL inside the engine, must walk the same trajectory as one GPU
-training on the whole batches.  Summation order differs, so this is a tolerance check."""
+"""Data-parallel engine parity on real GPUs (needs >= 2; skipped otherwise): a W-rank run (W = 2, 4, 8), each rank
+holding its row slice of every batch with the weight gradients exchanged inside the engine (NCCL all-reduce, or the fused
+peer-memory reduce-scatter / update / all-gather), must walk the same trajectory as one GPU training on the whole
+batches and leave bit-identical replicas.  Summation order differs, so rank-vs-single is a tolerance check."""
+import ctypes
 import importlib.util
 import os
 import sys
@@ -11,9 +13,22 @@ import pytest
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PREC = {"fp32": 0, "tf32": 1, "tf32x3": 3}
 
 
-def _worker(rank, world, port, name, prec_name, p2p, q):
+def _make_desc(b2nn, cases, c, prec, custom_act=False):
+    d = b2nn.make_desc(momentum=c.momentum, rate=c.rate, iters=c.iters, display=c.display, batch_num=c.batch_num,
+                       classify=c.classify, act=b2nn.ACT_TANH if c.hidden_act == cases.TANH else b2nn.ACT_SIGMOID,
+                       out=b2nn.OUT_SOFTMAX, cost=b2nn.COST_CROSSENTROPY, precision=PREC[prec])
+    if custom_act:      # the library's own exported ops fed back as "unknown" user pointers: the generic unfused path
+        tanh_case = c.hidden_act == cases.TANH
+        d.act_kind = b2nn.ACT_CUSTOM
+        d.act_fn = ctypes.cast(getattr(b2nn.lib(), "_Z7tanhGPUPKfPfi" if tanh_case else "_Z10sigmoidGPUPKfPfi"), ctypes.c_void_p).value
+        d.act_grad_fn = ctypes.cast(getattr(b2nn.lib(), "_Z9sechSqGPUPKfPfi" if tanh_case else "_Z14sigmoidGradGPUPKfPfi"), ctypes.c_void_p).value
+    return d
+
+
+def _worker(rank, world, port, name, prec_name, p2p, custom_act, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -37,11 +52,7 @@ def _worker(rank, world, port, name, prec_name, p2p, q):
             assert dp.enable_peer_exchange(net, rank, world)
         xl, yl, ml = dp.shard_training_set(x_cm, y_cm, c.m, n1, K, c.batch_num, rank, world)
         net.set_train_data(xl, yl, ml)
-        d = b2nn.make_desc(momentum=c.momentum, rate=c.rate, iters=c.iters, display=c.display, batch_num=c.batch_num,
-                           classify=c.classify, act=b2nn.ACT_TANH if c.hidden_act == cases.TANH else b2nn.ACT_SIGMOID,
-                           out=b2nn.OUT_SOFTMAX, cost=b2nn.COST_CROSSENTROPY,
-                           precision=b2nn.PREC_TF32 if prec_name == "tf32" else b2nn.PREC_FP32)
-        out = net.train(d)
+        out = net.train(_make_desc(b2nn, cases, c, prec_name, custom_act))
         th = net.get_weights()
         net.comm_barrier()
         q.put((rank, th, out.log_J, out.final_cost, out.error_count, out.kernel_launches))
@@ -50,43 +61,73 @@ def _worker(rank, world, port, name, prec_name, p2p, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,prec,p2p", [("clf_tanh_softmax", "fp32", False), ("wide_mini", "fp32", False),
-                                           ("wide_mini", "tf32", False), ("wide_mini", "tf32", True),
-                                           ("wide1024_skinny", "tf32", True), ("wide1024_skinny", "tf32", False)])
-def test_two_gpu_run_matches_single_gpu(b2nn, name, prec, p2p):
-    """p2p = True: the first layer's gradient (512 rows = 2 ranks x 256-column tiles) takes the fused peer-memory path
-    (reduce-scatter in the GEMM epilogue, update + all-gather on the owner); the others stay on NCCL."""
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def _run_world(world, name, prec, p2p, custom_act=False):
     import torch.multiprocessing as mp
-    import cases
-    c = cases.case_by_name(name)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 300)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, prec, p2p, q)) for r in range(2)]
+    port = 29600 + (os.getpid() % 300) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, prec, p2p, custom_act, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    # single-GPU reference run of the same global problem
+    return res
+
+
+def _single(b2nn, name, prec):
+    import cases
+    c = cases.case_by_name(name)
     net = b2nn.Net(0)
     net.set_layers(c.layers, c.init_kind, c.seed)
     x_cm, y_cm = cases.oracle_inputs(c)
     net.set_train_data(x_cm, y_cm, c.m)
-    d = b2nn.make_desc(momentum=c.momentum, rate=c.rate, iters=c.iters, display=c.display, batch_num=c.batch_num,
-                       classify=c.classify, act=b2nn.ACT_TANH if c.hidden_act == cases.TANH else b2nn.ACT_SIGMOID,
-                       out=b2nn.OUT_SOFTMAX, cost=b2nn.COST_CROSSENTROPY,
-                       precision=b2nn.PREC_TF32 if prec == "tf32" else b2nn.PREC_FP32)
-    one = net.train(d)
+    one = net.train(_make_desc(b2nn, cases, c, prec))
     th1 = net.get_weights()
     net.close()
-    tol = 2e-4 if prec == "fp32" else 2e-2
-    assert np.array_equal(res[0][1], res[1][1]), "replicas diverged: every rank must hold identical weights"
+    return c, one, th1
+
+
+def _check(res, c, one, th1, prec):
+    tol = 2e-2 if prec == "tf32" else 2e-4
+    for r in res[1:]:
+        assert np.array_equal(res[0][1], r[1]), "replicas diverged: every rank must hold identical weights"
     assert np.abs(res[0][1] - th1).max() <= tol * np.abs(th1).max()
     for r in res:
         np.testing.assert_allclose(r[2], one.log_J, rtol=tol)          # printed cost = GLOBAL batch-0 cost on every rank
         assert abs(r[3] - one.final_cost) <= tol * abs(one.final_cost) + 1e-7
         assert abs(r[4] - one.error_count) <= max(1.0, 0.005 * c.m)
+
+
+@pytest.mark.parametrize("name,prec,p2p", [("clf_tanh_softmax", "fp32", False), ("wide_mini", "fp32", False),
+                                           ("wide_mini", "tf32", False), ("wide_mini", "tf32", True),
+                                           ("wide_mini", "tf32x3", False), ("wide_mini", "tf32x3", True),
+                                           ("wide1024_skinny", "tf32", True), ("wide1024_skinny", "tf32", False)])
+def test_two_gpu_run_matches_single_gpu(b2nn, name, prec, p2p):
+    """p2p = True: the first layer's gradient (512 rows = 2 ranks x 256-column tiles) takes the fused peer-memory path
+    (reduce-scatter in the GEMM epilogue, update + all-gather on the owner); narrow layers go through slot buffers."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    c, one, th1 = _single(b2nn, name, prec)
+    _check(_run_world(2, name, prec, p2p), c, one, th1, prec)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("prec,p2p", [("tf32", True), ("tf32", False), ("tf32x3", True)])
+def test_c4_mini_ranks_match_single_gpu(b2nn, world, prec, p2p):
+    """Config C4 in miniature (nine weight layers): the per-layer flag schedule of the peer-memory exchange with a mix
+    of fused layers (rows split into 256-column tiles per rank) and slot-buffer layers, at 2, 4 and 8 ranks."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    c, one, th1 = _single(b2nn, "c4_mini", prec)
+    _check(_run_world(world, "c4_mini", prec, p2p), c, one, th1, prec)
+
+
+def test_custom_activation_under_peer_exchange(b2nn):
+    """User activation pointers with the peer-memory exchange open: the delta backprop runs BEFORE the gradient GEMM in
+    that mode and must still apply the user's derivative (round-1 advisor finding)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    c, one, th1 = _single(b2nn, "wide_mini", "fp32")
+    _check(_run_world(2, "wide_mini", "fp32", True, custom_act=True), c, one, th1, "fp32")

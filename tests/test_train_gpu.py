@@ -432,3 +432,28 @@ def test_function_pointer_path_matches_fused_builtins(b2nn, name, which):
     np.testing.assert_allclose(probs, wprobs, rtol=1e-4, atol=1e-6)
     assert (got != want).mean() <= 0.005
     net.close(); net2.close()
+
+
+@pytest.fixture(scope="module")
+def c4_mini_oracle(oracle):
+    """fp64 oracle run of the nine-weight-layer C4 miniature (about 20 s of CPU), shared by the three precision cases."""
+    c = cases.case_by_name("c4_mini")
+    th0 = oracle.init_weights(c.layers, c.init_kind, c.seed)
+    return c, th0, _oracle(oracle, c, th0, "f64")
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "tf32x3"])
+def test_c4_mini_nine_layers_match_oracle(b2nn, c4_mini_oracle, prec):
+    """Config C4's depth (8 hidden layers, cublasNN.cpp:642-685 walks them in a loop) at a size the oracle finishes:
+    every layer of the forward / delta-backprop / gradient chain against fp64."""
+    c, th0, ref64 = c4_mini_oracle
+    net, th0_engine, th, out = _engine(b2nn, c, prec)
+    assert np.array_equal(th0_engine, th0)
+    tol = TOL[prec]
+    assert np.abs(th - ref64.theta).max() <= tol["theta"] * np.abs(ref64.theta).max()
+    np.testing.assert_allclose(out.log_J, ref64.log_J, rtol=tol["J"])
+    assert abs(out.final_cost - ref64.final_cost) <= tol["J"] * abs(ref64.final_cost)
+    assert abs(out.error_count - ref64.error_count) <= max(1.0, 0.005 * c.m)
+    if prec != "fp32":
+        assert out.gemm_tc_launches >= 2 * 8 * out.steps, "the wide layers must run on the tcgen05 kernel"
+    net.close()
