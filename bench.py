@@ -684,17 +684,14 @@ def cpu_baseline(layers, sample_B, target_seconds=12.0):
 
 # ---- reference arm --------------------------------------------------------------------------------------------------------
 
-def _ref_step_seconds(O, layers, x_rows, y_rows, nb, it_short, it_long, repeats=2, **kw):
-    """The class only reports the time of a whole train*Momentum call (setup + loop + final cost, cublasNN.cpp:586-639):
-    per-step time = difference of two calls that differ only in the number of epochs, best of `repeats` pairs."""
+def _ref_step_seconds(O, layers, x_rows, y_rows, nb, it_short, it_long, repeats=3, **kw):
+    """The class only reports the time of a whole train*Momentum call (allocVarGPU + splitData + loop + calcFinalCost,
+    cublasNN.cpp:586-639): per-step time = difference of two calls that differ only in the number of epochs.  Setup time
+    jitters by more than a short loop lasts, so each of the two is the MINIMUM over `repeats` calls (positive noise only)."""
     O.ref_train(layers, x_rows, y_rows, iters=it_short, batch_num=nb, **kw)                    # warm-up call (also warms cuBLAS)
-    best = None
-    for _ in range(repeats):
-        t_short = O.ref_train(layers, x_rows, y_rows, iters=it_short, batch_num=nb, **kw).seconds
-        t_long = O.ref_train(layers, x_rows, y_rows, iters=it_long, batch_num=nb, **kw).seconds
-        dt = max(t_long - t_short, 1e-9) / ((it_long - it_short) * nb)
-        best = dt if best is None else min(best, dt)
-    return best
+    t_short = min(O.ref_train(layers, x_rows, y_rows, iters=it_short, batch_num=nb, **kw).seconds for _ in range(repeats))
+    t_long = min(O.ref_train(layers, x_rows, y_rows, iters=it_long, batch_num=nb, **kw).seconds for _ in range(repeats))
+    return max(t_long - t_short, 1e-9) / ((it_long - it_short) * nb)
 
 
 def run_reference(args):
@@ -739,7 +736,7 @@ def run_reference(args):
         try:        # C2 (main.cpp:54-96)
             cases = _load_cases()
             b = cases.bikeshare()
-            t = _ref_step_seconds(O, C2_LAYERS, cases.zscore(b["x"]), b["y"], 1, 300, 2300,
+            t = _ref_step_seconds(O, C2_LAYERS, cases.zscore(b["x"]), b["y"], 1, 500, 4500,
                                   **dict(kw, rate=0.003, hidden_act=O.SIGMOID, classify=False, init_kind=1))
             secondary["c2"] = {"us_per_step": round(t * 1e6, 2), "samples_per_s": round(b["x"].shape[0] / t)}
         except Exception as ex:  # noqa: BLE001
@@ -748,7 +745,7 @@ def run_reference(args):
             l4, B4, _ = WORKLOADS["c4"]
             x4, _y4, lab4 = synth_batches(l4, B4, 2, seed=3, rank=0)
             t = _ref_step_seconds(O, l4, np.ascontiguousarray(x4[1:].numpy().T), lab4.numpy().astype(np.float32).reshape(-1, 1),
-                                  2, 1, 2, repeats=1, **kw)
+                                  2, 1, 3, repeats=2, **kw)
             secondary["c4"] = {"ms_per_step": round(t * 1e3, 3), "samples_per_s": round(B4 / t), "batch": B4,
                                "tflops": round(step_flops(l4, B4) / t / 1e12, 1),
                                "note": "single GPU, 8192 rows: the reference is single-GPU and its int arena sizes overflow at >= 32768 rows"}
@@ -779,7 +776,7 @@ def run_reference(args):
             "data": "synthetic",
             "config": {"workload": desc_text, "layers": layers, "batch_per_gpu": B, "global_batch": B,
                        "parallelism": "dp1 (the reference is single-GPU: it runs on cuda:0 whatever --gpus says, see gpus_used)", "math": env_note,
-                       "timing": "difference of two trainClassifyMomentum calls (epochs E and E+K/nb): setup and final cost cancel; best of 2 pairs"},
+                       "timing": "difference of two trainClassifyMomentum calls (epochs E and E+K/nb): setup and final cost cancel; each the minimum of 3 calls"},
             "tflops": round(step_flops(layers, B) * K / secs / 1e12, 2),
             "cpu_baseline": {"value": round(value, 1), "unit": "samples/s", "cores": 0, "kind": "reference",
                              "sample": "unmodified reference built from /root/reference (oracle/_ref), its cuBLAS path on cuda:0; the reference has no CPU path"},

@@ -522,7 +522,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
             if (!g.g.A_lo) g.g.B_lo = nullptr;
         }
         // Peer-memory exchange: the layer's rows split evenly over the ranks in whole 256-column tiles of the gradient GEMM
-        const bool want_fused = c->p2p && prec == B2NN_PREC_TF32 && !custom && !tail_layer && nw <= P2P_MAX_LAYERS &&
+        const bool want_fused = c->p2p && (prec == B2NN_PREC_TF32 || x3) && !custom && !tail_layer && nw <= P2P_MAX_LAYERS &&
                                 li.out % (256 * c->nranks) == 0;
         if (want_fused) {
             for (int o = 0; o < c->nranks; ++o) g.g.scatter_base[o] = c->peers.G[o] + li.w_off;
@@ -533,7 +533,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         } else if (!(tail_layer && sp.tail_inline_g)) bind_backend(c, g, prec, true);
         // ... layers whose rows do not split into whole tiles per rank (the 10-unit output layer) exchange through slot
         // buffers in peer memory instead of NCCL: no foreign kernel competes with the persistent GEMMs for SMs
-        if (c->p2p && !sp.fused[j] && !custom && prec != B2NN_PREC_TF32X3 && nw <= P2P_MAX_LAYERS &&
+        if (c->p2p && !sp.fused[j] && !custom && (prec != B2NN_PREC_TF32X3 || x3) && nw <= P2P_MAX_LAYERS &&
             j < int(c->p2p_small_off.size()) && c->p2p_small_off[j] >= 0 && c->p2p_small_cnt[j] == li.ldw * li.out) sp.fused[j] = 2;
 
         // delta backprop  delta_{j-1} = (delta_j W_j)[:, no bias] .* f'(z_{j-1})   (cublasNN.cpp:673-676)
@@ -816,6 +816,9 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
             for (size_t j = 0; j < sp.fused.size(); ++j) if (sp.fused[j]) mask |= uint64_t(1) << j;
             B2_CUDA(p2p_gate_layers_launch(c->p2p_flags + 1 * P2P_MAX_LAYERS * P2P_MAX_WORLD, mask, c->nranks, c->p2p_step - 1, c->stream));
         }
+        // fp32-grade mode: the owners' kernels store new weight rows only; their low parts are re-derived here, once the
+        // gate above has seen every owner's rows of the previous step land (one streaming pass, 8 B per weight)
+        if (prec == B2NN_PREC_TF32X3 && c->W_lo) { int rl = ensure_w_lo(c); if (rl) return rl; }
     }
     int rc = B2NN_OK;
     const bool micro = sp.micro && !custom_oc && !c->comm;
@@ -881,6 +884,7 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
         if (any_fused) {
             B2_CUDA(cudaEventRecord(c->p2p_upd_done, c->upd_stream));
             B2_CUDA(cudaStreamWaitEvent(c->stream, c->p2p_upd_done, 0));
+            c->w_lo_valid = false;      // weights changed behind the low-part arena's back (refreshed after the next gate)
         }
         for (int j = nw - 1; j >= 0; --j) {
             const LayerInfo& li = c->L[j];

@@ -69,20 +69,25 @@ struct TcArgs {
     int a_3d, b_3d;                 // MN-major operand fetched with one 3-D TMA box per tile
     float* scatter_base[8];         // fused reduce-scatter: owner arenas (peer mappings); see GemmDesc
     int scatter_world, scatter_rank, scatter_rows;
+    int n_rot;                      // scatter mode: column-tile rotation, so every rank starts with a different owner's tiles
 };
 
 // Work item -> output tile.  Tiles are walked in groups of `group_m` row-tiles: inside a group the row-tile index is
 // fastest, then the column-tile index, so the ~148 tiles in flight at any time touch about group_m panels of A and
 // 148 / group_m panels of B.  group_m = 1 sweeps all column tiles of one row-tile first (B stays L2 resident when it is
 // the small operand, e.g. the weights in forward / backprop); large group_m approaches row-fastest order.
-__device__ __forceinline__ void decode_tile(int rem, int tiles_m, int tiles_n, int group_m, int& tile_m, int& tile_n) {
+// n_rot (fused reduce-scatter): the column-tile index is rotated by (rank + 1) owners' worth of tiles, so at any moment
+// the ranks are storing to DIFFERENT owners (no incast on one GPU's NVLink ingress) and each rank's own tiles — plain
+// local stores — come last, where the epilogue of the final wave is no longer hidden behind MMAs.
+__device__ __forceinline__ void decode_tile(int rem, int tiles_m, int tiles_n, int group_m, int n_rot, int& tile_m, int& tile_n) {
     const int per_group = group_m * tiles_n;
     const int g = rem / per_group;
     const int first_m = g * group_m;
     const int gsize = min(group_m, tiles_m - first_m);
     const int in_g = rem - g * per_group;
     tile_m = first_m + in_g % gsize;
-    tile_n = in_g / gsize;
+    tile_n = in_g / gsize + n_rot;
+    if (tile_n >= tiles_n) tile_n -= tiles_n;
 }
 
 // Fast forms for the tensor-core epilogue (tf32 mode): MUFU.EX2 + MUFU.RCP, relative error ~1e-6 — three orders below
@@ -160,7 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t ph = 0;
         for (int w = worker; w < total_work; w += n_workers) {
             const int split = w / tiles_mn, rem = w - split * tiles_mn;
-            int tile_m, tile_n; decode_tile(rem, p.tiles_m, p.tiles_n, p.group_m, tile_m, tile_n);
+            int tile_m, tile_n; decode_tile(rem, p.tiles_m, p.tiles_n, p.group_m, p.n_rot, tile_m, tile_n);
             const int m0 = (tile_m * NCTA + int(rank)) * BM;          // this CTA's 128 rows of A
             const int n0 = tile_n * BN + int(rank) * B_ROWS;          // this CTA's share of B
             const int kb0 = split * p.k_blocks;
@@ -288,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int t = 0;
         for (int w = worker; w < total_work; w += n_workers, ++t) {
             const int split = w / tiles_mn, rem = w - split * tiles_mn;
-            int tile_m, tile_n; decode_tile(rem, p.tiles_m, p.tiles_n, p.group_m, tile_m, tile_n);
+            int tile_m, tile_n; decode_tile(rem, p.tiles_m, p.tiles_n, p.group_m, p.n_rot, tile_m, tile_n);
             const int m = (tile_m * NCTA + int(rank)) * BM + q * 32 + lane;
             const int n0 = tile_n * BN;
             const bool m_ok = m < p.M;
@@ -587,7 +592,7 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& gu, std::string& err) {
     if (g.b_major && bn < 64) ncta = 1;    // a CTA of a pair must stage whole 32-float atoms of B
     // 3xTF32 stages four tiles per k-block: 128 x 128 alone (3 stages), 256 x 256 as a pair (3 stages)
     if (plan.x3 && ncta == 1 && bn > 128) bn = 128;
-    if (g.scatter_world > 0 && (g.scatter_rows % bn != 0 || plan.x3)) { err = "scatter rows not a multiple of the tile"; return false; }
+    if (g.scatter_world > 0 && g.scatter_rows % bn != 0) { err = "scatter rows not a multiple of the tile"; return false; }
     plan.block_n = bn;
     plan.g = gu;
     plan.ncta = ncta;
@@ -660,6 +665,9 @@ cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream) {
     a.D_lo = pl.x3 ? g.D_lo : nullptr;
     for (int i = 0; i < 8; ++i) a.scatter_base[i] = g.scatter_base[i];
     a.scatter_world = g.scatter_world; a.scatter_rank = g.scatter_rank; a.scatter_rows = g.scatter_rows;
+    a.n_rot = 0;
+    if (g.scatter_world > 1 && !std::getenv("B2NN_TC_NO_ROT"))
+        a.n_rot = (((g.scatter_rank + 1) % g.scatter_world) * (g.scatter_rows / pl.block_n)) % pl.tiles_n;
     a.M = g.M; a.N = g.N; a.d_trans = g.d_trans ? 1 : 0;
     a.tiles_m = pl.tiles_m; a.tiles_n = pl.tiles_n; a.splits = pl.splits;
     {

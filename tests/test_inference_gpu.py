@@ -13,9 +13,10 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 PREC = {"fp32": 0, "tf32": 1, "tf32x3": 3}
-# max |p - p64| on the class probabilities of the 784-50-10 net (|z| ~ 1.4): fp32-grade modes differ from the fp64
-# oracle by fp32 rounding only; tf32 truncates both operands of 785-long dot products to 10 mantissa bits.
-PROB_ATOL = {"fp32": 2e-5, "tf32x3": 2e-5, "tf32": 5e-3}
+# max |p - p64| on the class probabilities of the 784-50-10 net with 3x Glorot weights (|z| up to ~15): fp32-grade modes
+# differ from the fp64 oracle by fp32 rounding of 785-long sums only (observed <= 2.5e-5 over 655 370 probabilities); tf32
+# truncates both operands to 10 mantissa bits — a hundred times looser.
+PROB_ATOL = {"fp32": 5e-5, "tf32x3": 5e-5, "tf32": 5e-3}
 MNIST_NET = [784, 50, 10]
 
 
