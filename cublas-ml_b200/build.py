@@ -22,7 +22,7 @@ CUDA = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA, "bin", "nvcc")
 CXX = "/usr/bin/g++"
 
-CU_SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "elementwise.cu", "tail.cu", "skinny.cu", "micro.cu", "p2p.cu", "builtins.cu"]
+CU_SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "elementwise.cu", "tail.cu", "skinny.cu", "micro.cu", "mlp3.cu", "p2p.cu", "builtins.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-Wall", "-ccbin", CXX, "-I", os.path.join(ROOT, "include")]
 

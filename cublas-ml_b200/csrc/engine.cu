@@ -61,10 +61,12 @@ struct StepPlan {
     std::vector<GemmOp> wgrad;   // L-1 entries
     std::vector<GemmOp> bwd;     // entry j computes delta_{j-1} from delta_j (index 0 unused)
     std::vector<char> fused;     // data parallel over peer memory: layer's gradient is scattered to its owners by the GEMM
+    std::vector<char> fwd_waits; // ... and its forward tcgen05 kernel waits for the owners' weight rows itself (no gate launch)
     bool use_tail = false;       // skinny last layer: forward + output + delta backprop fused in tail.cu
     bool tail_inline_g = false;  // ... and its weight gradient too
     bool skinny_bwd = false;     // narrow last layer behind a wide hidden layer: delta backprop + gradient in one pass (skinny.cu)
     bool micro = false;          // the whole net fits shared memory: forward + backward + gradients in one kernel (micro.cu)
+    bool mlp3 = false;           // one hidden layer (config C1): X tile resident in shared memory, whole step in one kernel (mlp3.cu)
     MicroArgs micro_args{};
 };
 
@@ -175,6 +177,8 @@ struct b2nn_ctx {
     // while they are staged (b2nn_set_train_data_raw, b2nn_evaluate_raw, b2nn_predict_raw)
     float* d_mean = nullptr; float* d_std = nullptr; int norm_n = 0;
 
+    float* m3_partial = nullptr; int64_t m3_partial_cap = 0;    // per-block partial gradients of the one-hidden-layer kernel (mlp3.cu)
+
     Workspace ws;
     std::map<std::pair<int64_t, const float*>, StepPlan> plans;   // keyed by (rows, X base); valid for the (ws, ldx, precision, ...) below
     int plans_prec = -1;
@@ -195,6 +199,7 @@ struct b2nn_ctx {
     P2pPeers peers{};
     int* p2p_flags = nullptr;                 // local flag block: [kind][layer][rank], kind 0 = wg_done, 1 = w_done
     int p2p_step = 0;
+    std::vector<int> grad_order;              // layers in the order this step produced their gradients
     bool g_zero = false;                      // the whole gradient arena is known to be zero (small nets: the update leaves it so)
     std::vector<int64_t> p2p_small_off;       // per layer: float offset of its slot block in the small-layer area, -1 = none
     int64_t p2p_small_floats = 0;
@@ -205,6 +210,10 @@ struct b2nn_ctx {
     std::vector<void*> p2p_opened;
 
     int64_t launches = 0, tc_launches = 0;
+
+    // B2NN_TRACE=1: CUDA-event timeline of the last steps of a train call (both streams), printed to stderr when it ends
+    bool trace = false; int64_t trace_step = 0, trace_from = 0;
+    std::vector<std::pair<std::string, cudaEvent_t>> trace_ev;
 
     // optional per-launch CUDA-event timing (b2nn_profile_*): kind 0 forward, 1 delta backprop, 2 weight gradient,
     // 3 output layer, 4 momentum update
@@ -434,6 +443,12 @@ void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
     }
 }
 
+// One-hidden-layer nets in a tensor-core mode on a single GPU with built-in functions take the one-kernel step (mlp3.cu).
+bool mlp3_ok(const b2nn_ctx* c, int prec, int act_kind) {
+    return c->L.size() == 2 && !c->comm && act_kind != B2NN_ACT_CUSTOM && (prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3) &&
+           c->total_int > 16384 && (c->total_int & 3) == 0 && mlp3_supported(c->L[0].in + 1, c->L[0].out, c->L[1].out);
+}
+
 // x_total: number of sample columns of X that hold data.  The tensor maps over X span all of them so one plan serves
 // every batch of the same size; the batch start only moves the TMA coordinates (run_gemm).
 // x_aligned: every batch start passed to run_gemm is a multiple of 32 samples (one 3-D TMA box per X tile).
@@ -459,6 +474,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
     const float* X_lo = x3 ? find_lo(c, X) : nullptr;
     sp.fwd.resize(nw); sp.wgrad.resize(nw); sp.bwd.resize(nw);
     sp.fused.assign(nw, 0);
+    sp.fwd_waits.assign(nw, 0);
     {
         const LayerInfo& last = c->L[nw - 1];
         const bool no_tail = no_tail_arg || std::getenv("B2NN_NO_TAIL") != nullptr;
@@ -480,6 +496,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
             m.act_total = off; m.max_width = width; m.act_kind = act_kind;
             sp.micro = micro_supported(m);
         }
+        sp.mlp3 = !no_tail && !sp.micro && mlp3_ok(c, prec, act_kind);
     }
     for (int j = 0; j < nw; ++j) {
         const LayerInfo& li = c->L[j];
@@ -535,6 +552,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         // buffers in peer memory instead of NCCL: no foreign kernel competes with the persistent GEMMs for SMs
         if (c->p2p && !sp.fused[j] && !custom && (prec != B2NN_PREC_TF32X3 || x3) && nw <= P2P_MAX_LAYERS &&
             j < int(c->p2p_small_off.size()) && c->p2p_small_off[j] >= 0 && c->p2p_small_cnt[j] == li.ldw * li.out) sp.fused[j] = 2;
+        sp.fwd_waits[j] = sp.fused[j] == 1 && f.tc && prec == B2NN_PREC_TF32 && !tail_layer && !std::getenv("B2NN_P2P_GATE_KERNEL");
 
         // delta backprop  delta_{j-1} = (delta_j W_j)[:, no bias] .* f'(z_{j-1})   (cublasNN.cpp:673-676)
         if (j > 0) {
@@ -551,6 +569,29 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         }
     }
     return sp;
+}
+
+void trace_mark(b2nn_ctx* c, const char* name, int layer, cudaStream_t s) {
+    if (!c->trace || c->trace_step < c->trace_from) return;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    c->trace_ev.emplace_back(std::string(name) + (layer >= 0 ? std::to_string(layer) : "") + "@" + std::to_string(c->trace_step), e);
+}
+void trace_dump(b2nn_ctx* c) {
+    if (c->trace_ev.empty()) return;
+    cudaDeviceSynchronize();
+    std::string out = "[b2nn trace rank " + std::to_string(c->rank) + "] us since first mark:";
+    for (auto& kv : c->trace_ev) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->trace_ev.front().second, kv.second);
+        char buf[96];
+        std::snprintf(buf, sizeof(buf), " %s=%.1f", kv.first.c_str(), ms * 1e3f);
+        out += buf;
+    }
+    std::fprintf(stderr, "%s\n", out.c_str());
+    for (auto& kv : c->trace_ev) cudaEventDestroy(kv.second);
+    c->trace_ev.clear();
 }
 
 cudaEvent_t prof_event(b2nn_ctx* c) {
@@ -573,7 +614,7 @@ struct ProfScope {
     ~ProfScope() { if (on) { cudaEventRecord(c->prof.back().e1, c->stream); c->prof_chain = true; } }
 };
 
-int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind) {
+int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind, const TcWait* wait = nullptr) {
     ProfScope scope(c, kind, op.tc, 2.0 * double(op.g.M) * double(op.g.N) * double(op.g.K), 0.0);
     const bool d_is_grad = op.g.D >= c->G && op.g.D < c->G + c->total_int;
     if (op.zero_first && !(d_is_grad && c->g_zero))
@@ -582,9 +623,9 @@ int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind) {
         if (op.a_is_x && x_start != 0) {
             TcPlan shifted = op.plan;   // tensor maps span the whole training matrix; only the coordinates move
             if (op.g.a_major) shifted.g.a_mn0 += x_start; else shifted.g.a_k0 += x_start;
-            B2_CUDA(tc_plan_launch(shifted, c->stream));
+            B2_CUDA(tc_plan_launch(shifted, c->stream, wait));
         } else {
-            B2_CUDA(tc_plan_launch(op.plan, c->stream));
+            B2_CUDA(tc_plan_launch(op.plan, c->stream, wait));
         }
         ++c->tc_launches;
     } else {
@@ -599,11 +640,13 @@ int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind) {
 }
 
 // forwardPropagate (cublasNN.cpp:642-661) over rows [x_start, x_start+rows) of X; leaves z_{L-2} in ws.z_last.
-int forward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_desc* d) {
+int forward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_desc* d, int gate_step = 0) {
     const int nw = int(sp.fwd.size()) - (sp.use_tail ? 1 : 0);      // the tail kernel owns the last layer
     const bool custom = d->act_kind == B2NN_ACT_CUSTOM;
     for (int j = 0; j < nw; ++j) {
-        int rc = run_gemm(c, sp.fwd[j], x_start, 0);
+        // data parallel over peer memory: this layer's weights are complete once every owner's flag shows the previous step
+        TcWait wait{c->p2p_flags + (1 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD, c->nranks, gate_step};
+        int rc = run_gemm(c, sp.fwd[j], x_start, 0, (gate_step > 0 && sp.fwd_waits[j]) ? &wait : nullptr);
         if (rc) return rc;
         if (custom && j < int(sp.fwd.size()) - 1) {
             // User activation: a host function that launches on the legacy default stream (cublasNN.cpp:648, 655).  The
@@ -621,45 +664,13 @@ int forward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_de
 int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_desc* d) {
     const int nw = int(sp.fwd.size());
     const bool custom = d->act_kind == B2NN_ACT_CUSTOM;
-    for (int j = nw - 1; j >= 0; --j) {
-        const bool tail_layer = sp.use_tail && j == nw - 1;
-        int rc = B2NN_OK;
-        // With the peer-memory exchange an owner may overwrite W_j on this rank as soon as every rank has signalled its
-        // gradient of layer j, so the delta backprop that still reads W_j goes first.
-        const bool bwd_first = c->p2p;
-        const bool skinny = sp.skinny_bwd && j == nw - 1 && j > 0;
-        if (skinny) {
-            // narrow output layer behind a wide hidden layer: delta_{j-1} and G_j in one pass over a_{j-1} (skinny.cu)
-            const LayerInfo& li = c->L[j];
-            ProfScope scope(c, 1, false, 4.0 * double(sp.rows) * li.in * li.out, 8.0 * double(sp.rows) * li.in);
-            SkinnyArgs a{};
-            a.a = c->ws.a[j - 1]; a.delta = c->ws.delta[j]; a.W = c->W + li.w_off; a.delta_prev = c->ws.delta[j - 1];
-            a.G = c->G + li.w_off; a.ld = c->ws.ld; a.ldw = li.ldw; a.rows = sp.rows; a.H = li.in; a.K = li.out; a.act_kind = d->act_kind;
-            if (!c->g_zero) B2_CUDA(cudaMemsetAsync(a.G, 0, sizeof(float) * size_t(li.ldw) * li.out, c->stream));
-            B2_CUDA(skinny_bwd_launch(a, c->stream));
-            ++c->launches;
-            if (!c->ws.delta_lo.empty() && c->ws.delta_lo[j - 1])      // fp32-grade mode: the next contraction wants the low part too
-                B2_CUDA(split_lo_launch(c->ws.delta[j - 1], c->ws.delta_lo[j - 1], int64_t(li.in) * c->ws.ld, c->stream));
-        }
-        // user activation: sigGrad = f'(z_{j-1}) by the user's function, then delta = product .* sigGrad (cublasNN.cpp:673, 676);
-        // runs after the delta-backprop contraction wherever that sits in the order
-        auto custom_derivative = [&]() -> int {
-            if (!custom) return B2NN_OK;
-            const int64_t cnt = int64_t(c->layers[j]) * c->ws.ld;
-            if (cnt > INT32_MAX) { set_error("custom activation: element count exceeds int"); return B2NN_ERR_ARG; }
-            float* tmp = c->ws.delta[j - 1];
-            d->act_grad_fn(c->ws.z[j - 1], tmp, int(cnt));
-            B2_CUDA(multiply_launch(c->ws.scratch, tmp, tmp, cnt, c->stream));
-            ++c->launches;
-            return B2NN_OK;
-        };
-        if (!skinny && bwd_first && j > 0 && !tail_layer) {
-            rc = run_gemm(c, sp.bwd[j], 0, 1);
-            if (!rc) rc = custom_derivative();
-            if (rc) return rc;
-        }
-        if (!skinny && !(tail_layer && sp.tail_inline_g)) rc = run_gemm(c, sp.wgrad[j], x_start, 2);
-        if (rc) return rc;
+    c->grad_order.clear();
+    auto is_skinny = [&](int j) { return sp.skinny_bwd && j == nw - 1 && j > 0; };
+    auto is_tail = [&](int j) { return sp.use_tail && j == nw - 1; };
+
+    // G_j exists: hand it to the exchange (peer memory: slot copy / signal; NCCL: event for the communication stream)
+    auto post_gradient = [&](int j) -> int {
+        c->grad_order.push_back(j);
         if (sp.fused[j]) {
             if (sp.fused[j] == 2) {
                 const LayerInfo& li = c->L[j];
@@ -667,14 +678,66 @@ int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_d
                 B2_CUDA(p2p_small_scatter_launch(c->peers, c->G + li.w_off, c->p2p_small_off[j] + int64_t(c->rank) * cnt, cnt, c->stream));
                 ++c->launches;
             }
+            trace_mark(c, "wgrad_done", j, c->stream);
             B2_CUDA(p2p_signal_launch(c->peers, (0 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD + c->rank, c->p2p_step, c->stream));
             B2_CUDA(cudaEventRecord(c->p2p_wg_ev[j], c->stream));
         } else if (c->comm && !c->grad_ready.empty()) B2_CUDA(cudaEventRecord(c->grad_ready[j], c->stream));
-        if (!skinny && !bwd_first && j > 0 && !tail_layer) {
-            rc = run_gemm(c, sp.bwd[j], 0, 1);
-            if (!rc) rc = custom_derivative();
-            if (rc) return rc;
+        return B2NN_OK;
+    };
+    // delta_{j-1} from delta_j (cublasNN.cpp:673-676); the skinny kernel produces G_j in the same pass over a_{j-1}
+    auto delta_step = [&](int j) -> int {
+        if (j <= 0 || is_tail(j)) return B2NN_OK;              // the tail kernel already produced delta_{j-1}
+        if (is_skinny(j)) {
+            const LayerInfo& li = c->L[j];
+            {
+                ProfScope scope(c, 1, false, 4.0 * double(sp.rows) * li.in * li.out, 8.0 * double(sp.rows) * li.in);
+                SkinnyArgs a{};
+                a.a = c->ws.a[j - 1]; a.delta = c->ws.delta[j]; a.W = c->W + li.w_off; a.delta_prev = c->ws.delta[j - 1];
+                a.G = c->G + li.w_off; a.ld = c->ws.ld; a.ldw = li.ldw; a.rows = sp.rows; a.H = li.in; a.K = li.out; a.act_kind = d->act_kind;
+                if (!c->g_zero) B2_CUDA(cudaMemsetAsync(a.G, 0, sizeof(float) * size_t(li.ldw) * li.out, c->stream));
+                B2_CUDA(skinny_bwd_launch(a, c->stream));
+            }
+            ++c->launches;
+            if (!c->ws.delta_lo.empty() && c->ws.delta_lo[j - 1])      // fp32-grade mode: the next contraction wants the low part too
+                B2_CUDA(split_lo_launch(c->ws.delta[j - 1], c->ws.delta_lo[j - 1], int64_t(li.in) * c->ws.ld, c->stream));
+            return post_gradient(j);
         }
+        int rc = run_gemm(c, sp.bwd[j], 0, 1);
+        if (rc) return rc;
+        if (custom) {
+            // user activation: sigGrad = f'(z_{j-1}) by the user's function, then delta = product .* sigGrad (cublasNN.cpp:673, 676)
+            const int64_t cnt = int64_t(c->layers[j]) * c->ws.ld;
+            if (cnt > INT32_MAX) { set_error("custom activation: element count exceeds int"); return B2NN_ERR_ARG; }
+            float* tmp = c->ws.delta[j - 1];
+            d->act_grad_fn(c->ws.z[j - 1], tmp, int(cnt));
+            B2_CUDA(multiply_launch(c->ws.scratch, tmp, tmp, cnt, c->stream));
+            ++c->launches;
+        }
+        return B2NN_OK;
+    };
+    // G_j = delta_j^T [a_{j-1}, 1]  (cublasNN.cpp:680-684)
+    auto grad_step = [&](int j) -> int {
+        if (is_skinny(j)) return B2NN_OK;                        // produced by delta_step
+        if (!(is_tail(j) && sp.tail_inline_g)) { int rc = run_gemm(c, sp.wgrad[j], x_start, 2); if (rc) return rc; }
+        return post_gradient(j);
+    };
+
+    if (c->p2p) {
+        // Peer-memory exchange.  (1) An owner overwrites W_j on this rank as soon as EVERY rank has signalled its G_j, so
+        // the whole delta chain (which reads W_j) runs before any signal.  (2) The gradients then come input layer FIRST:
+        // the exchange of layer j hides behind the gradient GEMM of layer j+1, and the exchange of the LAST layer behind
+        // the next step's forward pass through the earlier layers (each forward contraction waits for its own layer's
+        // weights only, see forward_pass) — nothing is left exposed at the step boundary.
+        for (int j = nw - 1; j >= 1; --j) { int rc = delta_step(j); if (rc) return rc; }
+        for (int j = 0; j < nw; ++j) { int rc = grad_step(j); if (rc) return rc; }
+        return B2NN_OK;
+    }
+    // Single GPU / NCCL: G_j right after delta_j (the reference computes all deltas, then all gradients, :670-684), so its
+    // all-reduce overlaps the backprop of the earlier layers.
+    for (int j = nw - 1; j >= 0; --j) {
+        int rc = grad_step(j);
+        if (!rc) rc = delta_step(j);
+        if (rc) return rc;
     }
     return B2NN_OK;
 }
@@ -809,17 +872,25 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
     if (c->comm) c->prof_chain = false;      // waits on the exchange streams sit between steps: not part of any launch
     bool any_fused = false;
     for (char f : sp.fused) any_fused = any_fused || f;
+    ++c->trace_step;
+    trace_mark(c, "step_begin", -1, c->stream);
     if (any_fused) {
         ++c->p2p_step;
         if (c->p2p_step > 1) {     // every owner's rows of the previous step have landed in this rank's weights (and every
             uint64_t mask = 0;     // rank has consumed the small-layer slots this step will overwrite)
-            for (size_t j = 0; j < sp.fused.size(); ++j) if (sp.fused[j]) mask |= uint64_t(1) << j;
+            // Layers whose forward contraction is a tcgen05 launch wait for their own weights INSIDE that kernel (its TMA
+            // producer polls the owners' flags): the end-of-step exchange of the late layers then overlaps the forward pass
+            // through the early ones.  Everything else (slot layers, FFMA / tail consumers, the fp32-grade mode whose low
+            // parts are re-derived below) is gated here.
+            for (size_t j = 0; j < sp.fused.size(); ++j)
+                if (sp.fused[j] && !(sp.fwd_waits[j])) mask |= uint64_t(1) << j;
             B2_CUDA(p2p_gate_layers_launch(c->p2p_flags + 1 * P2P_MAX_LAYERS * P2P_MAX_WORLD, mask, c->nranks, c->p2p_step - 1, c->stream));
         }
         // fp32-grade mode: the owners' kernels store new weight rows only; their low parts are re-derived here, once the
         // gate above has seen every owner's rows of the previous step land (one streaming pass, 8 B per weight)
         if (prec == B2NN_PREC_TF32X3 && c->W_lo) { int rl = ensure_w_lo(c); if (rl) return rl; }
     }
+    trace_mark(c, "gated", -1, c->stream);
     int rc = B2NN_OK;
     const bool micro = sp.micro && !custom_oc && !c->comm;
     if (micro) {
@@ -831,9 +902,41 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
         ProfScope scope(c, 0, false, 6.0 * double(rows) * double(c->total_int), 4.0 * double(rows) * (c->layers[0] + 1));
         B2_CUDA(micro_launch(a, c->stream));
         ++c->launches;
+    } else if (sp.mlp3 && !custom_oc) {
+        // config C1's shape: forward, output, backward and both gradients in one kernel over 32-sample tiles, then one
+        // reduce + momentum-update kernel (2 launches; the reference: 15, cublasNN.cpp:597-629)
+        const int grid = mlp3_grid(rows);
+        const int64_t need = int64_t(grid) * c->total_int;
+        if (need > c->m3_partial_cap) {
+            B2_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(c->m3_partial); c->m3_partial = nullptr; c->m3_partial_cap = 0;
+            B2_CUDA(cudaMalloc(&c->m3_partial, sizeof(float) * size_t(need)));
+            c->m3_partial_cap = need;
+        }
+        Mlp3Args a{};
+        a.X = X + x_start; a.ldx = ldx; a.Y = Y + x_start; a.ldy = ldy;
+        a.W0 = c->W + c->L[0].w_off; a.ldw0 = int(c->L[0].ldw); a.W1 = c->W + c->L[1].w_off; a.ldw1 = int(c->L[1].ldw);
+        a.partial = c->m3_partial; a.total = int(c->total_int); a.w1_off = int(c->L[1].w_off);
+        a.cost_sum = cost_slot; a.rows = rows; a.n1 = c->L[0].in + 1; a.H = c->L[0].out; a.K = c->L[1].out;
+        a.act_kind = d->act_kind; a.out_kind = d->classify ? d->out_kind : B2NN_OUT_LINEAR;
+        a.cost_kind = d->classify ? d->cost_kind : B2NN_COST_SQUARED;
+        a.x3 = prec == B2NN_PREC_TF32X3 ? 1 : 0; a.train = 1;
+        {
+            ProfScope scope(c, 0, false, 6.0 * double(rows) * double(c->total_ref), 4.0 * double(rows) * (c->layers[0] + 1));
+            B2_CUDA(mlp3_launch(a, c->stream));
+        }
+        {
+            ProfScope scope(c, 4, false, 0.0, (4.0 * grid + 16.0) * double(c->total_int));
+            B2_CUDA(mlp3_reduce_update_launch(c->m3_partial, grid, c->total_int, c->W, c->V, d->momentum,
+                                              -d->rate / float(global_rows), c->stream));
+        }
+        c->launches += 2;
+        c->w_lo_valid = false;
+        return B2NN_OK;
     } else {
-    rc = forward_pass(c, sp, x_start, d);
+    rc = forward_pass(c, sp, x_start, d, (any_fused && c->p2p_step > 1) ? c->p2p_step - 1 : 0);
     if (rc) return rc;
+    trace_mark(c, "fwd_done", -1, c->stream);
     if (custom_oc) rc = output_custom(c, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
     else if (sp.use_tail) rc = run_tail(c, sp, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
     else rc = output_and_delta(c, d, Y + x_start, ldy, rows, cost_slot);
@@ -846,20 +949,23 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
     }
     rc = backward_pass(c, sp, x_start, d);
     if (rc) return rc;
+    trace_mark(c, "bwd_done", -1, c->stream);
     }
     const float alpha = -d->rate / float(global_rows);      // cublasNN.cpp:544, 601
     const int nw = int(c->L.size());
     if (c->comm) {
-        // gradient all-reduce per layer on the communication stream, issued in the order the gradients were produced
-        for (int j = nw - 1; j >= 0; --j) {
+        // gradient exchange per layer, issued in the order the gradients were produced
+        for (int j : c->grad_order) {
             const LayerInfo& li = c->L[j];
             if (sp.fused[j] == 2) {
                 // small layer: once every rank's copy sits in this rank's slots, sum them and update the local replica
                 const int64_t cnt = li.ldw * li.out;
                 B2_CUDA(cudaStreamWaitEvent(c->upd_stream, c->p2p_wg_ev[j], 0));
                 B2_CUDA(p2p_gate_launch(c->p2p_flags + (0 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD, c->nranks, c->p2p_step, c->upd_stream));
+                trace_mark(c, "U_gate", j, c->upd_stream);
                 B2_CUDA(p2p_small_reduce_update_launch(c->peers.S[c->rank] + c->p2p_small_off[j], cnt, c->nranks, c->W + li.w_off,
                                                        c->V + li.w_off, cnt, d->momentum, alpha, c->upd_stream));
+                trace_mark(c, "U_reduced", j, c->upd_stream);
                 B2_CUDA(p2p_signal_launch(c->peers, (1 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD + c->rank, c->p2p_step, c->upd_stream));
                 c->launches += 3;
                 continue;
@@ -870,7 +976,9 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
                 const int64_t R = li.out / c->nranks, slice = R * li.ldw, off = li.w_off + int64_t(c->rank) * slice;
                 B2_CUDA(cudaStreamWaitEvent(c->upd_stream, c->p2p_wg_ev[j], 0));
                 B2_CUDA(p2p_gate_launch(c->p2p_flags + (0 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD, c->nranks, c->p2p_step, c->upd_stream));
+                trace_mark(c, "U_gate", j, c->upd_stream);
                 B2_CUDA(p2p_reduce_update_launch(c->peers, c->G + li.w_off, slice, c->V + off, off, slice, d->momentum, alpha, c->upd_stream));
+                trace_mark(c, "U_reduced", j, c->upd_stream);
                 B2_CUDA(p2p_signal_launch(c->peers, (1 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD + c->rank, c->p2p_step, c->upd_stream));
                 c->launches += 3;
                 continue;
@@ -882,8 +990,13 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
             B2_CUDA(cudaEventRecord(c->grad_reduced[j], c->comm_stream));
         }
         if (any_fused) {
-            B2_CUDA(cudaEventRecord(c->p2p_upd_done, c->upd_stream));
-            B2_CUDA(cudaStreamWaitEvent(c->stream, c->p2p_upd_done, 0));
+            // No join of the two streams here: the next step orders itself against the owners' kernels (this rank's included)
+            // through the w_done flags — per layer, inside the forward kernels — so the exchange of the last layers keeps
+            // running under the next forward pass.  b2nn_train / b2nn_train_host end with a gate on every layer.
+            if (std::getenv("B2NN_P2P_SYNC_STEP")) {
+                B2_CUDA(cudaEventRecord(c->p2p_upd_done, c->upd_stream));
+                B2_CUDA(cudaStreamWaitEvent(c->stream, c->p2p_upd_done, 0));
+            }
             c->w_lo_valid = false;      // weights changed behind the low-part arena's back (refreshed after the next gate)
         }
         for (int j = nw - 1; j >= 0; --j) {
@@ -942,7 +1055,12 @@ int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float
     const int64_t chunk_cap = std::max<int64_t>(c->ws.cap, std::min<int64_t>(rows, std::max<int64_t>(1 << 16, budget_rows)));
     rc = ensure_workspace(c, chunk_cap, d->act_kind == B2NN_ACT_CUSTOM);
     if (rc) return rc;
-    if (prec == B2NN_PREC_TF32X3 && d->act_kind != B2NN_ACT_CUSTOM) {
+    // One-hidden-layer nets in the fp32-grade mode: the forward half of mlp3.cu (operands split in registers, X read once)
+    // instead of the tcgen05 path, which would first write a low-part copy of X (3x the HBM traffic of this HBM-bound pass).
+    // Plain tf32 inference keeps the tcgen05 path (B2NN_MLP3_FWD=1 forces the one-kernel forward there too).
+    const bool m3 = mlp3_ok(c, prec, d->act_kind) && !custom_outcost(d) && !std::getenv("B2NN_NO_TAIL") &&
+                    (prec == B2NN_PREC_TF32X3 || std::getenv("B2NN_MLP3_FWD") != nullptr);
+    if (prec == B2NN_PREC_TF32X3 && d->act_kind != B2NN_ACT_CUSTOM && !m3) {
         rc = prepare_x3(c, X, ldx * int64_t(c->layers[0] + 1), c->ws.cap, false);
         if (rc) return rc;
     }
@@ -952,6 +1070,21 @@ int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float
     const int cost_kind = d->classify ? d->cost_kind : B2NN_COST_SQUARED;
     for (int64_t s = 0; s < rows; s += chunk) {
         const int64_t r = std::min<int64_t>(chunk, rows - s);
+        if (m3) {
+            Mlp3Args a{};
+            a.X = X + s; a.ldx = ldx; a.Y = Y ? Y + s : nullptr; a.ldy = ldy;
+            a.W0 = c->W + c->L[0].w_off; a.ldw0 = int(c->L[0].ldw); a.W1 = c->W + c->L[1].w_off; a.ldw1 = int(c->L[1].ldw);
+            a.h_out = probs_out ? probs_out + s : nullptr; a.ldh = ldp;
+            a.pred = pred_out ? pred_out + s : nullptr; a.y_labels = labels ? labels + s : nullptr;
+            a.cost_sum = (Y && cost) ? c->d_acc : nullptr;
+            a.err_sum = (d->classify && errors && (Y || labels)) ? c->d_acc + 1 : nullptr;
+            a.rows = r; a.n1 = c->L[0].in + 1; a.H = c->L[0].out; a.K = c->L[1].out;
+            a.act_kind = d->act_kind; a.out_kind = out_kind; a.cost_kind = cost_kind;
+            a.x3 = prec == B2NN_PREC_TF32X3 ? 1 : 0; a.train = 0;
+            B2_CUDA(mlp3_launch(a, c->stream));
+            ++c->launches;
+            continue;
+        }
         // x_extent: sample columns of X the tensor maps may span (staging buffers: the whole padded buffer, so plans stay
         // valid from call to call; rows past `r` only feed accumulator rows that are never stored)
         StepPlan& sp = get_plan(c, r, X, ldx, x_extent > 0 ? x_extent : rows, true, prec, d->act_kind, custom_outcost(d));
@@ -1118,6 +1251,7 @@ void b2nn_destroy(b2nn_ctx* c) {
     cudaFree(c->X); cudaFree(c->Y); cudaFree(c->Xs); cudaFree(c->Ys); cudaFree(c->Xsp); cudaFree(c->Ysp);
     cudaFree(c->d_acc);
     cudaFree(c->d_mean); cudaFree(c->d_std);
+    cudaFree(c->m3_partial);
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->pr_x[i]); cudaFree(c->pr_p[i]); cudaFree(c->pr_h[i]);
         if (c->pr_hx[i]) cudaFreeHost(c->pr_hx[i]);
@@ -1488,6 +1622,10 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
     B2_CUDA(cudaEventCreate(&evs.a)); B2_CUDA(cudaEventCreate(&evs.b));
     cudaEvent_t const ev0 = evs.a, ev1 = evs.b;
     B2_CUDA(cudaEventRecord(ev0, c->stream));
+    c->trace = std::getenv("B2NN_TRACE") != nullptr;
+    c->trace_step = 0;
+    c->trace_from = int64_t(d->iters) * nb - 2;           // the last three steps
+    struct TraceDump { b2nn_ctx* c; ~TraceDump() { trace_dump(c); c->trace = false; } } trace_guard{c};
 
     int issued = 0, reported = 0;
     std::vector<int> slot_iter;
@@ -1582,6 +1720,7 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
     }
     B2_CUDA(cudaEventRecord(ev1, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->p2p && c->upd_stream) B2_CUDA(cudaStreamSynchronize(c->upd_stream));
     destroy_graphs();
     rc = flush_logs(true);
     if (rc) return rc;
@@ -1773,6 +1912,7 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
     }
     B2_CUDA(cudaEventRecord(ev1, c->stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->p2p && c->upd_stream) B2_CUDA(cudaStreamSynchronize(c->upd_stream));
     float ms = 0.f;
     B2_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     if (J_steps)

@@ -75,7 +75,9 @@ struct TcPlan {
 // Returns false (and sets err) when the operands violate a TMA constraint (alignment, stride) so the caller can
 // route the contraction to the FFMA kernel instead.
 bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err);
-cudaError_t tc_plan_launch(const TcPlan& plan, cudaStream_t stream);
+// Optional gate fused into the kernel: its TMA producer spins until flags[0 .. count) >= value before the first load.
+struct TcWait { const int* flags; int count; int value; };
+cudaError_t tc_plan_launch(const TcPlan& plan, cudaStream_t stream, const TcWait* wait = nullptr);
 bool tc_runtime_ok(std::string& err);      // driver entry point for cuTensorMapEncodeTiled available?
 // Persistent GEMM grids leave `n` SMs unoccupied so a concurrent NCCL kernel is never queued behind a whole GEMM.
 void tc_set_reserved_sms(int n);
@@ -169,6 +171,29 @@ struct MicroArgs {
 };
 bool micro_supported(const MicroArgs& a);
 cudaError_t micro_launch(const MicroArgs& a, cudaStream_t s);
+
+// One-hidden-layer network, whole step in one kernel (mlp3.cu).  X / Y point at the batch's first sample; `partial` holds
+// one gradient arena (internal layout, `total` floats) per block; the reduce/update kernel sums them into the update.
+struct Mlp3Args {
+    const float* X; int64_t ldx;           // (l0+1) feature rows, ones row last
+    const float* Y; int64_t ldy;           // K target rows (null: forward only without cost)
+    const float* W0; int ldw0;             // H rows of ldw0 floats
+    const float* W1; int ldw1;             // K rows of ldw1 floats
+    float* partial; int total; int w1_off; // training: [grid][total] partial gradients; w1_off = offset of layer 1 in the arena
+    float* h_out; int64_t ldh;             // activated output, K rows (may be null)
+    float* pred;                           // argmax class per row as float (may be null)
+    const float* y_labels;                 // class ids for the error count (validate path, may be null)
+    double* cost_sum; double* err_sum;     // double accumulators (may be null)
+    int64_t rows; int n1, H, K;
+    int act_kind, out_kind, cost_kind;
+    int x3;                                // fp32-grade arithmetic (hi/lo split in registers), else plain tf32
+    int train;
+};
+bool mlp3_supported(int n1, int H, int K);
+int mlp3_grid(int64_t rows);               // blocks mlp3_launch will use (= partial gradient slices)
+cudaError_t mlp3_launch(const Mlp3Args& a, cudaStream_t s);
+cudaError_t mlp3_reduce_update_launch(const float* partial, int nparts, int64_t total, float* theta, float* vel, float mu, float alpha,
+                                      cudaStream_t s);
 
 // ---- peer-memory data parallelism (p2p.cu) ---------------------------------------------------------------------------
 constexpr int P2P_MAX_WORLD = 8;

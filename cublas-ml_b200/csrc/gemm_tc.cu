@@ -70,6 +70,8 @@ struct TcArgs {
     float* scatter_base[8];         // fused reduce-scatter: owner arenas (peer mappings); see GemmDesc
     int scatter_world, scatter_rank, scatter_rows;
     int n_rot;                      // scatter mode: column-tile rotation, so every rank starts with a different owner's tiles
+    const int* wait_flags;          // data parallel over peer memory: the weights this contraction reads are complete once
+    int wait_count, wait_value;     // wait_flags[0 .. wait_count) >= wait_value (one flag per owner rank, written by the owners)
 };
 
 // Work item -> output tile.  Tiles are walked in groups of `group_m` row-tiles: inside a group the row-tile index is
@@ -159,6 +161,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
+        // Gate fused into the consumer: every owner's rows of this layer's weights (previous step's update, stored into this
+        // GPU's arena over NVLink) must have landed before the first TMA load reads them.  Lanes poll one owner flag each.
+        if (p.wait_count > 0) {
+            if (lane < p.wait_count) {
+                const long long t0 = clock64();
+                int v;
+                do {
+                    asm volatile("ld.acquire.sys.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p.wait_flags + lane) : "memory");
+                    if (v < p.wait_value && clock64() - t0 > 20000000000LL) __trap();      // a peer died: fail loudly
+                } while (v < p.wait_value);
+            }
+            __syncwarp();
+            asm volatile("fence.proxy.async;\n" ::: "memory");       // the TMA (async proxy) loads below must observe those rows
+        }
         // the whole warp walks the loop (warp-uniform control flow and operands); one elected lane issues
         const bool issuer = elect_one();
         int s = 0;
@@ -657,7 +673,7 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& gu, std::string& err) {
     return true;
 }
 
-cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream) {
+cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream, const TcWait* wait) {
     if (!pl.valid) return cudaErrorInvalidValue;
     const GemmDesc g = effective_desc(pl.g, pl.swapped);
     TcArgs a;
@@ -665,6 +681,7 @@ cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream) {
     a.D_lo = pl.x3 ? g.D_lo : nullptr;
     for (int i = 0; i < 8; ++i) a.scatter_base[i] = g.scatter_base[i];
     a.scatter_world = g.scatter_world; a.scatter_rank = g.scatter_rank; a.scatter_rows = g.scatter_rows;
+    a.wait_flags = wait ? wait->flags : nullptr; a.wait_count = wait ? wait->count : 0; a.wait_value = wait ? wait->value : 0;
     a.n_rot = 0;
     if (g.scatter_world > 1 && !std::getenv("B2NN_TC_NO_ROT"))
         a.n_rot = (((g.scatter_rank + 1) % g.scatter_world) * (g.scatter_rows / pl.block_n)) % pl.tiles_n;

@@ -51,7 +51,7 @@ __global__ void gate_layers_kernel(const int* flags, unsigned long long layer_ma
 }
 
 // Small layer, source side: this rank's whole gradient into slot `rank` of every peer (NVLink stores).
-__global__ void __launch_bounds__(256) small_scatter_kernel(P2pPeers peers, const float4* __restrict__ src, int64_t slot_off4,
+__global__ void __launch_bounds__(256, 8) small_scatter_kernel(P2pPeers peers, const float4* __restrict__ src, int64_t slot_off4,
                                                             int64_t n4) {
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -63,7 +63,10 @@ __global__ void __launch_bounds__(256) small_scatter_kernel(P2pPeers peers, cons
 
 // Small layer, every rank: g = sum of the slots in rank order (same order everywhere => replicas stay bit-identical),
 // then the momentum update of the local replica.
-__global__ void __launch_bounds__(256) small_reduce_update_kernel(const float4* __restrict__ slots, int64_t stride4, int world,
+// <= 32 registers (8 blocks / SM by the launch bound): a block then fits into the register file NEXT TO a persistent
+// tcgen05 GEMM CTA (576 threads x 96 registers leave 10 240), so the owner side of the exchange runs under the GEMMs
+// instead of waiting for one of them to retire.
+__global__ void __launch_bounds__(256, 8) small_reduce_update_kernel(const float4* __restrict__ slots, int64_t stride4, int world,
                                                                   float4* __restrict__ theta, float4* __restrict__ vel,
                                                                   int64_t n4, float mu, float alpha) {
     const int64_t step = int64_t(gridDim.x) * blockDim.x;
@@ -91,7 +94,7 @@ __global__ void signal_kernel(P2pPeers peers, int index, int value) {
 
 // Owner-side fused kernel for one layer: g = sum over sources of the partial slices, v <- mu v + alpha g,
 // theta <- theta + v, new theta stored into every rank's weight arena.  `count` = R * ldw floats (multiple of 4).
-__global__ void __launch_bounds__(256) reduce_update_allgather_kernel(P2pPeers peers, const float4* __restrict__ partial,
+__global__ void __launch_bounds__(256, 8) reduce_update_allgather_kernel(P2pPeers peers, const float4* __restrict__ partial,
                                                                       int64_t slice4, float4* __restrict__ vel,
                                                                       int64_t w_off4, int64_t count4, float mu, float alpha) {
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
