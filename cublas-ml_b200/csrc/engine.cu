@@ -552,7 +552,10 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         // buffers in peer memory instead of NCCL: no foreign kernel competes with the persistent GEMMs for SMs
         if (c->p2p && !sp.fused[j] && !custom && (prec != B2NN_PREC_TF32X3 || x3) && nw <= P2P_MAX_LAYERS &&
             j < int(c->p2p_small_off.size()) && c->p2p_small_off[j] >= 0 && c->p2p_small_cnt[j] == li.ldw * li.out) sp.fused[j] = 2;
-        sp.fwd_waits[j] = sp.fused[j] == 1 && f.tc && prec == B2NN_PREC_TF32 && !tail_layer && !std::getenv("B2NN_P2P_GATE_KERNEL");
+        // 1: a one-warp gate kernel in front of the layer's forward contraction; 2: the wait inside the tcgen05 kernel's TMA
+        // producer (B2NN_P2P_FWD_WAIT=1; only safe when the owners' kernels can become resident next to the GEMM CTAs:
+        // a GEMM that holds every SM while it spins on a flag whose writer needs an SM deadlocks the pair of GPUs)
+        sp.fwd_waits[j] = (sp.fused[j] == 1 && prec == B2NN_PREC_TF32 && !tail_layer) ? ((f.tc && std::getenv("B2NN_P2P_FWD_WAIT")) ? 2 : 1) : 0;
 
         // delta backprop  delta_{j-1} = (delta_j W_j)[:, no bias] .* f'(z_{j-1})   (cublasNN.cpp:673-676)
         if (j > 0) {
@@ -646,7 +649,9 @@ int forward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_de
     for (int j = 0; j < nw; ++j) {
         // data parallel over peer memory: this layer's weights are complete once every owner's flag shows the previous step
         TcWait wait{c->p2p_flags + (1 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD, c->nranks, gate_step};
-        int rc = run_gemm(c, sp.fwd[j], x_start, 0, (gate_step > 0 && sp.fwd_waits[j]) ? &wait : nullptr);
+        if (gate_step > 0 && sp.fwd_waits[j] == 1)
+            B2_CUDA(p2p_gate_launch(wait.flags, wait.count, wait.value, c->stream));
+        int rc = run_gemm(c, sp.fwd[j], x_start, 0, (gate_step > 0 && sp.fwd_waits[j] == 2) ? &wait : nullptr);
         if (rc) return rc;
         if (custom && j < int(sp.fwd.size()) - 1) {
             // User activation: a host function that launches on the legacy default stream (cublasNN.cpp:648, 655).  The

@@ -16,9 +16,17 @@
 // fp32-grade mode: every MMA operand is split in REGISTERS into its tf32 head and the exact remainder and each product is
 // issued as hi*hi + hi*lo + lo*hi (the dropped lo*lo term is 2^-22 relative): no low-part arrays in memory at all.
 //
-// Shared-memory X tile: row = feature, 36-float pitch, column (sample) index XOR 8 on odd 8-row groups.  Phase 1 reads it
-// "transposed" (lanes walk 4 features x 8 samples), phase 3 row-wise (8 features x 4 samples); with this pitch and swizzle
-// both fragment loads touch 32 distinct banks.
+// Shared memory.  X tile: row = feature, 128 B (32 samples) per row, no padding; the 16-byte slot index is XOR-swizzled
+// with the row (2 ((row >> 2) & 3) ^ 4 (row & 1)) so that BOTH fragment patterns are conflict-free 16-byte loads: phase 1
+// (lanes walk 4 feature rows x 8 slots) and phase 3 (8 feature rows x 4 slots).  The MMA's k index and the sample index of
+// its rows are PERMUTATIONS of features / samples chosen so that every lane's fragment values are 4 consecutive floats:
+//   phase 1  k-slot t   of k-step j  <->  feature kb + 4t + j,  k-slot t+4 <-> feature kb + 16 + 4t + j   (A and B alike)
+//            row g / g+8 of row tile mt  <->  samples 4g + 2mt, 4g + 2mt + 1
+//   phase 3  k-slot t / t+4 of k-step j  <->  samples 4t + j / 16 + 4t + j
+// W0 travels through a ring of stages of 128 features (4 chunks of 32, one per K group of warps), loaded with cp.async
+// together with the X rows of the same features — the first MMAs start when the first 128 feature rows have landed, and
+// the L2 latency of W0 (every block reads all of it) is paid once, not once per chunk.  Blocks start at different rounds
+// so that 132 blocks do not ask L2 for the same lines at the same moment.
 #include "engine.h"
 #include "pdl.cuh"
 #include "epilogue.cuh"
@@ -32,10 +40,17 @@ namespace {
 constexpr int M3_THREADS = 256;
 constexpr int M3_WARPS = M3_THREADS / 32;
 constexpr int M3_S = 32;                  // samples per tile
-constexpr int M3_XP = 36;                 // floats per shared-memory row
+constexpr int M3_KG = 4;                  // K groups of warps (chunks of a round processed concurrently)
+constexpr int M3_NG = 2;                  // column groups of warps
+constexpr int M3_RF = 32 * M3_KG;         // features per round
+constexpr int M3_AP = 36;                 // pitch of the small activation arrays (a1s)
 constexpr uint32_t TF32_MASK = 0xFFFFE000u;
 
-__device__ __forceinline__ int xs_index(int row, int col) { return row * M3_XP + (col ^ (((row >> 3) & 1) << 3)); }
+// float index of (row, 16-byte slot) in a 32-float-per-row array with the X-tile swizzle
+__device__ __forceinline__ int xs_slot(int row, int slot) { return row * 32 + ((slot ^ ((((row >> 2) & 3) << 1) ^ ((row & 1) << 2))) << 2); }
+// float index of (unit row, slot) in a W0 stage (128 floats per row) / in d1s (32 floats per row): slot ^ 4 on odd rows
+__device__ __forceinline__ int ws_slot(int row, int slot) { return row * M3_RF + ((slot ^ ((row & 1) << 2)) << 2); }
+__device__ __forceinline__ int ds_slot(int row, int slot) { return row * 32 + ((slot ^ ((row & 1) << 2)) << 2); }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(uint32_t(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
@@ -43,7 +58,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(uint32_t(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // D(16x8) += A(16x8) B(8x8), tf32 inputs (fp32 bit patterns), fp32 accumulate.
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -70,123 +86,167 @@ __device__ __forceinline__ void mma_prod(float (&d)[4], const float (&a)[4], flo
         mma_tf32(d, al, bh0, bh1);
     }
 }
+__device__ __forceinline__ float f4(const float4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
 
 __device__ __forceinline__ float act_fwd3(int kind, float z) { return kind == B2NN_ACT_SIGMOID ? sigmoid_f(z) : tanhf(z); }
 __device__ __forceinline__ float act_grad3(int kind, float a) { return kind == B2NN_ACT_SIGMOID ? a * (1.0f - a) : 1.0f - a * a; }
 
+__host__ __device__ constexpr int m3_stages(int nt) { return nt <= 7 ? 3 : 2; }
+
 // NT = 8-unit column tiles of the hidden layer (H <= 8 NT), X3 = fp32-grade arithmetic, TRAIN = backward + gradients.
 template <int NT, bool X3, bool TRAIN>
 __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
-    constexpr int MT = (NT + 1) / 2;             // 16-unit row tiles of the hidden layer in phase 3
-    constexpr int RED = 2 * NT * 4 * 32;         // floats one warp contributes to the phase-1 reduction
+    constexpr int NTG = (NT + M3_NG - 1) / M3_NG;    // column tiles per column group of warps
+    constexpr int MT = (NT + 1) / 2;                 // 16-unit row tiles of the hidden layer in phase 3
+    constexpr int NSTG = m3_stages(NT);
+    constexpr int WROWS = 8 * NT;
+    constexpr int STAGE = WROWS * M3_RF;             // floats per W0 stage
+    constexpr int RED = M3_NG * 2 * NTG * 4 * 32;    // floats one K group contributes to the phase-1 reduction
+    static_assert(M3_KG * RED <= NSTG * STAGE, "the reduction buffer aliases the W0 ring");
     extern __shared__ __align__(16) float m3_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int kg = warp & (M3_KG - 1), ng = warp / M3_KG;
     const int n1 = p.n1, H = p.H, K = p.K;
-    const int xrows = (n1 + 31) / 32 * 32;       // rows n1 .. xrows-1 stay zero: the feature loop runs in blocks of 32
-    float* Xs = m3_smem;                                   // [xrows][36]
-    float* red = Xs + size_t(xrows) * M3_XP;               // [8 warps][RED]
-    float* a1s = red + M3_WARPS * RED;                     // [H+1][36] hidden activations, ones row last
-    float* d1s = a1s + (8 * NT + 1) * M3_XP;               // [16 MT][36] delta of the hidden layer (rows >= H zero)
-    float* zs = d1s + 16 * MT * M3_XP;                     // [K][32] z, then h
+    const int xrows = (n1 + 31) / 32 * 32;           // rows n1 .. xrows-1 stay zero
+    const int rounds = (n1 + M3_RF - 1) / M3_RF;
+    float* Xs = m3_smem;                                   // [xrows][32] swizzled
+    float* ring = Xs + size_t(xrows) * 32;                 // [NSTG][WROWS][128] swizzled; after phase 1: the K-group partial sums
+    float* a1s = ring + NSTG * STAGE;                      // [H+1][36] hidden activations, ones row last
+    float* d1s = a1s + (WROWS + 1) * M3_AP;                // [16 MT][32] swizzled: delta of the hidden layer (rows >= H zero)
+    float* zs = d1s + 16 * MT * 32;                        // [K][32] z, then exp(z - max)
     float* d2s = zs + 16 * M3_S;                           // [K][32] output delta
-    float* w1s = d2s + 16 * M3_S;                          // [K][H+1]
+    float* ys = d2s + 16 * M3_S;                           // [K][32] targets of the tile
+    float* w1s = ys + 16 * M3_S;                           // [K][H+1]
 
     // ---- once per block: constants in shared memory (nothing here reads what the previous kernel wrote) ----
-    for (int i = tid; i < (xrows - n1) * M3_XP; i += M3_THREADS) Xs[size_t(n1) * M3_XP + i] = 0.f;
-    for (int i = tid; i < 16 * MT * M3_XP; i += M3_THREADS) d1s[i] = 0.f;
-    if (tid < M3_XP) a1s[H * M3_XP + tid] = 1.0f;
+    for (int i = tid; i < (xrows - n1) * 32; i += M3_THREADS) Xs[size_t(n1) * 32 + i] = 0.f;
+    for (int i = tid; i < NSTG * STAGE; i += M3_THREADS) ring[i] = 0.f;        // unit rows >= H are never loaded: zeros
+    for (int i = tid; i < 16 * MT * 32; i += M3_THREADS) d1s[i] = 0.f;
+    if (tid < M3_AP) a1s[H * M3_AP + tid] = 1.0f;
     pdl_enter();
     for (int i = tid; i < K * (H + 1); i += M3_THREADS) w1s[i] = __ldg(p.W1 + (i / (H + 1)) * p.ldw1 + i % (H + 1));
 
     const int64_t n_tiles = (p.rows + M3_S - 1) / M3_S;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) && (p.ldx % 4 == 0);
+    const bool yvec_ok = p.Y && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0) && (p.ldy % 4 == 0);
+    const int r0 = int(blockIdx.x % unsigned(rounds));      // blocks walk the rounds from different starting points
     double cost = 0.0, errs = 0.0;
     bool first_tile = true;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first_tile = false) {
         const int64_t s0 = tile * M3_S;
         const int valid = int(p.rows - s0 < M3_S ? p.rows - s0 : M3_S);
-        __syncthreads();                                    // the previous tile's phase 3 is done with Xs / d1s
-        // ---- X tile -> shared memory (features x samples, zero beyond the batch end) ----
-        if (vec_ok && valid == M3_S) {
-            for (int i = tid; i < n1 * 8; i += M3_THREADS) {
-                const int r = i >> 3, c4 = (i & 7) << 2;
-                cp_async16(Xs + xs_index(r, c4), p.X + int64_t(r) * p.ldx + s0 + c4);
-            }
-        } else {
-            for (int i = tid; i < n1 * M3_S; i += M3_THREADS) {
-                const int r = i >> 5, c = i & 31;
-                if (c < valid) cp_async4(Xs + xs_index(r, c), p.X + int64_t(r) * p.ldx + s0 + c);
-                else Xs[xs_index(r, c)] = 0.f;
-            }
-        }
-        cp_async_wait_all();
-        __syncthreads();
+        const bool full = valid == M3_S;
+        __syncthreads();                                    // the previous tile is done with Xs / ring / d1s / ys
 
-        // ---- phase 1: hidden pre-activations, split-K over the warps (blocks of 32 features) ----
+        // One load group = the X rows and the W0 columns of one round of 128 features (+ the targets with the first).
+        auto issue_round = [&](int i) {
+            const int rd = (r0 + i) % rounds, f0 = rd * M3_RF;
+            const int frows = min(M3_RF, n1 - f0);
+            if (vec_ok && full) {
+                for (int e = tid; e < frows * 8; e += M3_THREADS) {
+                    const int r = f0 + (e >> 3), sl = e & 7;
+                    cp_async16(Xs + xs_slot(r, sl), p.X + int64_t(r) * p.ldx + s0 + 4 * sl);
+                }
+            } else {
+                for (int e = tid; e < frows * M3_S; e += M3_THREADS) {
+                    const int r = f0 + (e >> 5), c = e & 31;
+                    float* dst = Xs + xs_slot(r, c >> 2) + (c & 3);
+                    if (c < valid) cp_async4(dst, p.X + int64_t(r) * p.ldx + s0 + c); else *dst = 0.f;
+                }
+            }
+            float* stage = ring + (i % NSTG) * STAGE;
+            for (int e = tid; e < H * 32; e += M3_THREADS) {
+                const int u = e >> 5, sl = e & 31, f = f0 + 4 * sl;
+                float* dst = stage + ws_slot(u, sl);
+                if (f + 3 < p.ldw0) cp_async16(dst, p.W0 + int64_t(u) * p.ldw0 + f);
+                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (i == 0 && p.Y) {
+                if (yvec_ok && full) {
+                    for (int e = tid; e < K * 8; e += M3_THREADS) cp_async16(ys + (e >> 3) * M3_S + 4 * (e & 7), p.Y + int64_t(e >> 3) * p.ldy + s0 + 4 * (e & 7));
+                } else {
+                    for (int e = tid; e < K * M3_S; e += M3_THREADS) {
+                        const int c = e & 31;
+                        if (c < valid) cp_async4(ys + e, p.Y + int64_t(e >> 5) * p.ldy + s0 + c); else ys[e] = 0.f;
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+
+        // ---- phase 1: hidden pre-activations.  Warp (kg, ng): chunk kg of every round, column tiles ng*NTG .. ----
         {
-            float acc[2][NT][4];
+            float acc[2][NTG][4];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
+                for (int nt = 0; nt < NTG; ++nt)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[mt][nt][q] = 0.f;
-            for (int kb = warp * 32; kb < n1; kb += M3_WARPS * 32) {
-                // B fragments: lane (g, t) holds W0[unit 8nt+g][kb + 4t + j] and [kb + 16 + 4t + j], j = 0..3 — the k index
-                // of the MMA is a permutation of the features, the same one on the A side
-                float4 w_lo4[NT], w_hi4[NT];
+#pragma unroll 1
+            for (int i = 0; i < NSTG - 1; ++i) { if (i < rounds) issue_round(i); else cp_async_commit(); }
+#pragma unroll 1
+            for (int i = 0; i < rounds; ++i) {
+                cp_async_wait<NSTG - 2>();                   // this thread's copies of round i have landed ...
+                __syncthreads();                             // ... everyone's have, and round i-1's stage is free again
+                if (i + NSTG - 1 < rounds) issue_round(i + NSTG - 1); else cp_async_commit();
+                const int rd = (r0 + i) % rounds, kb = rd * M3_RF + kg * 32;
+                if (kb < n1) {                               // warp-uniform
+                    const float* stage = ring + (i % NSTG) * STAGE;
+                    float4 xv1[4], xv2[4];
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const int u = nt * 8 + g;
-                    const float* wr = p.W0 + int64_t(u) * p.ldw0 + kb + 4 * t;
-                    const bool row_ok = u < H;
-                    w_lo4[nt] = (row_ok && kb + 4 * t + 3 < p.ldw0) ? __ldg(reinterpret_cast<const float4*>(wr)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    w_hi4[nt] = (row_ok && kb + 16 + 4 * t + 3 < p.ldw0) ? __ldg(reinterpret_cast<const float4*>(wr + 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float a[2][4];
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        a[mt][0] = Xs[xs_index(kb + 4 * t + j, mt * 16 + g)];
-                        a[mt][1] = Xs[xs_index(kb + 4 * t + j, mt * 16 + g + 8)];
-                        a[mt][2] = Xs[xs_index(kb + 16 + 4 * t + j, mt * 16 + g)];
-                        a[mt][3] = Xs[xs_index(kb + 16 + 4 * t + j, mt * 16 + g + 8)];
+                    for (int j = 0; j < 4; ++j) {
+                        xv1[j] = *reinterpret_cast<const float4*>(Xs + xs_slot(kb + 4 * t + j, g));
+                        xv2[j] = *reinterpret_cast<const float4*>(Xs + xs_slot(kb + 16 + 4 * t + j, g));
                     }
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        const float b0 = j == 0 ? w_lo4[nt].x : j == 1 ? w_lo4[nt].y : j == 2 ? w_lo4[nt].z : w_lo4[nt].w;
-                        const float b1 = j == 0 ? w_hi4[nt].x : j == 1 ? w_hi4[nt].y : j == 2 ? w_hi4[nt].z : w_hi4[nt].w;
-                        mma_prod<X3>(acc[0][nt], a[0], b0, b1);
-                        mma_prod<X3>(acc[1][nt], a[1], b0, b1);
+                    for (int nt = 0; nt < NTG; ++nt) {
+                        if (ng * NTG + nt < NT) {
+                            const int u = (ng * NTG + nt) * 8 + g;
+                            const float4 w1v = *reinterpret_cast<const float4*>(stage + ws_slot(u, kg * 8 + t));
+                            const float4 w2v = *reinterpret_cast<const float4*>(stage + ws_slot(u, kg * 8 + 4 + t));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float a0[4] = {xv1[j].x, xv1[j].y, xv2[j].x, xv2[j].y};      // samples 4g, 4g+1
+                                const float a1[4] = {xv1[j].z, xv1[j].w, xv2[j].z, xv2[j].w};      // samples 4g+2, 4g+3
+                                mma_prod<X3>(acc[0][nt], a0, f4(w1v, j), f4(w2v, j));
+                                mma_prod<X3>(acc[1][nt], a1, f4(w1v, j), f4(w2v, j));
+                            }
+                        }
                     }
                 }
             }
-            float* mine = red + warp * RED;
+            cp_async_wait<0>();
+            __syncthreads();                                 // every warp is done with the ring: it becomes the reduction buffer
+            float* mine = ring + kg * RED + ng * (2 * NTG * 4 * 32);
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
+                for (int nt = 0; nt < NTG; ++nt)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) mine[((mt * NT + nt) * 4 + q) * 32 + lane] = acc[mt][nt][q];
+                    for (int q = 0; q < 4; ++q) mine[((mt * NTG + nt) * 4 + q) * 32 + lane] = acc[mt][nt][q];
         }
         __syncthreads();
         for (int o = tid; o < RED; o += M3_THREADS) {
             float sum = 0.f;
 #pragma unroll
-            for (int w = 0; w < M3_WARPS; ++w) sum += red[w * RED + o];
-            const int l = o & 31, q = (o >> 5) & 3, tl = o >> 7, mt = tl / NT, nt = tl - mt * NT;
-            const int sample = mt * 16 + (l >> 2) + 8 * (q >> 1), unit = nt * 8 + 2 * (l & 3) + (q & 1);
-            if (unit < H) a1s[unit * M3_XP + sample] = act_fwd3(p.act_kind, sum);
+            for (int w = 0; w < M3_KG; ++w) sum += ring[w * RED + o];
+            const int l = o & 31, q = (o >> 5) & 3, tl = (o >> 7) % (2 * NTG), grp = (o >> 7) / (2 * NTG);
+            const int mt = tl / NTG, nt = grp * NTG + tl % NTG;
+            const int sample = 4 * (l >> 2) + 2 * mt + (q >> 1), unit = nt * 8 + 2 * (l & 3) + (q & 1);
+            if (unit < H) a1s[unit * M3_AP + sample] = act_fwd3(p.act_kind, sum);
         }
         __syncthreads();
+        if (TRAIN) {      // the ring is the W0 stage area again for the next tile: rows >= H must read as zeros
+            for (int i = tid; i < M3_KG * RED; i += M3_THREADS) ring[i] = 0.f;
+        }
 
         // ---- phase 2: output layer (fp32 FFMA), output activation, delta, cost, argmax ----
         for (int i = tid; i < K * M3_S; i += M3_THREADS) {
             const int k = i >> 5, s = i & 31;
             const float* w = w1s + k * (H + 1);
             float z = w[H];
-            for (int u = 0; u < H; ++u) z = fmaf(w[u], a1s[u * M3_XP + s], z);
+            for (int u = 0; u < H; ++u) z = fmaf(w[u], a1s[u * M3_AP + s], z);
             zs[k * M3_S + s] = z;
         }
         __syncthreads();
@@ -211,7 +271,7 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
                 if (ok && p.h_out) p.h_out[int64_t(k) * p.ldh + i] = hv;
                 float dv = 0.f;
                 if (p.Y) {
-                    const float yv = __ldg(p.Y + int64_t(k) * p.ldy + i);
+                    const float yv = ys[k * M3_S + s];
                     if (yv > best_y) { best_y = yv; arg_y = k; }
                     dv = hv - yv;
                     if (ok && p.cost_sum) {
@@ -233,7 +293,11 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
                 else if (p.Y)   errs += (arg_h != arg_y) ? 1.0 : 0.0;
             }
         }
-        if (!TRAIN) continue;
+        if (!TRAIN) {
+            // forward only: the ring must read as zeros above row H again before the next tile's loads (see above)
+            for (int i = tid; i < M3_KG * RED; i += M3_THREADS) ring[i] = 0.f;
+            continue;
+        }
         __syncthreads();
         float* part = p.partial + int64_t(blockIdx.x) * p.total;
         // delta of the hidden layer  d1 = (d2 W1) .* f'(a1)   (cublasNN.cpp:673-676), and the output-layer gradient
@@ -241,13 +305,13 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
             const int u = i >> 5, s = i & 31;
             float v = 0.f;
             for (int k = 0; k < K; ++k) v = fmaf(d2s[k * M3_S + s], w1s[k * (H + 1) + u], v);
-            d1s[u * M3_XP + s] = v * act_grad3(p.act_kind, a1s[u * M3_XP + s]);
+            d1s[ds_slot(u, s >> 2) + (s & 3)] = v * act_grad3(p.act_kind, a1s[u * M3_AP + s]);
         }
         for (int i = tid; i < K * p.ldw1; i += M3_THREADS) {       // pad columns (u > H) of the slice are written too: zeros
             const int k = i / p.ldw1, u = i - k * p.ldw1;
             float gsum = 0.f;
             if (u <= H)
-                for (int s = 0; s < M3_S; ++s) gsum = fmaf(d2s[k * M3_S + s], a1s[u * M3_XP + s], gsum);
+                for (int s = 0; s < M3_S; ++s) gsum = fmaf(d2s[k * M3_S + s], a1s[u * M3_AP + s], gsum);
             float* dst = part + p.w1_off + i;
             *dst = first_tile ? gsum : *dst + gsum;
         }
@@ -255,16 +319,14 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
 
         // ---- phase 3: input-layer gradient of this tile, G0[unit][feature] = sum_s d1[unit][s] x[feature][s] ----
         {
-            float af[4][MT][4];                              // A = d1: every feature tile reuses it
+            float4 af[MT][4];                                // A = d1 rows g, g+8 of every row tile: slots t and 4+t
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    af[ks][mt][0] = d1s[(mt * 16 + g) * M3_XP + ks * 8 + t];
-                    af[ks][mt][1] = d1s[(mt * 16 + g + 8) * M3_XP + ks * 8 + t];
-                    af[ks][mt][2] = d1s[(mt * 16 + g) * M3_XP + ks * 8 + t + 4];
-                    af[ks][mt][3] = d1s[(mt * 16 + g + 8) * M3_XP + ks * 8 + t + 4];
-                }
+            for (int mt = 0; mt < MT; ++mt) {
+                af[mt][0] = *reinterpret_cast<const float4*>(d1s + ds_slot(mt * 16 + g, t));
+                af[mt][1] = *reinterpret_cast<const float4*>(d1s + ds_slot(mt * 16 + g + 8, t));
+                af[mt][2] = *reinterpret_cast<const float4*>(d1s + ds_slot(mt * 16 + g, 4 + t));
+                af[mt][3] = *reinterpret_cast<const float4*>(d1s + ds_slot(mt * 16 + g + 8, 4 + t));
+            }
             const int f_tiles = (n1 + 7) / 8;
             for (int ft = warp; ft < f_tiles; ft += M3_WARPS) {
                 float acc[MT][4];
@@ -272,12 +334,15 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[mt][q] = 0.f;
+                const float4 b1v = *reinterpret_cast<const float4*>(Xs + xs_slot(ft * 8 + g, t));
+                const float4 b2v = *reinterpret_cast<const float4*>(Xs + xs_slot(ft * 8 + g, 4 + t));
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const float b0 = Xs[xs_index(ft * 8 + g, ks * 8 + t)];
-                    const float b1 = Xs[xs_index(ft * 8 + g, ks * 8 + t + 4)];
+                for (int j = 0; j < 4; ++j) {
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) mma_prod<X3>(acc[mt], af[ks][mt], b0, b1);
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const float a[4] = {f4(af[mt][0], j), f4(af[mt][1], j), f4(af[mt][2], j), f4(af[mt][3], j)};
+                        mma_prod<X3>(acc[mt], a, f4(b1v, j), f4(b2v, j));
+                    }
                 }
                 const int f = ft * 8 + 2 * t;                // this lane's two features: f, f + 1 (f even, ldw0 % 4 == 0)
                 if (f < p.ldw0) {
@@ -340,8 +405,8 @@ __global__ void __launch_bounds__(256) mlp3_reduce_update_kernel(const float4* _
 
 size_t mlp3_smem_bytes(int n1, int nt) {
     const int mt = (nt + 1) / 2, xrows = (n1 + 31) / 32 * 32;
-    const size_t floats = size_t(xrows) * M3_XP + size_t(M3_WARPS) * (2 * nt * 4 * 32) + size_t(8 * nt + 1) * M3_XP +
-                          size_t(16 * mt) * M3_XP + 2 * 16 * M3_S + 16 * (8 * nt + 1);
+    const size_t floats = size_t(xrows) * 32 + size_t(m3_stages(nt)) * (8 * nt) * M3_RF + size_t(8 * nt + 1) * M3_AP +
+                          size_t(16 * mt) * 32 + 3 * 16 * M3_S + 16 * (8 * nt + 1);
     return floats * sizeof(float);
 }
 

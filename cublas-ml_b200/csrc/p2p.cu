@@ -117,6 +117,14 @@ __global__ void __launch_bounds__(256, 8) reduce_update_allgather_kernel(P2pPeer
 
 }  // namespace
 
+// The owner kernels should run UNDER the persistent GEMMs, whose CTAs configure their SM for the largest shared-memory
+// carve-out: ask for the same carve-out, so that becoming resident on such an SM needs no reconfiguration.
+template <typename Kern>
+static void prefer_max_shared(Kern k) {
+    static bool done = false;      // per kernel instantiation; the attribute is advisory, failures are ignored
+    if (!done) { (void)cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); (void)cudaGetLastError(); done = true; }
+}
+
 cudaError_t p2p_gate_launch(const int* flags, int count, int value, cudaStream_t s) {
     gate_kernel<<<1, 32, 0, s>>>(flags, count, value);
     return cudaGetLastError();
@@ -135,6 +143,7 @@ cudaError_t p2p_small_scatter_launch(const P2pPeers& peers, const float* src, in
 cudaError_t p2p_small_reduce_update_launch(const float* slots, int64_t slot_stride, int world, float* theta, float* vel,
                                            int64_t count, float mu, float alpha, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
+    prefer_max_shared(small_reduce_update_kernel);
     const int64_t n4 = count / 4, want = (n4 + 255) / 256;
     small_reduce_update_kernel<<<unsigned(want < 148 ? want : 148), 256, 0, s>>>(reinterpret_cast<const float4*>(slots), slot_stride / 4,
                                                                                world, reinterpret_cast<float4*>(theta),
@@ -148,6 +157,7 @@ cudaError_t p2p_signal_launch(const P2pPeers& peers, int index, int value, cudaS
 cudaError_t p2p_reduce_update_launch(const P2pPeers& peers, const float* partial, int64_t slice_floats, float* vel,
                                      int64_t w_off, int64_t count, float mu, float alpha, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
+    prefer_max_shared(reduce_update_allgather_kernel);
     const int64_t n4 = count / 4;
     const int64_t want = (n4 + 255) / 256;
     const unsigned grid = unsigned(want < 148 * 4 ? want : 148 * 4);
