@@ -542,7 +542,9 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         const bool want_fused = c->p2p && (prec == B2NN_PREC_TF32 || x3) && !custom && !tail_layer && nw <= P2P_MAX_LAYERS &&
                                 li.out % (256 * c->nranks) == 0;
         if (want_fused) {
-            for (int o = 0; o < c->nranks; ++o) g.g.scatter_base[o] = c->peers.G[o] + li.w_off;
+            // B2NN_P2P_FAKE_LOCAL (timing experiments only, results are wrong): every tile goes to local memory
+            static const bool fake_local = std::getenv("B2NN_P2P_FAKE_LOCAL") != nullptr;
+            for (int o = 0; o < c->nranks; ++o) g.g.scatter_base[o] = (fake_local ? c->G : c->peers.G[o]) + li.w_off;
             g.g.scatter_world = c->nranks; g.g.scatter_rank = c->rank; g.g.scatter_rows = li.out / c->nranks;
             bind_backend(c, g, prec, false);
             if (g.tc) sp.fused[j] = 1;

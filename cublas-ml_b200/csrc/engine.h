@@ -69,6 +69,7 @@ struct TcPlan {
     unsigned grid_x = 0;      // persistent grid: min(work items, SMs / ncta) * ncta
     size_t smem_bytes = 0;
     bool a_3d = false, b_3d = false;
+    bool scatter_bulk = false;   // scatter mode: output chunks leave through bulk asynchronous stores (32 KB of staging)
     bool swapped = false;     // the kernel runs D^T = B A^T (see GemmDesc::d_trans); `g` stays the caller's description
     bool valid = false;
 };

@@ -45,6 +45,7 @@ constexpr int A_TILE_BYTES = BM * BK * 4;
 constexpr int ATOM_BYTES = 32 * BK * 4;   // one MN-major box: 32 (mn) x 32 (k) floats
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int MAX_STAGES = 8;
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 16 * 32 * 4;   // scatter mode: one 16-column x 32-row chunk per epilogue warp
 
 // bytes of the B tile ONE CTA stages: `rows` = N rows this CTA loads (BN, or BN/2 in a CTA pair)
 __host__ __device__ constexpr int b_tile_bytes(int rows, bool b_mn) {
@@ -70,6 +71,7 @@ struct TcArgs {
     float* scatter_base[8];         // fused reduce-scatter: owner arenas (peer mappings); see GemmDesc
     int scatter_world, scatter_rank, scatter_rows;
     int n_rot;                      // scatter mode: column-tile rotation, so every rank starts with a different owner's tiles
+    int scatter_bulk;               // scatter mode: tiles leave through bulk asynchronous stores staged in shared memory
     const int* wait_flags;          // data parallel over peer memory: the weights this contraction reads are complete once
     int wait_count, wait_value;     // wait_flags[0 .. wait_count) >= wait_value (one flag per owner rank, written by the owners)
 };
@@ -130,6 +132,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* tmem_full  = empty_bar + MAX_STAGES;          // [2]
     uint64_t* tmem_empty = tmem_full + 2;                   // [2]
     uint32_t* tmem_slot  = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* epi_stage = reinterpret_cast<float*>(smem + size_t(stages) * STAGE_BYTES + 256);       // only allocated in scatter mode
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
@@ -394,6 +397,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             for (int j = 0; j < CH; ++j) if (n0 + c0 + j < p.N) dst[j] = v[j];
                         }
                     }
+                } else if (p.scatter_bulk) {
+                    // Fused reduce-scatter over NVLink: the chunk is staged in shared memory (row = output column, 32
+                    // consecutive m per row) and leaves as one 128-byte bulk asynchronous store per column into the owner's
+                    // arena.  Ordinary stores to a peer stall the epilogue warps (an SM tracks only a handful of outstanding
+                    // remote writes: measured 1.2 GB/s per SM, the epilogue then outlasts the next tile's MMAs); bulk stores
+                    // are queued to the TMA unit and the warp moves on.
+                    float* stg = epi_stage + (warp - 2) * (CH * 32);
+                    if (lane < CH) bulk_wait_read_all();             // this lane's previous copy has left its staging row
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) stg[j * 32 + lane] = v[j];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    const int m0w = (tile_m * NCTA + int(rank)) * BM + q * 32;
+                    const int n = n0 + c0 + lane;
+                    if (lane < CH && n < p.N && m0w < int(p.ldd)) {
+                        const int owner = n0 / p.scatter_rows;
+                        float* dst = p.scatter_base[owner] + (int64_t(p.scatter_rank - owner) * p.scatter_rows + n) * p.ldd + m0w;
+                        const int run = int(p.ldd) - m0w < 32 ? int(p.ldd) - m0w : 32;      // pad columns of the row receive zeros
+                        bulk_store(dst, stg + lane * 32, uint32_t(run) * 4u);
+                    }
+                    if (lane < CH) bulk_commit();
                 } else if (m_ok) {
                     float* dst = Dp + int64_t(n0 + c0) * p.ldd + m;
                     if (p.scatter_world > 0) {
@@ -422,6 +447,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) { if (NCTA == 2) mbar_arrive_remote(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
         }
+        if (p.scatter_bulk) bulk_wait_all();       // every queued store has been performed before the kernel retires
     }
 
     __syncwarp();                 // producer / issuer lanes rejoin their warps
@@ -614,11 +640,14 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& gu, std::string& err) {
     plan.ncta = ncta;
 
     const int stage_bytes = (A_TILE_BYTES + b_tile_bytes(bn / ncta, g.b_major != 0)) * (plan.x3 ? 2 : 1);
-    int stages = (SMEM_LIMIT - 1024 - 256) / stage_bytes;
+    // scatter mode stages its output chunks for bulk stores: 32 KB less for the operand ring (7 -> 6 stages of 32 KB)
+    plan.scatter_bulk = g.scatter_world > 0 && !g.d_trans && (g.ldd % 4) == 0 && !std::getenv("B2NN_TC_NO_BULK");
+    const int epi_bytes = plan.scatter_bulk ? EPI_STAGE_BYTES : 0;
+    int stages = (SMEM_LIMIT - 1024 - 256 - epi_bytes) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) { err = "tile does not fit shared memory"; return false; }
     plan.stages = stages;
-    plan.smem_bytes = size_t(stages) * stage_bytes + 1024 + 256;
+    plan.smem_bytes = size_t(stages) * stage_bytes + 1024 + 256 + epi_bytes;
 
     plan.k_blocks_total = (g.K + BK - 1) / BK;
     plan.tiles_m = (g.M + BM * ncta - 1) / (BM * ncta);
@@ -681,6 +710,7 @@ cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream, const TcWait* 
     a.D_lo = pl.x3 ? g.D_lo : nullptr;
     for (int i = 0; i < 8; ++i) a.scatter_base[i] = g.scatter_base[i];
     a.scatter_world = g.scatter_world; a.scatter_rank = g.scatter_rank; a.scatter_rows = g.scatter_rows;
+    a.scatter_bulk = pl.scatter_bulk ? 1 : 0;
     a.wait_flags = wait ? wait->flags : nullptr; a.wait_count = wait ? wait->count : 0; a.wait_value = wait ? wait->value : 0;
     a.n_rot = 0;
     if (g.scatter_world > 1 && !std::getenv("B2NN_TC_NO_ROT"))

@@ -70,20 +70,30 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ uint32_t hi_of(float x) { return __float_as_uint(x) & TF32_MASK; }
 __device__ __forceinline__ uint32_t lo_of(float x) { return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & TF32_MASK)); }
 
-// One product tile: plain tf32 (operands truncated like tcgen05 kind::tf32 does) or fp32-grade (three MMAs).
+// One product tile.  Plain tf32: the fp32 bit patterns go to the tensor core as they are (mma.sync .tf32 reads the upper
+// 19 bits, i.e. truncates like tcgen05 kind::tf32).  fp32-grade: operands arrive pre-split into head and exact remainder
+// and the product is issued as hi*hi + hi*lo + lo*hi.
+struct Frag4 { uint32_t hi[4], lo[4]; };
 template <bool X3>
-__device__ __forceinline__ void mma_prod(float (&d)[4], const float (&a)[4], float b0, float b1) {
-    uint32_t ah[4];
+__device__ __forceinline__ Frag4 split4(float a0, float a1, float a2, float a3) {
+    Frag4 f;
+    const float v[4] = {a0, a1, a2, a3};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ah[i] = hi_of(a[i]);
-    const uint32_t bh0 = hi_of(b0), bh1 = hi_of(b1);
-    mma_tf32(d, ah, bh0, bh1);
+    for (int i = 0; i < 4; ++i) {
+        if (X3) { f.hi[i] = hi_of(v[i]); f.lo[i] = lo_of(v[i]); }
+        else    { f.hi[i] = __float_as_uint(v[i]); f.lo[i] = 0u; }
+    }
+    return f;
+}
+template <bool X3>
+__device__ __forceinline__ void mma_prod(float (&d)[4], const Frag4& a, float b0, float b1) {
     if (X3) {
-        uint32_t al[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) al[i] = lo_of(a[i]);
-        mma_tf32(d, ah, lo_of(b0), lo_of(b1));
-        mma_tf32(d, al, bh0, bh1);
+        const uint32_t bh0 = hi_of(b0), bh1 = hi_of(b1);
+        mma_tf32(d, a.hi, bh0, bh1);
+        mma_tf32(d, a.hi, lo_of(b0), lo_of(b1));
+        mma_tf32(d, a.lo, bh0, bh1);
+    } else {
+        mma_tf32(d, a.hi, __float_as_uint(b0), __float_as_uint(b1));
     }
 }
 __device__ __forceinline__ float f4(const float4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
@@ -120,7 +130,8 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
 
     // ---- once per block: constants in shared memory (nothing here reads what the previous kernel wrote) ----
     for (int i = tid; i < (xrows - n1) * 32; i += M3_THREADS) Xs[size_t(n1) * 32 + i] = 0.f;
-    for (int i = tid; i < NSTG * STAGE; i += M3_THREADS) ring[i] = 0.f;        // unit rows >= H are never loaded: zeros
+    for (int i = tid; i < NSTG * (WROWS - H) * M3_RF; i += M3_THREADS)        // unit rows >= H are never loaded: zeros
+        ring[(i / ((WROWS - H) * M3_RF)) * STAGE + H * M3_RF + i % ((WROWS - H) * M3_RF)] = 0.f;
     for (int i = tid; i < 16 * MT * 32; i += M3_THREADS) d1s[i] = 0.f;
     if (tid < M3_AP) a1s[H * M3_AP + tid] = 1.0f;
     pdl_enter();
@@ -137,6 +148,11 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
         const int valid = int(p.rows - s0 < M3_S ? p.rows - s0 : M3_S);
         const bool full = valid == M3_S;
         __syncthreads();                                    // the previous tile is done with Xs / ring / d1s / ys
+        if (!first_tile) {                                  // the ring held the K-group sums: rows >= H must read as zeros again
+            for (int i = tid; i < NSTG * (WROWS - H) * M3_RF; i += M3_THREADS)
+                ring[(i / ((WROWS - H) * M3_RF)) * STAGE + H * M3_RF + i % ((WROWS - H) * M3_RF)] = 0.f;
+            __syncthreads();
+        }
 
         // One load group = the X rows and the W0 columns of one round of 128 features (+ the targets with the first).
         auto issue_round = [&](int i) {
@@ -193,11 +209,13 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
                 const int rd = (r0 + i) % rounds, kb = rd * M3_RF + kg * 32;
                 if (kb < n1) {                               // warp-uniform
                     const float* stage = ring + (i % NSTG) * STAGE;
-                    float4 xv1[4], xv2[4];
+                    Frag4 fa[4][2];                           // A fragments of the four k-steps, both row tiles
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        xv1[j] = *reinterpret_cast<const float4*>(Xs + xs_slot(kb + 4 * t + j, g));
-                        xv2[j] = *reinterpret_cast<const float4*>(Xs + xs_slot(kb + 16 + 4 * t + j, g));
+                        const float4 x1 = *reinterpret_cast<const float4*>(Xs + xs_slot(kb + 4 * t + j, g));
+                        const float4 x2 = *reinterpret_cast<const float4*>(Xs + xs_slot(kb + 16 + 4 * t + j, g));
+                        fa[j][0] = split4<X3>(x1.x, x1.y, x2.x, x2.y);      // samples 4g, 4g+1
+                        fa[j][1] = split4<X3>(x1.z, x1.w, x2.z, x2.w);      // samples 4g+2, 4g+3
                     }
 #pragma unroll
                     for (int nt = 0; nt < NTG; ++nt) {
@@ -207,10 +225,8 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
                             const float4 w2v = *reinterpret_cast<const float4*>(stage + ws_slot(u, kg * 8 + 4 + t));
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float a0[4] = {xv1[j].x, xv1[j].y, xv2[j].x, xv2[j].y};      // samples 4g, 4g+1
-                                const float a1[4] = {xv1[j].z, xv1[j].w, xv2[j].z, xv2[j].w};      // samples 4g+2, 4g+3
-                                mma_prod<X3>(acc[0][nt], a0, f4(w1v, j), f4(w2v, j));
-                                mma_prod<X3>(acc[1][nt], a1, f4(w1v, j), f4(w2v, j));
+                                mma_prod<X3>(acc[0][nt], fa[j][0], f4(w1v, j), f4(w2v, j));
+                                mma_prod<X3>(acc[1][nt], fa[j][1], f4(w1v, j), f4(w2v, j));
                             }
                         }
                     }
@@ -237,9 +253,6 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
             if (unit < H) a1s[unit * M3_AP + sample] = act_fwd3(p.act_kind, sum);
         }
         __syncthreads();
-        if (TRAIN) {      // the ring is the W0 stage area again for the next tile: rows >= H must read as zeros
-            for (int i = tid; i < M3_KG * RED; i += M3_THREADS) ring[i] = 0.f;
-        }
 
         // ---- phase 2: output layer (fp32 FFMA), output activation, delta, cost, argmax ----
         for (int i = tid; i < K * M3_S; i += M3_THREADS) {
@@ -293,11 +306,7 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
                 else if (p.Y)   errs += (arg_h != arg_y) ? 1.0 : 0.0;
             }
         }
-        if (!TRAIN) {
-            // forward only: the ring must read as zeros above row H again before the next tile's loads (see above)
-            for (int i = tid; i < M3_KG * RED; i += M3_THREADS) ring[i] = 0.f;
-            continue;
-        }
+        if (!TRAIN) continue;
         __syncthreads();
         float* part = p.partial + int64_t(blockIdx.x) * p.total;
         // delta of the hidden layer  d1 = (d2 W1) .* f'(a1)   (cublasNN.cpp:673-676), and the output-layer gradient
@@ -320,12 +329,18 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
         // ---- phase 3: input-layer gradient of this tile, G0[unit][feature] = sum_s d1[unit][s] x[feature][s] ----
         {
             float4 af[MT][4];                                // A = d1 rows g, g+8 of every row tile: slots t and 4+t
+            float* prow[MT][2];                              // this lane's output rows in the block's gradient slice
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 af[mt][0] = *reinterpret_cast<const float4*>(d1s + ds_slot(mt * 16 + g, t));
                 af[mt][1] = *reinterpret_cast<const float4*>(d1s + ds_slot(mt * 16 + g + 8, t));
                 af[mt][2] = *reinterpret_cast<const float4*>(d1s + ds_slot(mt * 16 + g, 4 + t));
                 af[mt][3] = *reinterpret_cast<const float4*>(d1s + ds_slot(mt * 16 + g + 8, 4 + t));
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int u = mt * 16 + g + 8 * hrow;
+                    prow[mt][hrow] = u < H ? part + int64_t(u) * p.ldw0 + 2 * t : nullptr;
+                }
             }
             const int f_tiles = (n1 + 7) / 8;
             for (int ft = warp; ft < f_tiles; ft += M3_WARPS) {
@@ -340,19 +355,18 @@ __global__ void __launch_bounds__(M3_THREADS, 1) mlp3_kernel(const Mlp3Args p) {
                 for (int j = 0; j < 4; ++j) {
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
-                        const float a[4] = {f4(af[mt][0], j), f4(af[mt][1], j), f4(af[mt][2], j), f4(af[mt][3], j)};
+                        const Frag4 a = split4<X3>(f4(af[mt][0], j), f4(af[mt][1], j), f4(af[mt][2], j), f4(af[mt][3], j));
                         mma_prod<X3>(acc[mt], a, f4(b1v, j), f4(b2v, j));
                     }
                 }
-                const int f = ft * 8 + 2 * t;                // this lane's two features: f, f + 1 (f even, ldw0 % 4 == 0)
-                if (f < p.ldw0) {
+                // this lane's two features: ft*8 + 2t, + 1 (even, ldw0 % 4 == 0: an aligned pair inside the row)
+                if (ft * 8 + 2 * t < p.ldw0) {
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                         for (int hrow = 0; hrow < 2; ++hrow) {
-                            const int u = mt * 16 + g + 8 * hrow;
-                            if (u < H) {
-                                float2* dst = reinterpret_cast<float2*>(part + int64_t(u) * p.ldw0 + f);
+                            if (prow[mt][hrow]) {
+                                float2* dst = reinterpret_cast<float2*>(prow[mt][hrow] + ft * 8);
                                 float2 v = make_float2(acc[mt][2 * hrow], acc[mt][2 * hrow + 1]);
                                 if (!first_tile) { const float2 o = *dst; v.x += o.x; v.y += o.y; }
                                 *dst = v;
