@@ -443,9 +443,13 @@ void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
     }
 }
 
-// One-hidden-layer nets in a tensor-core mode on a single GPU with built-in functions take the one-kernel step (mlp3.cu).
+// One-hidden-layer nets in a tensor-core mode on a single GPU with built-in functions CAN take the one-kernel step of
+// mlp3.cu (B2NN_MLP3=1).  Opt-in: measured on config C1 it is no faster than the four-launch tcgen05 path (38-41 vs 37 us
+// per step) — its contractions run on the legacy mma.sync path, whose tf32 rate on sm_100 is ~136 multiply-adds per
+// clock per SM (ncu: HMMA sub-pipe busy 21 K cycles for 2 800 m16n8k8 per SM), one sixteenth of tcgen05's.
 bool mlp3_ok(const b2nn_ctx* c, int prec, int act_kind) {
-    return c->L.size() == 2 && !c->comm && act_kind != B2NN_ACT_CUSTOM && (prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3) &&
+    const char* e = std::getenv("B2NN_MLP3");
+    return e && std::atoi(e) != 0 && c->L.size() == 2 && !c->comm && act_kind != B2NN_ACT_CUSTOM && (prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3) &&
            c->total_int > 16384 && (c->total_int & 3) == 0 && mlp3_supported(c->L[0].in + 1, c->L[0].out, c->L[1].out);
 }
 

@@ -398,27 +398,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                     }
                 } else if (p.scatter_bulk) {
-                    // Fused reduce-scatter over NVLink: the chunk is staged in shared memory (row = output column, 32
-                    // consecutive m per row) and leaves as one 128-byte bulk asynchronous store per column into the owner's
-                    // arena.  Ordinary stores to a peer stall the epilogue warps (an SM tracks only a handful of outstanding
-                    // remote writes: measured 1.2 GB/s per SM, the epilogue then outlasts the next tile's MMAs); bulk stores
-                    // are queued to the TMA unit and the warp moves on.
-                    float* stg = epi_stage + (warp - 2) * (CH * 32);
-                    if (lane < CH) bulk_wait_read_all();             // this lane's previous copy has left its staging row
-                    __syncwarp();
+                    // Fused reduce-scatter over NVLink: the four warps that share this column slice (one per TMEM lane
+                    // quarter) stage their 16 x 32 chunks side by side (row = output column, 128 consecutive m), then every
+                    // column leaves as ONE 512-byte bulk asynchronous store into the owner's arena.  Ordinary stores to a
+                    // peer stall the epilogue warps (an SM tracks only a handful of outstanding remote writes: measured
+                    // ~1.2 GB/s per SM, the epilogue then outlasts the next tile's MMAs); bulk stores are queued to the TMA
+                    // unit and the warps move on.
+                    float* stg = epi_stage + part * (CH * BM);
+                    const uint32_t bar_id = 1u + uint32_t(part);       // named barrier of this slice's four warps
+                    if (lane < CH / 4) bulk_wait_read_all();            // the columns this lane sent last time have left
+                    asm volatile("bar.sync %0, 128;\n" ::"r"(bar_id) : "memory");
 #pragma unroll
-                    for (int j = 0; j < CH; ++j) stg[j * 32 + lane] = v[j];
+                    for (int j = 0; j < CH; ++j) stg[j * BM + q * 32 + lane] = v[j];
                     fence_proxy_async_smem();
-                    __syncwarp();
-                    const int m0w = (tile_m * NCTA + int(rank)) * BM + q * 32;
-                    const int n = n0 + c0 + lane;
-                    if (lane < CH && n < p.N && m0w < int(p.ldd)) {
+                    asm volatile("bar.sync %0, 128;\n" ::"r"(bar_id) : "memory");
+                    const int m0c = (tile_m * NCTA + int(rank)) * BM;   // this CTA's first output row index m
+                    const int col = q * (CH / 4) + lane;                // each warp sends a quarter of the chunk's columns
+                    const int n = n0 + c0 + col;
+                    if (lane < CH / 4 && n < p.N && m0c < int(p.ldd)) {
                         const int owner = n0 / p.scatter_rows;
-                        float* dst = p.scatter_base[owner] + (int64_t(p.scatter_rank - owner) * p.scatter_rows + n) * p.ldd + m0w;
-                        const int run = int(p.ldd) - m0w < 32 ? int(p.ldd) - m0w : 32;      // pad columns of the row receive zeros
-                        bulk_store(dst, stg + lane * 32, uint32_t(run) * 4u);
+                        float* dst = p.scatter_base[owner] + (int64_t(p.scatter_rank - owner) * p.scatter_rows + n) * p.ldd + m0c;
+                        const int run = int(p.ldd) - m0c < BM ? int(p.ldd) - m0c : BM;      // pad columns of the row receive zeros
+                        bulk_store(dst, stg + col * BM, uint32_t(run) * 4u);
                     }
-                    if (lane < CH) bulk_commit();
+                    if (lane < CH / 4) bulk_commit();
                 } else if (m_ok) {
                     float* dst = Dp + int64_t(n0 + c0) * p.ldd + m;
                     if (p.scatter_world > 0) {

@@ -457,3 +457,25 @@ def test_c4_mini_nine_layers_match_oracle(b2nn, c4_mini_oracle, prec):
     if prec != "fp32":
         assert out.gemm_tc_launches >= 2 * 8 * out.steps, "the wide layers must run on the tcgen05 kernel"
     net.close()
+
+
+@pytest.mark.parametrize("prec", ["tf32", "tf32x3"])
+def test_one_kernel_step_for_one_hidden_layer_nets(b2nn, oracle, monkeypatch, prec):
+    """mlp3.cu (opt-in, B2NN_MLP3=1): the whole step of a one-hidden-layer net in one kernel, warp-level tf32 MMA with the
+    fp32-grade split done in registers.  Same bounds as the default path; inference (fp32-grade) goes through its forward half."""
+    monkeypatch.setenv("B2NN_MLP3", "1")
+    c = cases.case_by_name("mnist_mini")
+    net, th0, th, out = _engine(b2nn, c, prec)
+    ref64 = _oracle(oracle, c, th0, "f64")
+    tol = TOL[prec]
+    assert out.kernel_launches == 2 * out.steps, "one step kernel + one reduce/update kernel per step"
+    assert np.abs(th - ref64.theta).max() <= tol["theta"] * np.abs(ref64.theta).max()
+    np.testing.assert_allclose(out.log_J, ref64.log_J, rtol=tol["J"])
+    assert abs(out.final_cost - ref64.final_cost) <= tol["J"] * abs(ref64.final_cost) + 1e-7
+    assert abs(out.error_count - ref64.error_count) <= max(1.0, 0.005 * c.m)
+    x_cm, _ = cases.oracle_inputs(c)
+    got, probs = net.predict(_desc(b2nn, c, prec), x_cm, c.m)
+    want, wprobs = oracle.predict(c.layers, th, x_cm, c.m, hidden_act=c.hidden_act, classify=True, out_act=c.out_act, precision="f64")
+    assert np.abs(probs - wprobs).max() <= (5e-3 if prec == "tf32" else 5e-5)
+    assert (got != want).mean() <= 0.01
+    net.close()
