@@ -194,6 +194,8 @@ def tensor_peak(precision, clocks, pk, pk_src):
         return bf16 / 2.0, f"0.5 x {key} ({pk_src}): tf32 is half-rate on the tcgen05 pipe", capped
     if precision == "tf32x3":
         return bf16 / 6.0, f"{key} / 6 ({pk_src}): three tf32 MMAs per algorithmic multiply-add", capped
+    if precision == "bf16":
+        return bf16, f"{key} ({pk_src}): kind::f16 with bf16 inputs runs at the measured cuBLAS bf16 rate", capped
     y = yardsticks()
     if y and y.get("fp32_ffma_tflops"):
         return float(y["fp32_ffma_tflops"]), "cuBLAS SGEMM 8192^3 measured by tools/measure_peaks.py (profiles/r2_peaks.json)", capped
@@ -468,7 +470,7 @@ def run_ours(args):
     if args.batch:
         B = args.batch
     K, W = args.steps, max(args.warmup, 3)
-    prec = {"tf32": b2nn.PREC_TF32, "fp32": b2nn.PREC_FP32, "tf32x3": b2nn.PREC_TF32X3}[args.precision]
+    prec = {"tf32": b2nn.PREC_TF32, "fp32": b2nn.PREC_FP32, "tf32x3": b2nn.PREC_TF32X3, "bf16": b2nn.PREC_BF16}[args.precision]
     pk, pk_src = peaks()
     dev_uuid = None
     try:
@@ -568,26 +570,28 @@ def run_ours(args):
     e2e = e2e_leg(prec)
 
     secondary = {}
-    # ---- secondary: the fp32-grade tensor-core mode (3xTF32) on the same workload, same K steps, with its own e2e ------
+    # ---- secondary: the other tensor-core modes on the same workload, same K steps, each with its own e2e ------------
     if args.precision == "tf32" and not args.no_secondary:
-        try:
-            d3 = classify_desc(b2nn, b2nn.PREC_TF32X3, nb, iters)
-            net.train(classify_desc(b2nn, b2nn.PREC_TF32X3, nb, 1))
-            barrier(world)
-            with Clocks(local, dev_uuid) as ck3:
-                o3 = net.train(d3)
+        for key, code, pname, note in (
+                ("c3_tf32x3", b2nn.PREC_TF32X3, "tf32x3", "fp32-grade (the engine's DEFAULT precision): hi*hi + hi*lo + lo*hi tcgen05.mma per product, held to the fp32 parity tolerances in tests/"),
+                ("c3_bf16", b2nn.PREC_BF16, "bf16", "opt-in: tcgen05 kind::f16 on bf16 copies of the operands (fp32 accumulate, fp32 master weights / activations / deltas); stated bound 6e-2 on the weights (tests/)")):
+            try:
+                net.train(classify_desc(b2nn, code, nb, 1))
                 barrier(world)
-            s3 = max_over_ranks(o3.loop_seconds, world)
-            p3, n3, cap3 = tensor_peak("tf32x3", ck3.summary, pk, pk_src)
-            tf3 = step_flops(layers, B) * K / s3 / 1e12
-            secondary["c3_tf32x3"] = {
-                "value": round(B * world * K / s3, 1), "unit": "samples/s", "ms_per_step": round(s3 / K * 1e3, 4), "clocks": ck3.summary,
-                "roofline": {"bound": "tensor", "achieved": round(tf3, 2), "peak": round(p3, 1), "unit": "TFLOP/s", "frac": round(tf3 / p3, 4),
-                             "peak_source": n3, "regime": "sustained (power-capped)" if cap3 else "burst (boost clocks)"},
-                "e2e": e2e_leg(b2nn.PREC_TF32X3),
-                "note": "fp32-grade (the engine's DEFAULT precision): hi*hi + hi*lo + lo*hi tcgen05.mma per product, held to the fp32 parity tolerances in tests/"}
-        except Exception as ex:  # noqa: BLE001
-            secondary["c3_tf32x3"] = {"value": None, "note": f"failed: {ex}"}
+                with Clocks(local, dev_uuid) as ck3:
+                    o3 = net.train(classify_desc(b2nn, code, nb, iters))
+                    barrier(world)
+                s3 = max_over_ranks(o3.loop_seconds, world)
+                p3, n3, cap3 = tensor_peak(pname, ck3.summary, pk, pk_src)
+                tf3 = step_flops(layers, B) * K / s3 / 1e12
+                secondary[key] = {
+                    "value": round(B * world * K / s3, 1), "unit": "samples/s", "ms_per_step": round(s3 / K * 1e3, 4), "clocks": ck3.summary,
+                    "roofline": {"bound": "tensor", "achieved": round(tf3, 2), "peak": round(p3, 1), "unit": "TFLOP/s", "frac": round(tf3 / p3, 4),
+                                 "peak_source": n3, "regime": "sustained (power-capped)" if cap3 else "burst (boost clocks)",
+                                 "note": "whole step (every launch) over the mode's tensor peak"},
+                    "e2e": e2e_leg(code), "note": note}
+            except Exception as ex:  # noqa: BLE001
+                secondary[key] = {"value": None, "note": f"failed: {ex}"}
 
     # ---- data parallel: the NCCL path must land on the same weights as the peer-memory path ---------------------------
     dp_check = None
@@ -793,7 +797,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "tf32x3"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "tf32x3", "bf16"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-secondary", action="store_true", help="headline only (skip the C1/C2/C4/C5/tf32x3 legs)")
     args = ap.parse_args()

@@ -18,7 +18,7 @@ ACT_SIGMOID, ACT_TANH, ACT_CUSTOM = 0, 1, 2
 OUT_SIGMOID, OUT_SOFTMAX, OUT_LINEAR, OUT_CUSTOM = 0, 1, 2, 3
 COST_NEGLNMAX, COST_CROSSENTROPY, COST_SQUARED, COST_CUSTOM = 0, 1, 2, 3
 INIT_1, INIT_2, INIT_CUSTOM = 1, 2, 3
-PREC_FP32, PREC_TF32, PREC_AUTO, PREC_TF32X3 = 0, 1, 2, 3
+PREC_FP32, PREC_TF32, PREC_AUTO, PREC_TF32X3, PREC_BF16 = 0, 1, 2, 3, 4
 EPI_STORE, EPI_SIGMOID, EPI_TANH, EPI_DSIGMOID, EPI_DTANH = 0, 1, 2, 3, 4
 
 ACT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int)

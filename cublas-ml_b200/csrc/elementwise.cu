@@ -5,6 +5,8 @@
 #include "epilogue.cuh"
 #include "../../include/b2nn.h"
 
+#include <cuda_bf16.h>
+
 namespace b2 {
 namespace {
 
@@ -232,6 +234,26 @@ __global__ void __launch_bounds__(256) momentum_update_lo_kernel(float* __restri
     }
 }
 
+// bf16 copies (round to nearest even) of an fp32 array: the operands of the bf16 tensor-core mode.
+__global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ h, int64_t count) {
+    pdl_enter();
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) h[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void __launch_bounds__(256) momentum_update_bf16_kernel(float* __restrict__ theta, float* __restrict__ vel,
+                                                                   const float* __restrict__ grad, __nv_bfloat16* __restrict__ theta_h,
+                                                                   int64_t count, float mu, float alpha) {
+    pdl_enter();
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const float v = fmaf(mu, vel[i], alpha * grad[i]);
+        const float t = theta[i] + v;
+        vel[i] = v;
+        theta[i] = t;
+        theta_h[i] = __float2bfloat16_rn(t);
+    }
+}
+
 __global__ void __launch_bounds__(256) abs_sum_kernel(const float* __restrict__ J, int64_t ld, int64_t rows, int K, double* out) {
     __shared__ double sh[8];
     double s = 0.0;
@@ -377,6 +399,18 @@ cudaError_t momentum_update_lo_launch(float* theta, float* vel, const float* gra
     const int64_t want = (count + 255) / 256;
     return launch_pdl(momentum_update_lo_kernel, dim3(unsigned(want < 148 * 16 ? want : 148 * 16)), dim3(256), 0, stream, theta, vel,
                       grad, theta_lo, count, mu, alpha);
+}
+cudaError_t to_bf16_launch(const float* x, void* h, int64_t count, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    const int64_t want = (count + 255) / 256;
+    return launch_pdl(to_bf16_kernel, dim3(unsigned(want < 148 * 8 ? want : 148 * 8)), dim3(256), 0, s, x, static_cast<__nv_bfloat16*>(h), count);
+}
+cudaError_t momentum_update_bf16_launch(float* theta, float* vel, const float* grad, void* theta_h, int64_t count, float mu,
+                                        float alpha, cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    const int64_t want = (count + 255) / 256;
+    return launch_pdl(momentum_update_bf16_kernel, dim3(unsigned(want < 148 * 16 ? want : 148 * 16)), dim3(256), 0, stream, theta, vel,
+                      grad, static_cast<__nv_bfloat16*>(theta_h), count, mu, alpha);
 }
 cudaError_t abs_sum_launch(const float* J, int64_t ld, int64_t rows, int K, double* out, cudaStream_t s) {
     if (rows <= 0 || K <= 0) return cudaSuccess;

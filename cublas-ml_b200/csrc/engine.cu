@@ -142,7 +142,8 @@ struct b2nn_ctx {
     std::vector<LayerInfo> L;
     int64_t total_ref = 0, total_int = 0;
     float *W = nullptr, *V = nullptr, *G = nullptr;
-    float* W_lo = nullptr; bool w_lo_valid = false;      // low parts of the weights (fp32-grade tensor-core mode)
+    float* W_lo = nullptr; bool w_lo_valid = false;      // companion of the weights: low parts (fp32-grade mode) or bf16 copies
+    bool comp_bf16 = false;                              // which of the two the companion buffers currently hold
     std::map<const float*, std::pair<float*, int64_t>> lo_cache;   // low-part companions of input matrices, by base pointer
 
     // training set, engine layout
@@ -247,16 +248,29 @@ int check_device(int device, std::string& why) {
 }
 
 int resolve_precision(int prec) {
-    if (prec == B2NN_PREC_FP32 || prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3) return prec;
+    if (prec == B2NN_PREC_FP32 || prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3 || prec == B2NN_PREC_BF16) return prec;
     const char* e = std::getenv("B2NN_PRECISION");
     if (e && (std::strcmp(e, "fp32") == 0 || std::strcmp(e, "FP32") == 0)) return B2NN_PREC_FP32;
     if (e && (std::strcmp(e, "tf32") == 0 || std::strcmp(e, "TF32") == 0)) return B2NN_PREC_TF32;
+    if (e && (std::strcmp(e, "bf16") == 0 || std::strcmp(e, "BF16") == 0)) return B2NN_PREC_BF16;
     // Default = fp32-grade (3xTF32 on the tensor cores): a drop-in for the reference's default-math cublasSgemm
     // (cublasNN.cpp:25 never changes the math mode) must not silently narrow the arithmetic; plain tf32 is an opt-in.
     return B2NN_PREC_TF32X3;
 }
 
-// Low-part companion buffer of an input matrix (allocated on demand, content refreshed by the caller with split_lo).
+// Tensor-core modes whose contractions read a COMPANION of every operand: the fp32-grade mode its low part
+// x - trunc_tf32(x) (fp32), the bf16 mode its bf16 copy (two-byte elements at the start of the same buffers).
+inline bool is_tc_prec(int prec) { return prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3 || prec == B2NN_PREC_BF16; }
+inline bool is_comp_prec(int prec) { return prec == B2NN_PREC_TF32X3 || prec == B2NN_PREC_BF16; }
+// companion of element `off` of an array whose companion buffer starts at `base`
+inline float* comp_at(float* base, int64_t off, bool bf) {
+    return bf ? reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(base) + off) : base + off;
+}
+inline cudaError_t make_companion(const float* x, float* comp, int64_t count, bool bf, cudaStream_t s) {
+    return bf ? to_bf16_launch(x, comp, count, s) : split_lo_launch(x, comp, count, s);
+}
+
+// Companion buffer of an input matrix (allocated on demand, content refreshed by the caller).
 float* lo_buffer(b2nn_ctx* c, const float* x, int64_t count) {
     auto it = c->lo_cache.find(x);
     if (it != c->lo_cache.end() && it->second.second >= count) return it->second.first;
@@ -283,7 +297,7 @@ int ensure_w_lo(b2nn_ctx* c) {
         c->w_lo_valid = false;
     }
     if (!c->w_lo_valid) {
-        B2_CUDA(split_lo_launch(c->W, c->W_lo, c->total_int, c->stream));
+        B2_CUDA(make_companion(c->W, c->W_lo, c->total_int, c->comp_bf16, c->stream));
         c->w_lo_valid = true;
     }
     return B2NN_OK;
@@ -374,14 +388,25 @@ int ensure_workspace(b2nn_ctx* c, int64_t rows, bool custom, bool want_lo = fals
 
 // Everything the fp32-grade tensor-core mode needs around one input matrix X (count floats): workspace low parts,
 // weight low parts, and X's own low part, freshly split.
-int prepare_x3(b2nn_ctx* c, const float* X, int64_t count, int64_t rows, bool custom) {
+int prepare_x3(b2nn_ctx* c, const float* X, int64_t count, int64_t rows, bool custom, bool bf = false) {
+    if (c->comp_bf16 != bf) {            // the companion buffers change their meaning: nothing in them is valid any more
+        c->comp_bf16 = bf;
+        c->w_lo_valid = false;
+        c->plans.clear();
+    }
     int rc = ensure_workspace(c, std::max<int64_t>(rows, c->ws.cap), custom, true);
     if (rc) return rc;
+    // the ones row of every hidden activation is written once and never by a contraction: its companion (0 as a low
+    // part, bf16(1) as a copy) is set here
+    for (size_t j = 0; j < c->ws.a.size() && j < c->ws.a_lo.size(); ++j) {
+        const int64_t off = int64_t(c->layers[j + 1]) * c->ws.ld;
+        B2_CUDA(make_companion(c->ws.a[j] + off, comp_at(c->ws.a_lo[j], off, bf), c->ws.ld, bf, c->stream));
+    }
     rc = ensure_w_lo(c);
     if (rc) return rc;
     float* lo = lo_buffer(c, X, count);
     if (!lo) { set_error("cudaMalloc Failed"); return B2NN_ERR_ALLOC; }
-    B2_CUDA(split_lo_launch(X, lo, count, c->stream));
+    B2_CUDA(make_companion(X, lo, count, bf, c->stream));
     return B2NN_OK;
 }
 
@@ -390,7 +415,7 @@ constexpr double kTcMinWork = double(1 << 26);     // multiply-adds below which 
 // A tensor-core mode on a network none of whose contractions would reach the tensor cores (config C2's bikeshare net) is
 // plain fp32: skip the low-part bookkeeping of the fp32-grade mode altogether.
 int effective_precision(const b2nn_ctx* c, int prec, int64_t rows) {
-    if (prec != B2NN_PREC_TF32 && prec != B2NN_PREC_TF32X3) return prec;
+    if (!is_tc_prec(prec)) return prec;
     for (size_t j = 0; j < c->L.size(); ++j) {
         const LayerInfo& li = c->L[j];
         const double work = double(rows) * double(li.in + 1) * double(li.out);
@@ -407,7 +432,7 @@ void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
     if (allow_split) {
         // Weight gradient: K = batch rows is long while M x N can be a handful of tiles (50 x 785, 10 x 4097).  Split K so
         // the grid covers the 148 SMs; partial sums meet in a zeroed gradient block via red.global.add.f32.
-        const bool tc_mode = prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3;
+        const bool tc_mode = is_tc_prec(prec);
         const int tile_m = tc_mode ? 128 : 64;
         const int tile_n = tc_mode ? (g.N > 128 ? 256 : g.N > 64 ? 128 : g.N > 32 ? 64 : g.N > 16 ? 32 : 16) : 64;
         const int64_t tiles = int64_t((g.M + tile_m - 1) / tile_m) * ((g.N + tile_n - 1) / tile_n);
@@ -422,7 +447,7 @@ void bind_backend(b2nn_ctx* c, GemmOp& op, int prec, bool allow_split) {
     // ... except long-K contractions with few rows (small-batch inference on a wide input, config C5): the FFMA kernel
     // would walk K serially in a single block, the tcgen05 pipeline streams it in a few microseconds.
     const bool long_k_few_rows = !allow_split && g.a_major == 1 && g.b_major == 0 && g.K >= 512 && work >= double(1 << 15);
-    if ((prec == B2NN_PREC_TF32 || prec == B2NN_PREC_TF32X3) && (work >= kTcMinWork || long_k_few_rows)) {
+    if (is_tc_prec(prec) && (work >= kTcMinWork || long_k_few_rows)) {
         std::string err;
         const int requested = g.split_k;
         if (g.epi == EPI_STORE && (allow_split || g.N <= 32)) g.split_k = 0;     // let the tcgen05 plan pick the split
@@ -474,7 +499,9 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
     const int nw = nl - 1;
     Workspace& w = c->ws;
     const bool custom = act_kind == B2NN_ACT_CUSTOM;
-    const bool x3 = prec == B2NN_PREC_TF32X3 && !custom && !w.a_lo.empty() && c->W_lo != nullptr;
+    // x3: the contractions carry companions of their operands (low parts, or bf16 copies when bf)
+    const bool bf = prec == B2NN_PREC_BF16;
+    const bool x3 = is_comp_prec(prec) && !custom && !w.a_lo.empty() && c->W_lo != nullptr && c->comp_bf16 == bf;
     const float* X_lo = x3 ? find_lo(c, X) : nullptr;
     sp.fwd.resize(nw); sp.wgrad.resize(nw); sp.bwd.resize(nw);
     sp.fused.assign(nw, 0);
@@ -508,7 +535,8 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         // forward  z_j = [a_{j-1}, 1] W_j^T     (cublasNN.cpp:645-646, 653-654, 658-659)
         GemmOp& f = sp.fwd[j];
         f.g = GemmDesc();
-        if (j == 0) { f.g.A = X; f.g.lda = ldx; f.a_is_x = true; f.g.a_mn_end = x_total; f.g.mn_slack = x_aligned; }
+        // (bf16 boxes are 64 samples wide while batch starts are only 32-aligned: X then takes one 2-D box per 64 samples)
+        if (j == 0) { f.g.A = X; f.g.lda = ldx; f.a_is_x = true; f.g.a_mn_end = x_total; f.g.mn_slack = x_aligned && !bf; }
         else { f.g.A = w.a[j - 1]; f.g.lda = w.ld; f.g.mn_slack = true; }       // workspace rows are padded to 32 samples
         f.g.a_major = 1;
         f.g.B = c->W + li.w_off; f.g.ldb = li.ldw; f.g.b_major = 0;
@@ -520,8 +548,9 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         }
         if (x3) {
             f.g.A_lo = (j == 0) ? X_lo : w.a_lo[j - 1];
-            f.g.B_lo = c->W_lo + li.w_off;
+            f.g.B_lo = comp_at(c->W_lo, li.w_off, bf);
             f.g.D_lo = (j < nw - 1) ? w.a_lo[j] : nullptr;
+            f.g.bf16 = bf;
             if (!f.g.A_lo) { f.g.B_lo = nullptr; f.g.D_lo = nullptr; }
         }
         if (!tail_layer) bind_backend(c, f, prec, false);
@@ -540,6 +569,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         if (x3) {
             g.g.A_lo = (j == 0) ? X_lo : w.a_lo[j - 1];
             g.g.B_lo = w.delta_lo[j];
+            g.g.bf16 = bf;
             if (!g.g.A_lo) g.g.B_lo = nullptr;
         }
         // Peer-memory exchange: the layer's rows split evenly over the ranks in whole 256-column tiles of the gradient GEMM
@@ -556,7 +586,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
         } else if (!(tail_layer && sp.tail_inline_g)) bind_backend(c, g, prec, true);
         // ... layers whose rows do not split into whole tiles per rank (the 10-unit output layer) exchange through slot
         // buffers in peer memory instead of NCCL: no foreign kernel competes with the persistent GEMMs for SMs
-        if (c->p2p && !sp.fused[j] && !custom && (prec != B2NN_PREC_TF32X3 || x3) && nw <= P2P_MAX_LAYERS &&
+        if (c->p2p && !sp.fused[j] && !custom && (!is_comp_prec(prec) || x3) && nw <= P2P_MAX_LAYERS &&
             j < int(c->p2p_small_off.size()) && c->p2p_small_off[j] >= 0 && c->p2p_small_cnt[j] == li.ldw * li.out) sp.fused[j] = 2;
         // 1: a one-warp gate kernel in front of the layer's forward contraction; 2: the wait inside the tcgen05 kernel's TMA
         // producer (B2NN_P2P_FWD_WAIT=1; only safe when the owners' kernels can become resident next to the GEMM CTAs:
@@ -573,7 +603,7 @@ StepPlan& get_plan(b2nn_ctx* c, int64_t rows, const float* X, int64_t ldx, int64
             b.g.M = int(rows); b.g.N = li.in; b.g.K = li.out;
             if (custom) { b.g.D = w.scratch; b.g.ldd = w.ld; b.g.epi = EPI_STORE; }
             else { b.g.D = w.delta[j - 1]; b.g.ldd = w.ld; b.g.epi = epi_backward(act_kind); b.g.aux = w.a[j - 1]; b.g.ldaux = w.ld; }
-            if (x3 && !custom) { b.g.A_lo = w.delta_lo[j]; b.g.B_lo = c->W_lo + li.w_off; b.g.D_lo = w.delta_lo[j - 1]; }
+            if (x3 && !custom) { b.g.A_lo = w.delta_lo[j]; b.g.B_lo = comp_at(c->W_lo, li.w_off, bf); b.g.D_lo = w.delta_lo[j - 1]; b.g.bf16 = bf; }
             if (!tail_layer) bind_backend(c, b, prec, false);
         }
     }
@@ -642,7 +672,7 @@ int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind, const TcW
         if (op.a_is_x) { if (g.a_major) g.a_mn0 += x_start; else g.a_k0 += x_start; }
         B2_CUDA(gemm_simt_launch(g, c->stream));
         // fp32-grade mode: a later tensor-core contraction may consume this output, so it needs its low part too
-        if (g.D_lo) B2_CUDA(split_lo_launch(g.D, g.D_lo, int64_t(g.N) * g.ldd, c->stream));
+        if (g.D_lo) B2_CUDA(make_companion(g.D, g.D_lo, int64_t(g.N) * g.ldd, g.bf16, c->stream));
     }
     ++c->launches;
     return B2NN_OK;
@@ -709,8 +739,8 @@ int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_d
                 B2_CUDA(skinny_bwd_launch(a, c->stream));
             }
             ++c->launches;
-            if (!c->ws.delta_lo.empty() && c->ws.delta_lo[j - 1])      // fp32-grade mode: the next contraction wants the low part too
-                B2_CUDA(split_lo_launch(c->ws.delta[j - 1], c->ws.delta_lo[j - 1], int64_t(li.in) * c->ws.ld, c->stream));
+            if (!c->ws.delta_lo.empty() && c->ws.delta_lo[j - 1])      // companion modes: the next contraction wants the low part / bf16 copy too
+                B2_CUDA(make_companion(c->ws.delta[j - 1], c->ws.delta_lo[j - 1], int64_t(li.in) * c->ws.ld, c->comp_bf16, c->stream));
             return post_gradient(j);
         }
         int rc = run_gemm(c, sp.bwd[j], 0, 1);
@@ -899,7 +929,7 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
         }
         // fp32-grade mode: the owners' kernels store new weight rows only; their low parts are re-derived here, once the
         // gate above has seen every owner's rows of the previous step land (one streaming pass, 8 B per weight)
-        if (prec == B2NN_PREC_TF32X3 && c->W_lo) { int rl = ensure_w_lo(c); if (rl) return rl; }
+        if (is_comp_prec(prec) && c->W_lo) { int rl = ensure_w_lo(c); if (rl) return rl; }
     }
     trace_mark(c, "gated", -1, c->stream);
     int rc = B2NN_OK;
@@ -952,11 +982,11 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
     else if (sp.use_tail) rc = run_tail(c, sp, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
     else rc = output_and_delta(c, d, Y + x_start, ldy, rows, cost_slot);
     if (rc) return rc;
-    if (prec == B2NN_PREC_TF32X3 && !c->ws.delta_lo.empty()) {
+    if (is_comp_prec(prec) && !c->ws.delta_lo.empty()) {
         const int nwl = int(c->L.size());
-        B2_CUDA(split_lo_launch(c->ws.delta[nwl - 1], c->ws.delta_lo[nwl - 1], int64_t(c->L[nwl - 1].out) * c->ws.ld, c->stream));
+        B2_CUDA(make_companion(c->ws.delta[nwl - 1], c->ws.delta_lo[nwl - 1], int64_t(c->L[nwl - 1].out) * c->ws.ld, c->comp_bf16, c->stream));
         if (sp.use_tail)
-            B2_CUDA(split_lo_launch(c->ws.delta[nwl - 2], c->ws.delta_lo[nwl - 2], int64_t(c->L[nwl - 1].in) * c->ws.ld, c->stream));
+            B2_CUDA(make_companion(c->ws.delta[nwl - 2], c->ws.delta_lo[nwl - 2], int64_t(c->L[nwl - 1].in) * c->ws.ld, c->comp_bf16, c->stream));
     }
     rc = backward_pass(c, sp, x_start, d);
     if (rc) return rc;
@@ -1016,7 +1046,10 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
             B2_CUDA(cudaStreamWaitEvent(c->stream, c->grad_reduced[j], 0));
             {
                 ProfScope scope(c, 4, false, 0.0, 20.0 * double(li.ldw) * li.out);
-                if (prec == B2NN_PREC_TF32X3 && c->W_lo)
+                if (prec == B2NN_PREC_BF16 && c->W_lo)
+                    B2_CUDA(momentum_update_bf16_launch(c->W + li.w_off, c->V + li.w_off, c->G + li.w_off, comp_at(c->W_lo, li.w_off, true),
+                                                        li.ldw * li.out, d->momentum, alpha, c->stream));
+                else if (prec == B2NN_PREC_TF32X3 && c->W_lo)
                     B2_CUDA(momentum_update_lo_launch(c->W + li.w_off, c->V + li.w_off, c->G + li.w_off, c->W_lo + li.w_off,
                                                       li.ldw * li.out, d->momentum, alpha, c->stream));
                 else
@@ -1032,9 +1065,11 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
             // small nets: the update also zeroes the gradient arena, so the atomically accumulating producers of the next
             // step (split-K, in-kernel gradient sums) need no memset node in front of them — two to three fewer links in
             // a chain of few-microsecond launches.  Large nets keep the memsets (the extra 4 B per weight would cost more).
-            const bool zeroing = !(prec == B2NN_PREC_TF32X3 && c->W_lo) && c->total_int <= (int64_t(1) << 20) &&
+            const bool zeroing = !(is_comp_prec(prec) && c->W_lo) && c->total_int <= (int64_t(1) << 20) &&
                                  (c->total_int & 3) == 0 && !std::getenv("B2NN_NO_ZERO_UPDATE");
-            if (prec == B2NN_PREC_TF32X3 && c->W_lo)
+            if (prec == B2NN_PREC_BF16 && c->W_lo)
+                B2_CUDA(momentum_update_bf16_launch(c->W, c->V, c->G, c->W_lo, c->total_int, d->momentum, alpha, c->stream));
+            else if (prec == B2NN_PREC_TF32X3 && c->W_lo)
                 B2_CUDA(momentum_update_lo_launch(c->W, c->V, c->G, c->W_lo, c->total_int, d->momentum, alpha, c->stream));
             else if (zeroing) {
                 B2_CUDA(momentum_update_zero_launch(c->W, c->V, c->G, c->total_int, d->momentum, alpha, c->stream));
@@ -1071,8 +1106,8 @@ int evaluate_device(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float
     // Plain tf32 inference keeps the tcgen05 path (B2NN_MLP3_FWD=1 forces the one-kernel forward there too).
     const bool m3 = mlp3_ok(c, prec, d->act_kind) && !custom_outcost(d) && !std::getenv("B2NN_NO_TAIL") &&
                     (prec == B2NN_PREC_TF32X3 || std::getenv("B2NN_MLP3_FWD") != nullptr);
-    if (prec == B2NN_PREC_TF32X3 && d->act_kind != B2NN_ACT_CUSTOM && !m3) {
-        rc = prepare_x3(c, X, ldx * int64_t(c->layers[0] + 1), c->ws.cap, false);
+    if (is_comp_prec(prec) && d->act_kind != B2NN_ACT_CUSTOM && !m3) {
+        rc = prepare_x3(c, X, ldx * int64_t(c->layers[0] + 1), c->ws.cap, false, prec == B2NN_PREC_BF16);
         if (rc) return rc;
     }
     // chunk starts stay on 32-sample boundaries so the forward contractions keep their one-box TMA loads
@@ -1307,7 +1342,7 @@ int b2nn_set_layers(b2nn_ctx* c, const int* layers, int n_layers, int init_kind,
     for (int j = 0; j < n_layers - 1; ++j) {
         LayerInfo& li = c->L[j];
         li.in = layers[j]; li.out = layers[j + 1];
-        li.ldw = round_up(int64_t(li.in) + 1, 4);
+        li.ldw = round_up(int64_t(li.in) + 1, 8);      // 8: rows of the bf16 copy of the weights start 16-byte aligned too (TMA)
         li.ref_off = c->total_ref; li.ref_size = (int64_t(li.in) + 1) * li.out;
         li.w_off = c->total_int;
         c->total_ref += li.ref_size;
@@ -1621,11 +1656,11 @@ int b2nn_train(b2nn_ctx* c, const b2nn_train_desc* d, b2nn_log_cb log, void* log
         Xtrain = c->Xsp; Ytrain = c->Ysp; ld_train = ldsp; x_total = ldsp; b_stride = bs_pad; x_aligned = true;
     }
 
-    if (prec == B2NN_PREC_TF32X3 && d->act_kind != B2NN_ACT_CUSTOM) {
-        rc = prepare_x3(c, Xtrain, ld_train * int64_t(c->n + 1), last_rows, false);
+    if (is_comp_prec(prec) && d->act_kind != B2NN_ACT_CUSTOM) {
+        rc = prepare_x3(c, Xtrain, ld_train * int64_t(c->n + 1), last_rows, false, prec == B2NN_PREC_BF16);
         if (rc) return rc;
     } else {
-        c->w_lo_valid = false;       // the weights are about to change without their low parts being refreshed
+        c->w_lo_valid = false;       // the weights are about to change without their companions being refreshed
     }
 
     const int64_t launches0 = c->launches, tc0 = c->tc_launches;
@@ -1797,8 +1832,8 @@ int b2nn_train_step_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, 
     if (rc) return rc;
     B2_CUDA(cudaMemcpy2DAsync(c->Ys, sizeof(float) * c->lds, y, sizeof(float) * rows, sizeof(float) * rows, size_t(K),
                               cudaMemcpyHostToDevice, c->stream));
-    if (prec == B2NN_PREC_TF32X3 && d->act_kind != B2NN_ACT_CUSTOM) {
-        rc = prepare_x3(c, c->Xs, c->lds * int64_t(n + 1), rows, false);
+    if (is_comp_prec(prec) && d->act_kind != B2NN_ACT_CUSTOM) {
+        rc = prepare_x3(c, c->Xs, c->lds * int64_t(n + 1), rows, false, prec == B2NN_PREC_BF16);
         if (rc) return rc;
     } else {
         c->w_lo_valid = false;
@@ -1860,9 +1895,9 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
     }
     rc = ensure_workspace(c, last_rows, d->act_kind == B2NN_ACT_CUSTOM);
     if (rc) return rc;
-    const bool x3 = prec == B2NN_PREC_TF32X3 && d->act_kind != B2NN_ACT_CUSTOM;
+    const bool x3 = is_comp_prec(prec) && d->act_kind != B2NN_ACT_CUSTOM;
     if (x3) {
-        for (int i = 0; i < 2; ++i) { rc = prepare_x3(c, c->Xst[i], c->ldst * int64_t(n_plus_1), last_rows, false); if (rc) return rc; }
+        for (int i = 0; i < 2; ++i) { rc = prepare_x3(c, c->Xst[i], c->ldst * int64_t(n_plus_1), last_rows, false, prec == B2NN_PREC_BF16); if (rc) return rc; }
     } else {
         c->w_lo_valid = false;
     }
@@ -1909,7 +1944,7 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
         const int buf = int(s & 1), b = int(s % nb);
         if (s + 1 < steps) { rc = issue_copy(s + 1); if (rc) return rc; }      // next batch travels while this one computes
         B2_CUDA(cudaStreamWaitEvent(c->stream, c->st_copied[buf], 0));
-        if (x3) B2_CUDA(split_lo_launch(c->Xst[buf], lo_buffer(c, c->Xst[buf], c->ldst * int64_t(n_plus_1)), c->ldst * int64_t(n_plus_1), c->stream));
+        if (x3) B2_CUDA(make_companion(c->Xst[buf], lo_buffer(c, c->Xst[buf], c->ldst * int64_t(n_plus_1)), c->ldst * int64_t(n_plus_1), c->comp_bf16, c->stream));
         rc = train_step(c, d, prec, c->Xst[buf], c->ldst, c->ldst, true, c->Yst[buf], c->ldst, 0, batch_rows(b), global_rows[b],
                         c->d_jsteps + s);
         if (rc) return rc;
@@ -2145,23 +2180,28 @@ int b2nn_gemm(b2nn_ctx* c, int backend, const float* A, int64_t lda, int a_major
     GemmDesc g;
     g.A = A; g.lda = lda; g.a_major = a_major; g.B = B; g.ldb = ldb; g.b_major = b_major;
     g.D = D; g.ldd = ldd; g.M = M; g.N = N; g.K = K; g.epi = epi; g.aux = aux; g.ldaux = ldaux;
-    if (backend == 1 || backend == 3 || backend == 5 || backend == 7) {
+    if (backend == 1 || backend == 3 || backend == 5 || backend == 7 || backend == 9 || backend == 11) {
         g.mn_slack = (backend & 2) != 0;
+        const bool bf = (backend & 8) != 0;
         DevBuf alo, blo;
-        if (backend & 4) {          // fp32-grade mode: split the operands into temporaries first
+        if (backend & 12) {         // fp32-grade / bf16 mode: the operands' companions go into temporaries first
+            // the caller's slack (32 floats past the last row) is converted too; the temporaries carry a little more,
+            // since the folded bf16 view may touch one 64-element box past the end (feeding rows that are never stored)
             const int64_t na = (a_major ? int64_t(K) : int64_t(M)) * lda + (g.mn_slack ? 32 : 0);
             const int64_t nbb = (b_major ? int64_t(K) : int64_t(N)) * ldb + (g.mn_slack ? 32 : 0);
-            B2_CUDA(cudaMalloc(&alo.p, sizeof(float) * na));
-            B2_CUDA(cudaMalloc(&blo.p, sizeof(float) * nbb));
-            B2_CUDA(split_lo_launch(A, alo.as<float>(), na, c->stream));
-            B2_CUDA(split_lo_launch(B, blo.as<float>(), nbb, c->stream));
-            g.A_lo = alo.as<float>(); g.B_lo = blo.as<float>();
+            B2_CUDA(cudaMalloc(&alo.p, sizeof(float) * (na + 64)));
+            B2_CUDA(cudaMalloc(&blo.p, sizeof(float) * (nbb + 64)));
+            B2_CUDA(cudaMemsetAsync(alo.p, 0, sizeof(float) * (na + 64), c->stream));
+            B2_CUDA(cudaMemsetAsync(blo.p, 0, sizeof(float) * (nbb + 64), c->stream));
+            B2_CUDA(make_companion(A, alo.as<float>(), na, bf, c->stream));
+            B2_CUDA(make_companion(B, blo.as<float>(), nbb, bf, c->stream));
+            g.A_lo = alo.as<float>(); g.B_lo = blo.as<float>(); g.bf16 = bf;
         }
         TcPlan plan;
         std::string err;
         if (!tc_plan_build(plan, g, err)) { set_error("tcgen05 plan: " + err); return B2NN_ERR_ARG; }
         cudaError_t le = tc_plan_launch(plan, c->stream);
-        if (backend & 4) cudaStreamSynchronize(c->stream);      // the temporaries are freed when this scope ends
+        if (backend & 12) cudaStreamSynchronize(c->stream);     // the temporaries are freed when this scope ends
         B2_CUDA(le);
         ++c->tc_launches;
     } else {

@@ -43,6 +43,9 @@ struct GemmDesc {
     // fp32-grade tensor-core mode (3xTF32): low parts x - trunc_tf32(x) of both operands, same layout and leading
     // dimension as A / B; D_lo (optional) receives the low part of the output.  Null = plain tf32.
     const float* A_lo = nullptr; const float* B_lo = nullptr; float* D_lo = nullptr;
+    // bf16 mode: the three companion pointers above hold BF16 copies (two bytes per element, same indexing and leading
+    // dimensions) and the contraction runs on them alone with kind::f16; D stays fp32, D_lo receives its bf16 copy.
+    bool bf16 = false;
     // Reduce-scatter fused into the epilogue (data parallel over peer memory): output rows n in [o*R, (o+1)*R) are stored
     // into scatter_base[o] + ((rank - o) * R + n) * ldd + m, i.e. into owner o's arena, slice `rank`.  R % tile_n == 0.
     float* scatter_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -59,6 +62,7 @@ struct TcPlan {
     alignas(64) CUtensorMap map_a_lo;
     alignas(64) CUtensorMap map_b_lo;
     bool x3 = false;
+    bool bf16 = false;
     GemmDesc g;
     int block_n = 0;          // tile N: 16, 32, 64, 128 or 256
     int stages = 0;
@@ -111,6 +115,11 @@ cudaError_t fill_launch(float* p, float v, int64_t count, cudaStream_t s);
 cudaError_t abs_sum_launch(const float* J, int64_t ld, int64_t rows, int K, double* out, cudaStream_t s);
 // lo[i] = x[i] - trunc_tf32(x[i])  (exact; what tcgen05 kind::tf32 drops from x)
 cudaError_t split_lo_launch(const float* x, float* lo, int64_t count, cudaStream_t s);
+// h[i] = bf16(x[i]), round to nearest even (h: two-byte elements)
+cudaError_t to_bf16_launch(const float* x, void* h, int64_t count, cudaStream_t s);
+// momentum update that also refreshes the bf16 copy of the weights
+cudaError_t momentum_update_bf16_launch(float* theta, float* vel, const float* grad, void* theta_h, int64_t count, float mu,
+                                        float alpha, cudaStream_t stream);
 // momentum update that also refreshes the low parts of the weights
 cudaError_t momentum_update_lo_launch(float* theta, float* vel, const float* grad, float* theta_lo, int64_t count, float mu,
                                       float alpha, cudaStream_t stream);

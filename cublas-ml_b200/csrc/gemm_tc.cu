@@ -27,6 +27,8 @@
 #include "ptx.cuh"
 #include "pdl.cuh"
 
+#include <cuda_bf16.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -47,9 +49,12 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_STAGE_BYTES = EPI_WARPS * 16 * 32 * 4;   // scatter mode: one 16-column x 32-row chunk per epilogue warp
 
-// bytes of the B tile ONE CTA stages: `rows` = N rows this CTA loads (BN, or BN/2 in a CTA pair)
-__host__ __device__ constexpr int b_tile_bytes(int rows, bool b_mn) {
-    return b_mn ? ((rows + 31) / 32) * ATOM_BYTES : rows * BK * 4;
+constexpr int ATOM_BYTES_BF = 64 * 64 * 2;   // bf16 mode: one MN-major box is 64 (mn) x 64 (k) two-byte elements
+
+// bytes of the B tile ONE CTA stages: `rows` = N rows this CTA loads (BN, or BN/2 in a CTA pair).  A K block is 128
+// bytes of K in every mode (32 floats or 64 bf16), so K-major tiles have the same size in all of them.
+__host__ __device__ constexpr int b_tile_bytes(int rows, bool b_mn, bool bf = false) {
+    return b_mn ? (bf ? ((rows + 63) / 64) * ATOM_BYTES_BF : ((rows + 31) / 32) * ATOM_BYTES) : rows * BK * 4;
 }
 
 struct TcArgs {
@@ -66,7 +71,8 @@ struct TcArgs {
     int atomic;                     // split-K: accumulate with red.global.add
     int d_trans;                    // store D[m * ldd + n] (row of this thread's TMEM lane, 32 consecutive columns)
     int stages;
-    uint32_t mn_lbo, mn_sbo, mn_layout;   // MN-major descriptor: 4096 / 512 / type 1 (overridable for bring-up)
+    uint32_t mn_lbo, mn_sbo, mn_layout;   // MN-major descriptor: 4096 / 512 / type 1 (tf32), 8192 / 1024 / type 2 (bf16)
+    uint32_t mn_kstep;                    // bytes one MMA K step advances an MN-major operand: 1024 (8 rows) / 2048 (16 rows)
     int a_3d, b_3d;                 // MN-major operand fetched with one 3-D TMA box per tile
     float* scatter_base[8];         // fused reduce-scatter: owner arenas (peer mappings); see GemmDesc
     int scatter_world, scatter_rank, scatter_rows;
@@ -111,18 +117,25 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f,
 // probe_tf32_rounding.py), so an fp32 array already is its own high part hi = x & 0xFFFFE000; the producers additionally
 // keep lo = x - hi (exact).  Each K step then issues A*B + A*B_lo + A_lo*B into the same fp32 accumulator; the dropped
 // lo*lo term is 2^-22 relative.  Four tiles per stage instead of two.
-template <int BN, bool A_MN, bool B_MN, int NCTA, bool X3>
+// MODE 0: kind::tf32 on the fp32 arrays.  MODE 1: fp32-grade 3xTF32 (fp32 arrays + their low-part companions).
+// MODE 2: kind::f16 with bf16 inputs — the operands are the bf16 COMPANION arrays (map_a / map_b describe those), a K block
+// is 64 elements, an MMA K step 16; accumulation and the stored output stay fp32, D_lo receives the bf16 copy of the output.
+template <int BN, bool A_MN, bool B_MN, int NCTA, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_lo, const TcArgs p) {
+    constexpr bool X3 = MODE == 1, BF = MODE == 2;
+    constexpr int BKE = BF ? 64 : 32;                       // elements per K block (128 bytes)
+    constexpr int MN_ATOM = BF ? 64 : 32;                   // contiguous M/N elements per MN-major box
+    constexpr int MN_BOX = BF ? ATOM_BYTES_BF : ATOM_BYTES; // bytes per MN-major box
     constexpr int B_ROWS = BN / NCTA;                       // N rows of B this CTA stages
-    constexpr int B_TILE = b_tile_bytes(B_ROWS, B_MN);
+    constexpr int B_TILE = b_tile_bytes(B_ROWS, B_MN, BF);
     constexpr int HALF_STAGE = A_TILE_BYTES + B_TILE;       // one (A, B) tile pair
     constexpr int STAGE_BYTES = X3 ? 2 * HALF_STAGE : HALF_STAGE;      // per CTA
     constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;        // TMEM columns of one accumulator buffer
     constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;            // 64 .. 512, always a power of two
-    constexpr uint32_t IDESC = umma_idesc_tf32(BM * NCTA, BN, A_MN, B_MN);
-    static_assert(!(B_MN && NCTA == 2 && BN < 64), "a CTA of a pair must stage whole 32-float atoms of B");
+    constexpr uint32_t IDESC = BF ? umma_idesc_bf16(BM * NCTA, BN, A_MN, B_MN) : umma_idesc_tf32(BM * NCTA, BN, A_MN, B_MN);
+    static_assert(!(B_MN && NCTA == 2 && (BN / 2) % MN_ATOM != 0), "a CTA of a pair must stage whole MN-major boxes of B");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -195,19 +208,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 uint8_t* sa = smem + size_t(s) * STAGE_BYTES;
                 uint8_t* sb = sa + A_TILE_BYTES;
                 uint64_t* bar = &full_bar[s];
-                const int kc = (kb0 + kb) * BK;
+                const int kc = (kb0 + kb) * BKE;
                 if (issuer) {
                     if (NCTA == 1) mbar_expect_tx(bar, STAGE_BYTES);
                     auto load_pair = [&](uint8_t* ta, uint8_t* tb, const CUtensorMap* ma, const CUtensorMap* mb) {
                         if (A_MN) {
                             if (p.a_3d) {
-                                if (NCTA == 2) tma_load_3d_pair(ta, ma, bar, 0, p.a_k0 + kc, (p.a_mn0 + m0) >> 5);
-                                else tma_load_3d(ta, ma, bar, 0, p.a_k0 + kc, (p.a_mn0 + m0) >> 5);
+                                if (NCTA == 2) tma_load_3d_pair(ta, ma, bar, 0, p.a_k0 + kc, (p.a_mn0 + m0) / MN_ATOM);
+                                else tma_load_3d(ta, ma, bar, 0, p.a_k0 + kc, (p.a_mn0 + m0) / MN_ATOM);
                             } else {
 #pragma unroll
-                                for (int i = 0; i < BM / 32; ++i) {
-                                    if (NCTA == 2) tma_load_2d_pair(ta + i * ATOM_BYTES, ma, bar, p.a_mn0 + m0 + i * 32, p.a_k0 + kc);
-                                    else tma_load_2d(ta + i * ATOM_BYTES, ma, bar, p.a_mn0 + m0 + i * 32, p.a_k0 + kc);
+                                for (int i = 0; i < BM / MN_ATOM; ++i) {
+                                    if (NCTA == 2) tma_load_2d_pair(ta + i * MN_BOX, ma, bar, p.a_mn0 + m0 + i * MN_ATOM, p.a_k0 + kc);
+                                    else tma_load_2d(ta + i * MN_BOX, ma, bar, p.a_mn0 + m0 + i * MN_ATOM, p.a_k0 + kc);
                                 }
                             }
                         } else {
@@ -216,13 +229,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                         if (B_MN) {
                             if (p.b_3d) {
-                                if (NCTA == 2) tma_load_3d_pair(tb, mb, bar, 0, p.b_k0 + kc, (p.b_mn0 + n0) >> 5);
-                                else tma_load_3d(tb, mb, bar, 0, p.b_k0 + kc, (p.b_mn0 + n0) >> 5);
+                                if (NCTA == 2) tma_load_3d_pair(tb, mb, bar, 0, p.b_k0 + kc, (p.b_mn0 + n0) / MN_ATOM);
+                                else tma_load_3d(tb, mb, bar, 0, p.b_k0 + kc, (p.b_mn0 + n0) / MN_ATOM);
                             } else {
 #pragma unroll
-                                for (int i = 0; i < (B_ROWS + 31) / 32; ++i) {
-                                    if (NCTA == 2) tma_load_2d_pair(tb + i * ATOM_BYTES, mb, bar, p.b_mn0 + n0 + i * 32, p.b_k0 + kc);
-                                    else tma_load_2d(tb + i * ATOM_BYTES, mb, bar, p.b_mn0 + n0 + i * 32, p.b_k0 + kc);
+                                for (int i = 0; i < (B_ROWS + MN_ATOM - 1) / MN_ATOM; ++i) {
+                                    if (NCTA == 2) tma_load_2d_pair(tb + i * MN_BOX, mb, bar, p.b_mn0 + n0 + i * MN_ATOM, p.b_k0 + kc);
+                                    else tma_load_2d(tb + i * MN_BOX, mb, bar, p.b_mn0 + n0 + i * MN_ATOM, p.b_k0 + kc);
                                 }
                             }
                         } else {
@@ -254,8 +267,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                           : umma_smem_desc(smem_base, 16, 1024);
             const uint64_t b_desc0 = B_MN ? umma_smem_desc(smem_base + A_TILE_BYTES, p.mn_lbo, p.mn_sbo, p.mn_layout)
                                           : umma_smem_desc(smem_base + A_TILE_BYTES, 16, 1024);
-            constexpr uint32_t A_KSTEP = (A_MN ? 1024 : UMMA_K * 4) >> 4;      // descriptor units of 16 bytes
-            constexpr uint32_t B_KSTEP = (B_MN ? 1024 : UMMA_K * 4) >> 4;
+            // one MMA K step = 32 bytes of K (8 floats / 16 bf16) on a K-major operand, 8 / 16 box rows on an MN-major one
+            const uint32_t A_KSTEP = (A_MN ? p.mn_kstep : uint32_t(UMMA_K * 4)) >> 4;      // descriptor units of 16 bytes
+            const uint32_t B_KSTEP = (B_MN ? p.mn_kstep : uint32_t(UMMA_K * 4)) >> 4;
             constexpr uint32_t STAGE_STEP = STAGE_BYTES >> 4;
             constexpr uint32_t LO_STEP = HALF_STAGE >> 4;
             const bool issuer = elect_one();
@@ -280,8 +294,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
                             auto mma = [&](uint64_t da, uint64_t db, uint32_t accumulate) {
-                                if (NCTA == 2) umma_tf32_pair(tmem_d, da, db, IDESC, accumulate);
-                                else umma_tf32(tmem_d, da, db, IDESC, accumulate);
+                                if (BF) { if (NCTA == 2) umma_f16_pair(tmem_d, da, db, IDESC, accumulate); else umma_f16(tmem_d, da, db, IDESC, accumulate); }
+                                else    { if (NCTA == 2) umma_tf32_pair(tmem_d, da, db, IDESC, accumulate); else umma_tf32(tmem_d, da, db, IDESC, accumulate); }
                             };
                             const uint64_t da = da0 + kk * A_KSTEP, db = db0 + kk * B_KSTEP;
                             mma(da, db, (kb | kk) != 0 ? 1u : 0u);
@@ -379,6 +393,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int j = 0; j < CH; ++j) {
                         if (n0 + c0 + j < p.N) *dlo = v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
                         dlo += p.ldd;
+                    }
+                }
+                if (BF && p.D_lo != nullptr && m_ok) {
+                    // bf16 copy of the output (round to nearest even): the operand of the next contraction that consumes it
+                    __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(p.D_lo) + int64_t(n0 + c0) * p.ldd + m;
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        if (n0 + c0 + j < p.N) *dh = __float2bfloat16_rn(v[j]);
+                        dh += p.ldd;
                     }
                 }
                 if (p.d_trans) {
@@ -483,16 +506,20 @@ void load_encode() {
 
 // Tensor map over the allocation that holds the operand.  The tensor extent ends where the sub-matrix ends, so
 // TMA's out-of-bounds zero fill supplies the K tail (wgrad: nothing past the batch is summed) and the M/N tails.
-bool encode_operand(CUtensorMap* map, const float* base, int64_t ld, bool mn_major, int64_t mn_end, int64_t k_end,
-                    int box_rows, bool as_3d, std::string& err) {
+bool encode_operand(CUtensorMap* map, const void* base, int64_t ld, bool mn_major, int64_t mn_end, int64_t k_end,
+                    int box_rows, bool as_3d, std::string& err, bool bf = false) {
+    const int64_t esz = bf ? 2 : 4;                // element size
+    const cuuint32_t atom = bf ? 64u : 32u;        // elements per 128-byte row of a box
+    const CUtensorMapDataType dt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) { err = "operand base not 16-byte aligned"; return false; }
-    if ((ld & 3) != 0) { err = "leading dimension not a multiple of 4 floats"; return false; }
+    if ((ld * esz) % 16 != 0) { err = "leading dimension not a multiple of 16 bytes"; return false; }
     const int64_t inner = mn_major ? mn_end : k_end;
     const int64_t outer = mn_major ? k_end : mn_end;
     if (inner <= 0 || outer <= 0 || inner > ld) { err = "operand extent inconsistent with leading dimension"; return false; }
     if (inner >= (int64_t(1) << 32) || outer >= (int64_t(1) << 32)) { err = "operand extent exceeds TMA limits"; return false; }
-    // MN-major fp32 tiles must use the 32-byte-chunk flavour of the 128-byte swizzle (see umma_smem_desc).
-    CUtensorMapSwizzle swz = mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    // MN-major fp32 tiles must use the 32-byte-chunk flavour of the 128-byte swizzle (see umma_smem_desc); two-byte
+    // elements take the ordinary 128-byte swizzle in both major-nesses.
+    CUtensorMapSwizzle swz = (mn_major && !bf) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
     if (mn_major) if (const char* e = std::getenv("B2NN_TC_MN_TMA_SWIZZLE")) swz = CUtensorMapSwizzle(std::atoi(e));
     CUresult r;
     if (mn_major && as_3d) {
@@ -500,18 +527,18 @@ bool encode_operand(CUtensorMap* map, const float* base, int64_t ld, bool mn_maj
         // single box {32, 32, box_rows/32} lands in shared memory exactly as box_rows/32 consecutive 2-D boxes would.
         // Elements of the last atom past mn_end alias the start of the next k-row (readable: rows are padded, arenas carry
         // slack); they only feed output rows / columns >= M / N, which the epilogue never stores.
-        cuuint64_t gdim[3] = {32u, cuuint64_t(outer), cuuint64_t((inner + 31) / 32)};
-        cuuint64_t gstride[2] = {cuuint64_t(ld) * 4, 128u};
-        cuuint32_t box[3] = {32u, 32u, cuuint32_t((box_rows + 31) / 32)};
+        cuuint64_t gdim[3] = {atom, cuuint64_t(outer), cuuint64_t((inner + atom - 1) / atom)};
+        cuuint64_t gstride[2] = {cuuint64_t(ld * esz), 128u};
+        cuuint32_t box[3] = {atom, atom, cuuint32_t((box_rows + atom - 1) / atom)};
         cuuint32_t estr[3] = {1u, 1u, 1u};
-        r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
+        r = g_encode(map, dt, 3, const_cast<void*>(base), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         cuuint64_t gdim[2] = {cuuint64_t(inner), cuuint64_t(outer)};
-        cuuint64_t gstride[1] = {cuuint64_t(ld) * 4};
-        cuuint32_t box[2] = {32u, cuuint32_t(mn_major ? 32 : box_rows)};
+        cuuint64_t gstride[1] = {cuuint64_t(ld * esz)};
+        cuuint32_t box[2] = {atom, cuuint32_t(mn_major ? atom : box_rows)};
         cuuint32_t estr[2] = {1u, 1u};
-        r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+        r = g_encode(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed, CUresult " + std::to_string(int(r)); return false; }
@@ -521,9 +548,9 @@ bool encode_operand(CUtensorMap* map, const float* base, int64_t ld, bool mn_maj
 int g_num_sms = 0;
 int g_reserved_sms = 0;      // SMs left free for a concurrent communication kernel (data parallel)
 
-template <int BN, bool A_MN, bool B_MN, int NCTA, bool X3>
+template <int BN, bool A_MN, bool B_MN, int NCTA, int MODE>
 cudaError_t launch_one(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NCTA, X3>;
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NCTA, MODE>;
     static std::atomic<unsigned long long> done{0};   // per instantiation, one bit per device
     if (cudaError_t e = ensure_dyn_smem(kern, SMEM_LIMIT, done)) return e;
     cudaLaunchConfig_t cfg{};
@@ -545,30 +572,35 @@ cudaError_t launch_one(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, kern, pl.map_a, pl.map_b, X3 ? pl.map_a_lo : pl.map_a, X3 ? pl.map_b_lo : pl.map_b, a);
+    return cudaLaunchKernelEx(&cfg, kern, pl.map_a, pl.map_b, MODE == 1 ? pl.map_a_lo : pl.map_a, MODE == 1 ? pl.map_b_lo : pl.map_b, a);
 }
 
-template <int BN, int NCTA, bool X3>
+// A CTA of a pair stages BN/2 columns of B; MN-major B comes in whole boxes of 32 (fp32) or 64 (bf16) columns.
+template <int BN, int NCTA, int MODE>
+constexpr bool b_mn_ok() { return NCTA == 1 ? (MODE == 2 ? BN >= 64 : BN >= 32) : (BN / 2) % (MODE == 2 ? 64 : 32) == 0; }
+
+template <int BN, int NCTA, int MODE>
 cudaError_t launch_majors(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
     const bool am = (pl.swapped ? pl.g.b_major : pl.g.a_major) != 0, bm = (pl.swapped ? pl.g.a_major : pl.g.b_major) != 0;
     if (am && bm) {
-        if constexpr (NCTA == 2 && BN < 64) return cudaErrorInvalidValue; else return launch_one<BN, true, true, NCTA, X3>(pl, a, stream);
+        if constexpr (!b_mn_ok<BN, NCTA, MODE>()) return cudaErrorInvalidValue; else return launch_one<BN, true, true, NCTA, MODE>(pl, a, stream);
     }
-    if (am && !bm) return launch_one<BN, true, false, NCTA, X3>(pl, a, stream);
+    if (am && !bm) return launch_one<BN, true, false, NCTA, MODE>(pl, a, stream);
     if (!am && bm) {
-        if constexpr (NCTA == 2 && BN < 64) return cudaErrorInvalidValue; else return launch_one<BN, false, true, NCTA, X3>(pl, a, stream);
+        if constexpr (!b_mn_ok<BN, NCTA, MODE>()) return cudaErrorInvalidValue; else return launch_one<BN, false, true, NCTA, MODE>(pl, a, stream);
     }
-    return launch_one<BN, false, false, NCTA, X3>(pl, a, stream);
+    return launch_one<BN, false, false, NCTA, MODE>(pl, a, stream);
 }
 
 template <int BN>
 cudaError_t launch_bn(const TcPlan& pl, const TcArgs& a, cudaStream_t stream) {
     if (pl.x3) {
         // the fp32-grade mode keeps 4 tiles per stage: a single CTA takes tiles up to 128 columns, a pair up to 256
-        if (pl.ncta == 2) return launch_majors<BN, 2, true>(pl, a, stream);
-        if constexpr (BN <= 128) return launch_majors<BN, 1, true>(pl, a, stream); else return cudaErrorInvalidValue;
+        if (pl.ncta == 2) return launch_majors<BN, 2, 1>(pl, a, stream);
+        if constexpr (BN <= 128) return launch_majors<BN, 1, 1>(pl, a, stream); else return cudaErrorInvalidValue;
     }
-    return pl.ncta == 2 ? launch_majors<BN, 2, false>(pl, a, stream) : launch_majors<BN, 1, false>(pl, a, stream);
+    if (pl.bf16) return pl.ncta == 2 ? launch_majors<BN, 2, 2>(pl, a, stream) : launch_majors<BN, 1, 2>(pl, a, stream);
+    return pl.ncta == 2 ? launch_majors<BN, 2, 0>(pl, a, stream) : launch_majors<BN, 1, 0>(pl, a, stream);
 }
 
 }  // namespace
@@ -623,18 +655,21 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& gu, std::string& err) {
 
     int bn;
     if (g.N > 128) bn = 256; else if (g.N > 64) bn = 128; else if (g.N > 32) bn = 64; else if (g.N > 16) bn = 32; else bn = 16;
-    if (g.b_major && bn < 32) bn = 32;     // an MN-major box is 32 floats wide
+    const bool bf = g.bf16 && g.A_lo != nullptr && g.B_lo != nullptr;       // bf16 mode: the companions ARE the operands
+    const int atom = bf ? 64 : 32;         // an MN-major box is 32 floats / 64 bf16 wide
+    if (g.b_major && bn < atom) bn = atom;
     if (plan.swapped) {
         // largest sample tile that still gives every SM one: the weights are re-read per tile, so wider is cheaper
         bn = 32;
         for (int cand : {256, 128, 64}) if ((int64_t(g.N) + cand - 1) / cand >= g_num_sms) { bn = cand; break; }
     }
-    plan.x3 = g.A_lo != nullptr && g.B_lo != nullptr;
+    plan.bf16 = bf;
+    plan.x3 = !bf && g.A_lo != nullptr && g.B_lo != nullptr;
     // CTA pairs (cta_group::2, 256-row tiles, each CTA stages half of B) whenever there are two 128-row tiles to pair:
     // 745 vs 692 TFLOP/s on 8192 x 4096 x 4097 (profiles/r1_gemm_pair.md).  B2NN_TC_NCTA=1 forces single CTAs.
     int ncta = g.M > BM ? 2 : 1;
     if (const char* e = std::getenv("B2NN_TC_NCTA")) { if (std::atoi(e) == 1) ncta = 1; }
-    if (g.b_major && bn < 64) ncta = 1;    // a CTA of a pair must stage whole 32-float atoms of B
+    if (g.b_major && bn < 2 * atom) ncta = 1;    // a CTA of a pair must stage whole MN-major boxes of B
     // 3xTF32 stages four tiles per k-block: 128 x 128 alone (3 stages), 256 x 256 as a pair (3 stages)
     if (plan.x3 && ncta == 1 && bn > 128) bn = 128;
     if (g.scatter_world > 0 && g.scatter_rows % bn != 0) { err = "scatter rows not a multiple of the tile"; return false; }
@@ -642,7 +677,7 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& gu, std::string& err) {
     plan.g = gu;
     plan.ncta = ncta;
 
-    const int stage_bytes = (A_TILE_BYTES + b_tile_bytes(bn / ncta, g.b_major != 0)) * (plan.x3 ? 2 : 1);
+    const int stage_bytes = (A_TILE_BYTES + b_tile_bytes(bn / ncta, g.b_major != 0, bf)) * (plan.x3 ? 2 : 1);
     // scatter mode stages its output chunks for bulk stores: 32 KB less for the operand ring (7 -> 6 stages of 32 KB)
     plan.scatter_bulk = g.scatter_world > 0 && !g.d_trans && (g.ldd % 4) == 0 && !std::getenv("B2NN_TC_NO_BULK");
     const int epi_bytes = plan.scatter_bulk ? EPI_STAGE_BYTES : 0;
@@ -652,7 +687,8 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& gu, std::string& err) {
     plan.stages = stages;
     plan.smem_bytes = size_t(stages) * stage_bytes + 1024 + 256 + epi_bytes;
 
-    plan.k_blocks_total = (g.K + BK - 1) / BK;
+    const int bke = bf ? 64 : BK;          // elements per 128-byte K block
+    plan.k_blocks_total = (g.K + bke - 1) / bke;
     plan.tiles_m = (g.M + BM * ncta - 1) / (BM * ncta);
     plan.tiles_n = (g.N + bn - 1) / bn;
     int usable_sms = g_num_sms - g_reserved_sms;
@@ -691,12 +727,14 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& gu, std::string& err) {
     // One 3-D box per MN-major tile needs the operand origin on a 32-float atom boundary (tile offsets always are) and
     // the folded view to stay inside memory the caller owns (mn_slack: the operand allocation is padded accordingly).
     const bool no3d = std::getenv("B2NN_TC_NO_3D") != nullptr;
-    plan.a_3d = g.a_major && g.mn_slack && !no3d && (g.a_mn0 % 32 == 0);
-    plan.b_3d = g.b_major && g.mn_slack && !no3d && (g.b_mn0 % 32 == 0);
-    if (!encode_operand(&plan.map_a, g.A, g.lda, g.a_major != 0, a_mn_end, a_k_end, BM, plan.a_3d, err)) return false;
+    plan.a_3d = g.a_major && g.mn_slack && !no3d && (g.a_mn0 % atom == 0);
+    plan.b_3d = g.b_major && g.mn_slack && !no3d && (g.b_mn0 % atom == 0);
+    const void* a_src = bf ? static_cast<const void*>(g.A_lo) : static_cast<const void*>(g.A);
+    const void* b_src = bf ? static_cast<const void*>(g.B_lo) : static_cast<const void*>(g.B);
+    if (!encode_operand(&plan.map_a, a_src, g.lda, g.a_major != 0, a_mn_end, a_k_end, BM, plan.a_3d, err, bf)) return false;
     const int64_t b_mn_end = g.b_mn_end > 0 ? g.b_mn_end : g.b_mn0 + g.N;
     const int64_t b_k_end = g.b_k_end > 0 ? g.b_k_end : g.b_k0 + g.K;
-    if (!encode_operand(&plan.map_b, g.B, g.ldb, g.b_major != 0, b_mn_end, b_k_end, bn / ncta, plan.b_3d, err)) return false;   // each CTA of a pair stages half of B
+    if (!encode_operand(&plan.map_b, b_src, g.ldb, g.b_major != 0, b_mn_end, b_k_end, bn / ncta, plan.b_3d, err, bf)) return false;   // each CTA of a pair stages half of B
     if (plan.x3) {
         if (!encode_operand(&plan.map_a_lo, g.A_lo, g.lda, g.a_major != 0, a_mn_end, a_k_end, BM, plan.a_3d, err)) return false;
         if (!encode_operand(&plan.map_b_lo, g.B_lo, g.ldb, g.b_major != 0, b_mn_end, b_k_end, bn / ncta, plan.b_3d, err)) return false;
@@ -710,7 +748,7 @@ cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream, const TcWait* 
     const GemmDesc g = effective_desc(pl.g, pl.swapped);
     TcArgs a;
     a.D = g.D; a.ldd = g.ldd; a.aux = g.aux; a.ldaux = g.ldaux;
-    a.D_lo = pl.x3 ? g.D_lo : nullptr;
+    a.D_lo = (pl.x3 || pl.bf16) ? g.D_lo : nullptr;
     for (int i = 0; i < 8; ++i) a.scatter_base[i] = g.scatter_base[i];
     a.scatter_world = g.scatter_world; a.scatter_rank = g.scatter_rank; a.scatter_rows = g.scatter_rows;
     a.scatter_bulk = pl.scatter_bulk ? 1 : 0;
@@ -732,7 +770,10 @@ cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream, const TcWait* 
     a.a_mn0 = int(g.a_mn0); a.a_k0 = int(g.a_k0); a.b_mn0 = int(g.b_mn0); a.b_k0 = int(g.b_k0);
     a.epi = g.epi; a.atomic = pl.splits > 1 ? 1 : 0; a.stages = pl.stages;
     a.a_3d = pl.a_3d ? 1 : 0; a.b_3d = pl.b_3d ? 1 : 0;
-    a.mn_lbo = ATOM_BYTES; a.mn_sbo = 512; a.mn_layout = 1;
+    a.mn_lbo = ATOM_BYTES; a.mn_sbo = 512; a.mn_layout = 1; a.mn_kstep = 1024;
+    // bf16 MN-major: boxes of 64 (mn) x 64 (k), ordinary 128-byte swizzle; 8-row groups 1024 B apart, boxes 8192 B apart
+    if (pl.bf16) { a.mn_lbo = ATOM_BYTES_BF; a.mn_sbo = 1024; a.mn_layout = 2; a.mn_kstep = 2048; }
+    if (const char* e = std::getenv("B2NN_TC_MN_KSTEP")) a.mn_kstep = uint32_t(std::atoi(e));
     if (const char* e = std::getenv("B2NN_TC_MN_LBO")) a.mn_lbo = uint32_t(std::atoi(e));   // bring-up knobs
     if (const char* e = std::getenv("B2NN_TC_MN_SBO")) a.mn_sbo = uint32_t(std::atoi(e));
     if (const char* e = std::getenv("B2NN_TC_MN_LAYOUT")) a.mn_layout = uint32_t(std::atoi(e));

@@ -117,6 +117,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same with 16-bit inputs (kind::f16; the instruction descriptor selects bf16), FP32 accumulate.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive on `bar` once every tcgen05.mma issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
@@ -212,6 +222,15 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a,
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Commit to the barrier at this offset in every CTA of `cta_mask` (0b11 = both CTAs of the pair).
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
     asm volatile(
@@ -242,6 +261,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, bool a_mn_m
     return (1u << 4)                               // D format: F32
            | (2u << 7)                             // A format: TF32
            | (2u << 10)                            // B format: TF32
+           | ((a_mn_major ? 1u : 0u) << 15)        // A major-ness (0 = K-major)
+           | ((b_mn_major ? 1u : 0u) << 16)        // B major-ness
+           | (static_cast<uint32_t>(N >> 3) << 17) // N / 8
+           | (static_cast<uint32_t>(M >> 4) << 24);// M / 16
+}
+
+// Instruction descriptor for kind::f16 with bf16 inputs, fp32 accumulate, dense, no negate.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
+    return (1u << 4)                               // D format: F32
+           | (1u << 7)                             // A format: BF16
+           | (1u << 10)                            // B format: BF16
            | ((a_mn_major ? 1u : 0u) << 15)        // A major-ness (0 = K-major)
            | ((b_mn_major ? 1u : 0u) << 16)        // B major-ness
            | (static_cast<uint32_t>(N >> 3) << 17) // N / 8

@@ -58,7 +58,10 @@ enum { B2NN_PREC_FP32 = 0 /* fp32 FFMA, matches cublasSgemm default math up to s
        B2NN_PREC_AUTO = 2 /* B2NN_PRECISION env var ("fp32" | "tf32" | "tf32x3" | "bf16"); default tf32x3 = fp32-grade, so a
                              drop-in caller keeps the reference's fp32 tolerance without asking                        */,
        B2NN_PREC_TF32X3 = 3 /* fp32-grade on tensor cores: every operand carries its tf32 remainder and each K step
-                               issues hi*hi + hi*lo + lo*hi (3 tcgen05.mma) into the fp32 TMEM accumulator            */ };
+                               issues hi*hi + hi*lo + lo*hi (3 tcgen05.mma) into the fp32 TMEM accumulator            */,
+       B2NN_PREC_BF16 = 4   /* tcgen05 kind::f16 on bf16 COPIES of the operands (8 mantissa bits, round to nearest even),
+                               fp32 accumulate; weights, velocity, gradients, activations and deltas stay fp32 — only the
+                               contractions read the bf16 copies.  OPT-IN, stated bound 6e-2 on the weights              */ };
 
 /* Function-pointer shapes of the reference's pluggable device ops (cublasNN.h:33, 45-50).  All pointers are DEVICE
  * pointers; the functions are HOST functions that enqueue work on the legacy default stream. */

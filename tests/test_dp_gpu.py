@@ -13,7 +13,7 @@ import pytest
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PREC = {"fp32": 0, "tf32": 1, "tf32x3": 3}
+PREC = {"fp32": 0, "tf32": 1, "tf32x3": 3, "bf16": 4}
 
 
 def _make_desc(b2nn, cases, c, prec, custom_act=False):
@@ -90,7 +90,7 @@ def _single(b2nn, name, prec):
 
 
 def _check(res, c, one, th1, prec):
-    tol = 2e-2 if prec == "tf32" else 2e-4
+    tol = {"tf32": 2e-2, "bf16": 6e-2}.get(prec, 2e-4)
     for r in res[1:]:
         assert np.array_equal(res[0][1], r[1]), "replicas diverged: every rank must hold identical weights"
     assert np.abs(res[0][1] - th1).max() <= tol * np.abs(th1).max()
@@ -114,7 +114,7 @@ def test_two_gpu_run_matches_single_gpu(b2nn, name, prec, p2p):
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("prec,p2p", [("tf32", True), ("tf32", False), ("tf32x3", True)])
+@pytest.mark.parametrize("prec,p2p", [("tf32", True), ("tf32", False), ("tf32x3", True), ("bf16", True)])
 def test_c4_mini_ranks_match_single_gpu(b2nn, world, prec, p2p):
     """Config C4 in miniature (nine weight layers): the per-layer flag schedule of the peer-memory exchange with a mix
     of fused layers (rows split into 256-column tiles per rank) and slot-buffer layers, at 2, 4 and 8 ranks."""

@@ -30,7 +30,7 @@ def _run(net, b2nn, backend, M, N, K, majors, epi=0, seed=0):
     gen = torch.Generator(device="cuda")
     gen.manual_seed(seed)
     a_major, b_major = majors
-    pad = 32 if backend in (3, 7) else 4
+    pad = {3: 32, 7: 32, 9: 8, 11: 64}.get(backend, 4)      # bf16 rows must start 16-byte aligned: ld % 8 == 0
     A, lda, Ad = _operand(M, K, a_major, gen, pad)
     B, ldb, Bd = _operand(N, K, b_major, gen, pad)
     ldd = (M + 3) // 4 * 4 + 8
@@ -104,6 +104,21 @@ def test_tcgen05_3xtf32_gemm_is_fp32_grade(net, b2nn, kind, shape, backend):
     tol = 2.0 ** -18 * bound + 1e-6
     bad = err > tol
     assert not bool(bad.any()), (kind, shape, float(err.max()), float((err / bound).max()), int(bad.sum()))
+
+
+@pytest.mark.parametrize("backend", [9, 11])
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("kind", list(MAJORS))
+def test_tcgen05_bf16_gemm_matches_fp64_within_bf16(net, b2nn, kind, shape, backend):
+    """bf16 mode: both operands rounded to nearest-even bf16 (8 mantissa bits: relative error <= 2^-9 each), fp32
+    accumulation in TMEM: |err| <= ~2^-8 * sum|a||b| per output element.  backend 11 = one 3-D TMA box per
+    M/N-contiguous tile (64-element boxes; NaN in the padding must never reach a stored output)."""
+    M, N, K = shape
+    got, ref, bound = _run(net, b2nn, backend, M, N, K, MAJORS[kind])
+    err = (got - ref).abs()
+    tol = 1.1 * 2.0 ** -8 * bound + 1e-5
+    bad = err > tol
+    assert not bool(bad.any()), (kind, shape, float(err.max()), int(bad.sum()), bad.nonzero()[:4].tolist())
 
 
 @pytest.mark.parametrize("epi", [1, 2, 3, 4])
