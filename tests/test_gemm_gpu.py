@@ -110,13 +110,13 @@ def test_tcgen05_3xtf32_gemm_is_fp32_grade(net, b2nn, kind, shape, backend):
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("kind", list(MAJORS))
 def test_tcgen05_bf16_gemm_matches_fp64_within_bf16(net, b2nn, kind, shape, backend):
-    """bf16 mode: both operands rounded to nearest-even bf16 (8 mantissa bits: relative error <= 2^-9 each), fp32
-    accumulation in TMEM: |err| <= ~2^-8 * sum|a||b| per output element.  backend 11 = one 3-D TMA box per
+    """bf16 mode: both operands rounded to nearest-even bf16 (8 significant bits: relative error <= 2^-8 each), fp32
+    accumulation in TMEM: |err| <= ~2^-7 * sum|a||b| per output element (reached only by short K: errors average out).  backend 11 = one 3-D TMA box per
     M/N-contiguous tile (64-element boxes; NaN in the padding must never reach a stored output)."""
     M, N, K = shape
     got, ref, bound = _run(net, b2nn, backend, M, N, K, MAJORS[kind])
     err = (got - ref).abs()
-    tol = 1.1 * 2.0 ** -8 * bound + 1e-5
+    tol = 1.05 * 2.0 ** -7 * bound + 1e-5
     bad = err > tol
     assert not bool(bad.any()), (kind, shape, float(err.max()), int(bad.sum()), bad.nonzero()[:4].tolist())
 
