@@ -390,13 +390,14 @@ def sec_c4(b2nn, local, rank, world, uuid, pk, pk_src, steps=4):
     net.close()
     fl = step_flops(layers, B) * world
     peak, note, capped = tensor_peak("tf32", ck.summary, pk, pk_src)
+    burst = pk.get("bf16_tflops", 1590.0) / 2.0
     tf = fl * r.steps / secs / 1e12
     return {"workload": WORKLOADS["c4"][2], "global_batch": B * world, "n_gpus": world, "ms_per_step": round(secs / r.steps * 1e3, 3),
             "samples_per_s": round(B * world * r.steps / secs), "steps": int(r.steps), "tflops": round(tf, 1),
             "precision": "tf32", "clocks": ck.summary, "replicas_identical": bool(same),
             "gradient_exchange": "peer-memory (fused)" if p2p_on else ("NCCL" if world > 1 else "none"),
             "roofline": {"bound": "tensor", "achieved": round(tf / world, 1), "peak": round(peak, 1), "unit": "TFLOP/s per GPU",
-                         "frac": round(tf / world / peak, 4), "peak_source": note,
+                         "frac": round(tf / world / peak, 4), "frac_of_burst": round(tf / world / burst, 4), "peak_source": note,
                          "regime": "sustained (power-capped)" if capped else "burst (boost clocks)",
                          "algorithmic_flops_per_step": fl}}
 
@@ -512,7 +513,11 @@ def run_ours(args):
         prof = net.profile_read()
         net.profile_enable(False)
     c2 = ck_roof.summary
-    peak, peak_note, capped = tensor_peak(args.precision, c2, pk, pk_src)
+    # Headline denominator: ALWAYS the burst figure (the timed region is tens of milliseconds; NVML's 4 ms samples of it
+    # flip between regimes from run to run).  The sustained figure is reported beside it (`frac_of_sustained`).
+    _, _, capped = tensor_peak(args.precision, c2, pk, pk_src)
+    peak, peak_note, _ = tensor_peak(args.precision, {"sm_mhz": None}, pk, pk_src)
+    peak_sus, _, _ = tensor_peak(args.precision, {"sm_mhz": 1, "sm_max_mhz": 1000}, pk, pk_src)
     gemm_ms = sum(prof[k]["ms"] for k in ("forward", "backprop", "wgrad"))
     gemm_fl = sum(prof[k]["flops"] for k in ("forward", "backprop", "wgrad"))
     gemm_launches = sum(prof[k]["launches"] for k in ("forward", "backprop", "wgrad"))
@@ -528,7 +533,8 @@ def run_ours(args):
         "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
         "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_flops_per_launch_mean": round(gemm_fl / max(gemm_launches, 1)), "peak_source": peak_note,
-        "regime": "sustained (power-capped)" if capped else "burst (boost clocks)", "clocks": c2,
+        "frac_of_sustained": round(achieved / peak_sus, 4), "peak_sustained": round(peak_sus, 1),
+        "regime_seen": "sustained (power-capped)" if capped else "burst (boost clocks)", "clocks": c2,
         "launches": gemm_launches, "avg_launch_ms": round(gemm_ms / max(gemm_launches, 1), 4),
         "share_of_step": round(gemm_ms / total_ms, 4) if total_ms > 0 else None,
         "whole_step": {"tflops": round(step_flops(layers, B) * K / secs / 1e12, 2),
@@ -583,12 +589,14 @@ def run_ours(args):
                     barrier(world)
                 s3 = max_over_ranks(o3.loop_seconds, world)
                 p3, n3, cap3 = tensor_peak(pname, ck3.summary, pk, pk_src)
+                burst3 = pk.get("bf16_tflops", 1590.0) / {"tf32x3": 6.0, "bf16": 1.0}[pname]
                 tf3 = step_flops(layers, B) * K / s3 / 1e12
                 secondary[key] = {
                     "value": round(B * world * K / s3, 1), "unit": "samples/s", "ms_per_step": round(s3 / K * 1e3, 4), "clocks": ck3.summary,
                     "roofline": {"bound": "tensor", "achieved": round(tf3, 2), "peak": round(p3, 1), "unit": "TFLOP/s", "frac": round(tf3 / p3, 4),
                                  "peak_source": n3, "regime": "sustained (power-capped)" if cap3 else "burst (boost clocks)",
-                                 "note": "whole step (every launch) over the mode's tensor peak"},
+                                 "frac_of_burst": round(tf3 / burst3, 4),
+                                 "note": "whole step (every launch) over the mode's tensor peak; the sustained figure of MEASURED_PEAKS.json was taken at 1297 MHz, a leg that ran between the two regimes can read above 1.0 of it"},
                     "e2e": e2e_leg(code), "note": note}
             except Exception as ex:  # noqa: BLE001
                 secondary[key] = {"value": None, "note": f"failed: {ex}"}

@@ -240,12 +240,29 @@ __global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ 
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) h[i] = __float2bfloat16_rn(x[i]);
 }
+// 22 B per weight: read v, g, theta (12), write v, theta (8) and the bf16 copy (2); four weights per thread and access.
 __global__ void __launch_bounds__(256) momentum_update_bf16_kernel(float* __restrict__ theta, float* __restrict__ vel,
                                                                    const float* __restrict__ grad, __nv_bfloat16* __restrict__ theta_h,
                                                                    int64_t count, float mu, float alpha) {
     pdl_enter();
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const int64_t n4 = count >> 2;
+    float4* th4 = reinterpret_cast<float4*>(theta);
+    float4* v4 = reinterpret_cast<float4*>(vel);
+    const float4* g4 = reinterpret_cast<const float4*>(grad);
+    uint2* h4 = reinterpret_cast<uint2*>(theta_h);
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = v4[i], t = th4[i];
+        const float4 g = __ldcs(g4 + i);
+        v.x = fmaf(mu, v.x, alpha * g.x); v.y = fmaf(mu, v.y, alpha * g.y);
+        v.z = fmaf(mu, v.z, alpha * g.z); v.w = fmaf(mu, v.w, alpha * g.w);
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        v4[i] = v;
+        th4[i] = t;
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y), hi = __floats2bfloat162_rn(t.z, t.w);
+        h4[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
+    for (int64_t i = (n4 << 2) + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
         const float v = fmaf(mu, vel[i], alpha * grad[i]);
         const float t = theta[i] + v;
         vel[i] = v;
@@ -408,8 +425,11 @@ cudaError_t to_bf16_launch(const float* x, void* h, int64_t count, cudaStream_t 
 cudaError_t momentum_update_bf16_launch(float* theta, float* vel, const float* grad, void* theta_h, int64_t count, float mu,
                                         float alpha, cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
-    const int64_t want = (count + 255) / 256;
-    return launch_pdl(momentum_update_bf16_kernel, dim3(unsigned(want < 148 * 16 ? want : 148 * 16)), dim3(256), 0, stream, theta, vel,
+    // the vector path needs 16-byte aligned fp32 arenas and an 8-byte aligned bf16 copy: layer offsets are multiples of 8 floats
+    if ((reinterpret_cast<uintptr_t>(theta) | reinterpret_cast<uintptr_t>(vel) | reinterpret_cast<uintptr_t>(grad)) & 15 ||
+        (reinterpret_cast<uintptr_t>(theta_h) & 7)) return cudaErrorInvalidValue;
+    const int64_t want = (count / 4 + 255) / 256 + 1;
+    return launch_pdl(momentum_update_bf16_kernel, dim3(unsigned(want < 148 * 8 ? want : 148 * 8)), dim3(256), 0, stream, theta, vel,
                       grad, static_cast<__nv_bfloat16*>(theta_h), count, mu, alpha);
 }
 cudaError_t abs_sum_launch(const float* J, int64_t ld, int64_t rows, int K, double* out, cudaStream_t s) {

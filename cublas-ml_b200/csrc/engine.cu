@@ -659,13 +659,8 @@ int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind, const TcW
     if (op.zero_first && !(d_is_grad && c->g_zero))
         B2_CUDA(cudaMemsetAsync(op.g.D, 0, sizeof(float) * size_t(op.g.ldd) * op.g.N, c->stream));
     if (op.tc) {
-        if (op.a_is_x && x_start != 0) {
-            TcPlan shifted = op.plan;   // tensor maps span the whole training matrix; only the coordinates move
-            if (op.g.a_major) shifted.g.a_mn0 += x_start; else shifted.g.a_k0 += x_start;
-            B2_CUDA(tc_plan_launch(shifted, c->stream, wait));
-        } else {
-            B2_CUDA(tc_plan_launch(op.plan, c->stream, wait));
-        }
+        // tensor maps span the whole training matrix; a batch start only moves the TMA coordinates
+        B2_CUDA(tc_plan_launch(op.plan, c->stream, wait, op.a_is_x ? x_start : 0));
         ++c->tc_launches;
     } else {
         GemmDesc g = op.g;
@@ -736,11 +731,13 @@ int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_d
                 a.a = c->ws.a[j - 1]; a.delta = c->ws.delta[j]; a.W = c->W + li.w_off; a.delta_prev = c->ws.delta[j - 1];
                 a.G = c->G + li.w_off; a.ld = c->ws.ld; a.ldw = li.ldw; a.rows = sp.rows; a.H = li.in; a.K = li.out; a.act_kind = d->act_kind;
                 if (!c->g_zero) B2_CUDA(cudaMemsetAsync(a.G, 0, sizeof(float) * size_t(li.ldw) * li.out, c->stream));
+                const bool have_comp = !c->ws.delta_lo.empty() && c->ws.delta_lo[j - 1];
+                if (have_comp && c->comp_bf16) a.delta_prev_bf16 = c->ws.delta_lo[j - 1];      // bf16 copy written in the same pass
                 B2_CUDA(skinny_bwd_launch(a, c->stream));
             }
             ++c->launches;
-            if (!c->ws.delta_lo.empty() && c->ws.delta_lo[j - 1])      // companion modes: the next contraction wants the low part / bf16 copy too
-                B2_CUDA(make_companion(c->ws.delta[j - 1], c->ws.delta_lo[j - 1], int64_t(li.in) * c->ws.ld, c->comp_bf16, c->stream));
+            if (!c->ws.delta_lo.empty() && c->ws.delta_lo[j - 1] && !c->comp_bf16)      // fp32-grade mode: the next contraction wants the low part too
+                B2_CUDA(make_companion(c->ws.delta[j - 1], c->ws.delta_lo[j - 1], int64_t(li.in) * c->ws.ld, false, c->stream));
             return post_gradient(j);
         }
         int rc = run_gemm(c, sp.bwd[j], 0, 1);

@@ -82,7 +82,7 @@ struct TcPlan {
 bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err);
 // Optional gate fused into the kernel: its TMA producer spins until flags[0 .. count) >= value before the first load.
 struct TcWait { const int* flags; int count; int value; };
-cudaError_t tc_plan_launch(const TcPlan& plan, cudaStream_t stream, const TcWait* wait = nullptr);
+cudaError_t tc_plan_launch(const TcPlan& plan, cudaStream_t stream, const TcWait* wait = nullptr, int64_t a_shift = 0);
 bool tc_runtime_ok(std::string& err);      // driver entry point for cuTensorMapEncodeTiled available?
 // Persistent GEMM grids leave `n` SMs unoccupied so a concurrent NCCL kernel is never queued behind a whole GEMM.
 void tc_set_reserved_sms(int n);
@@ -157,6 +157,7 @@ struct SkinnyArgs {
     const float* delta;        // K rows
     const float* W;            // K rows of ldw
     float* delta_prev;         // H rows
+    void* delta_prev_bf16 = nullptr;   // optional bf16 copy of delta_prev (same indexing, two-byte elements)
     float* G;                  // K rows of ldw
     int64_t ld, ldw, rows;
     int H, K, act_kind;

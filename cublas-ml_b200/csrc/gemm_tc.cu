@@ -743,9 +743,15 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& gu, std::string& err) {
     return true;
 }
 
-cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream, const TcWait* wait) {
+cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream, const TcWait* wait, int64_t a_shift) {
     if (!pl.valid) return cudaErrorInvalidValue;
-    const GemmDesc g = effective_desc(pl.g, pl.swapped);
+    GemmDesc g = effective_desc(pl.g, pl.swapped);
+    // a_shift: the caller's A operand (the training matrix) starts `a_shift` samples further on — only its TMA coordinates
+    // move, the tensor maps span the whole matrix.  (In the swapped plan the caller's A is this description's B.)
+    if (a_shift != 0) {
+        if (pl.swapped) { if (g.b_major) g.b_mn0 += a_shift; else g.b_k0 += a_shift; }
+        else            { if (g.a_major) g.a_mn0 += a_shift; else g.a_k0 += a_shift; }
+    }
     TcArgs a;
     a.D = g.D; a.ldd = g.ldd; a.aux = g.aux; a.ldaux = g.ldaux;
     a.D_lo = (pl.x3 || pl.bf16) ? g.D_lo : nullptr;

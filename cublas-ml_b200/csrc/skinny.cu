@@ -16,6 +16,7 @@
 //            added to the (pre-zeroed) gradient with one atomic per (k, unit) per block
 // Exact fp32 arithmetic in every precision mode.  HBM traffic: read a, write delta_prev = 8 B per element.
 #include "engine.h"
+#include <cuda_bf16.h>
 #include <cstdlib>
 #include "pdl.cuh"
 #include "../../include/b2nn.h"
@@ -136,9 +137,15 @@ __global__ void __launch_bounds__(SK_THREADS, 4) skinny_bwd_kernel(const SkinnyA
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int hh = h0 + warp * 4 + r;
-                if (hh < p.H)
-                    *reinterpret_cast<float4*>(p.delta_prev + int64_t(hh) * p.ld + sc) =
-                        *reinterpret_cast<const float4*>(a_s + (warp * 4 + r) * SK_PITCH + lane * 4);
+                if (hh < p.H) {
+                    const float4 v = *reinterpret_cast<const float4*>(a_s + (warp * 4 + r) * SK_PITCH + lane * 4);
+                    *reinterpret_cast<float4*>(p.delta_prev + int64_t(hh) * p.ld + sc) = v;
+                    if (p.delta_prev_bf16) {       // bf16 mode: the copy the next contractions read, written in the same pass
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.delta_prev_bf16) + int64_t(hh) * p.ld + sc) =
+                            make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                    }
+                }
             }
         }
         __syncthreads();                               // the tile after next streams into this buffer

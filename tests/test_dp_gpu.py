@@ -28,7 +28,7 @@ def _make_desc(b2nn, cases, c, prec, custom_act=False):
     return d
 
 
-def _worker(rank, world, port, name, prec_name, p2p, custom_act, q):
+def _worker(rank, world, port, name, prec_name, p2p, custom_act, q, relayer=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -50,6 +50,13 @@ def _worker(rank, world, port, name, prec_name, p2p, custom_act, q):
         net.comm_init(rank, world, dp.exchange_unique_id(b2nn.Net.comm_unique_id, rank, world))
         if p2p:
             assert dp.enable_peer_exchange(net, rank, world)
+        if relayer:
+            # a second set_layers with the peer exchange open: the engine closes its imports, meets the other ranks at a
+            # barrier, frees and reallocates the arenas; the exchange is then exported / opened again on the new arenas
+            net.set_layers([7, 300, 5], c.init_kind, 3)
+            net.set_layers(c.layers, c.init_kind, c.seed)
+            if p2p:
+                assert dp.enable_peer_exchange(net, rank, world)
         xl, yl, ml = dp.shard_training_set(x_cm, y_cm, c.m, n1, K, c.batch_num, rank, world)
         net.set_train_data(xl, yl, ml)
         out = net.train(_make_desc(b2nn, cases, c, prec_name, custom_act))
@@ -61,12 +68,12 @@ def _worker(rank, world, port, name, prec_name, p2p, custom_act, q):
         dist.destroy_process_group()
 
 
-def _run_world(world, name, prec, p2p, custom_act=False):
+def _run_world(world, name, prec, p2p, custom_act=False, relayer=False):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + (os.getpid() % 300) + world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, prec, p2p, custom_act, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, prec, p2p, custom_act, q, relayer)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
@@ -131,3 +138,12 @@ def test_custom_activation_under_peer_exchange(b2nn):
         pytest.skip("needs 2 GPUs")
     c, one, th1 = _single(b2nn, "wide_mini", "fp32")
     _check(_run_world(2, "wide_mini", "fp32", True, custom_act=True), c, one, th1, "fp32")
+
+
+def test_set_layers_again_with_peer_exchange_open(b2nn):
+    """b2nn_set_layers while peers hold IPC mappings of the old arenas (round-1 advisor finding): collective teardown,
+    then a fresh export / open; the run must still match the single-GPU trajectory with identical replicas."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    c, one, th1 = _single(b2nn, "wide_mini", "tf32")
+    _check(_run_world(2, "wide_mini", "tf32", True, relayer=True), c, one, th1, "tf32")
