@@ -210,6 +210,10 @@ struct b2nn_ctx {
     cudaEvent_t p2p_upd_done = nullptr;
     std::vector<void*> p2p_opened;
 
+    // single GPU, large nets: per-layer momentum updates on the exchange stream, under the remaining backward GEMMs
+    bool ov_active = false; float ov_mu = 0.f, ov_alpha = 0.f; int ov_prec = 0;
+    std::vector<cudaEvent_t> ov_ev; cudaEvent_t ov_done = nullptr;
+
     int64_t launches = 0, tc_launches = 0;
 
     // B2NN_TRACE=1: CUDA-event timeline of the last steps of a train call (both streams), printed to stderr when it ends
@@ -772,9 +776,31 @@ int backward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_d
     }
     // Single GPU / NCCL: G_j right after delta_j (the reference computes all deltas, then all gradients, :670-684), so its
     // all-reduce overlaps the backprop of the earlier layers.
+    // ... and (single GPU, large nets) the momentum update of layer j leaves for the exchange stream the moment G_j exists
+    // and W_j has been read for the last time: a <= 32-register streaming kernel that becomes resident next to the
+    // persistent GEMM CTAs and uses the HBM bandwidth the tensor-bound contractions leave idle.  Only the input layer's
+    // (small) update is still exposed at the end of the step.
+    auto overlapped_update = [&](int j) -> int {
+        if (!c->ov_active) return B2NN_OK;
+        const LayerInfo& li = c->L[j];
+        const int64_t cnt = li.ldw * li.out;
+        B2_CUDA(cudaEventRecord(c->ov_ev[j], c->stream));
+        B2_CUDA(cudaStreamWaitEvent(c->upd_stream, c->ov_ev[j], 0));
+        if (c->ov_prec == B2NN_PREC_BF16 && c->W_lo)
+            B2_CUDA(momentum_update_bf16_launch(c->W + li.w_off, c->V + li.w_off, c->G + li.w_off, comp_at(c->W_lo, li.w_off, true), cnt,
+                                                c->ov_mu, c->ov_alpha, c->upd_stream));
+        else if (c->ov_prec == B2NN_PREC_TF32X3 && c->W_lo)
+            B2_CUDA(momentum_update_lo_launch(c->W + li.w_off, c->V + li.w_off, c->G + li.w_off, c->W_lo + li.w_off, cnt, c->ov_mu,
+                                              c->ov_alpha, c->upd_stream));
+        else
+            B2_CUDA(momentum_update_launch(c->W + li.w_off, c->V + li.w_off, c->G + li.w_off, cnt, c->ov_mu, c->ov_alpha, c->upd_stream));
+        ++c->launches;
+        return B2NN_OK;
+    };
     for (int j = nw - 1; j >= 0; --j) {
         int rc = grad_step(j);
         if (!rc) rc = delta_step(j);
+        if (!rc) rc = overlapped_update(j);
         if (rc) return rc;
     }
     return B2NN_OK;
@@ -985,8 +1011,22 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
         if (sp.use_tail)
             B2_CUDA(make_companion(c->ws.delta[nwl - 2], c->ws.delta_lo[nwl - 2], int64_t(c->L[nwl - 1].in) * c->ws.ld, c->comp_bf16, c->stream));
     }
+    {
+        // overlapped per-layer updates (see backward_pass): single GPU, built-in functions, nets too large for the
+        // graph-replayed small-net path, not while per-launch profiling or capturing
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        (void)cudaStreamIsCapturing(c->stream, &cap);
+        c->ov_active = !c->comm && d->act_kind != B2NN_ACT_CUSTOM && c->total_int > (int64_t(1) << 20) && !c->profile &&
+                       cap == cudaStreamCaptureStatusNone && !std::getenv("B2NN_NO_OVERLAP_UPDATE");
+        if (c->ov_active) {
+            if (!c->upd_stream) B2_CUDA(cudaStreamCreateWithFlags(&c->upd_stream, cudaStreamNonBlocking));
+            if (!c->ov_done) B2_CUDA(cudaEventCreateWithFlags(&c->ov_done, cudaEventDisableTiming));
+            while (c->ov_ev.size() < c->L.size()) { cudaEvent_t e; B2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ov_ev.push_back(e); }
+            c->ov_mu = d->momentum; c->ov_alpha = -d->rate / float(global_rows); c->ov_prec = prec;
+        }
+    }
     rc = backward_pass(c, sp, x_start, d);
-    if (rc) return rc;
+    if (rc) { c->ov_active = false; return rc; }
     trace_mark(c, "bwd_done", -1, c->stream);
     }
     const float alpha = -d->rate / float(global_rows);      // cublasNN.cpp:544, 601
@@ -1055,6 +1095,11 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
             }
             ++c->launches;
         }
+    } else if (c->ov_active) {
+        // every layer's update is already running (or done) on the exchange stream: the next step starts behind the last one
+        c->ov_active = false;
+        B2_CUDA(cudaEventRecord(c->ov_done, c->upd_stream));
+        B2_CUDA(cudaStreamWaitEvent(c->stream, c->ov_done, 0));
     } else {
         // all layers in one pass: W, V, G share one arena layout (cublasNN.cpp:558-566 is 2 launches per layer)
         {
@@ -1316,6 +1361,8 @@ void b2nn_destroy(b2nn_ctx* c) {
     for (auto e : c->log_events) cudaEventDestroy(e);
     for (auto& r : c->prof) { if (r.own_e0) cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : c->prof_pool) cudaEventDestroy(e);
+    for (auto e : c->ov_ev) cudaEventDestroy(e);
+    if (c->ov_done) cudaEventDestroy(c->ov_done);
     for (auto e : c->grad_ready) cudaEventDestroy(e);
     for (auto e : c->grad_reduced) cudaEventDestroy(e);
     if (c->gen) curandDestroyGenerator(c->gen);
