@@ -178,6 +178,7 @@ struct b2nn_ctx {
     // while they are staged (b2nn_set_train_data_raw, b2nn_evaluate_raw, b2nn_predict_raw)
     float* d_mean = nullptr; float* d_std = nullptr; int norm_n = 0;
 
+    int* out_counters = nullptr; int out_counters_cap = 0;      // fused output layer: one self-resetting counter per 32-sample slice
     float* m3_partial = nullptr; int64_t m3_partial_cap = 0;    // per-block partial gradients of the one-hidden-layer kernel (mlp3.cu)
 
     Workspace ws;
@@ -657,14 +658,14 @@ struct ProfScope {
     ~ProfScope() { if (on) { cudaEventRecord(c->prof.back().e1, c->stream); c->prof_chain = true; } }
 };
 
-int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind, const TcWait* wait = nullptr) {
+int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind, const TcWait* wait = nullptr, const TcOutput* out = nullptr) {
     ProfScope scope(c, kind, op.tc, 2.0 * double(op.g.M) * double(op.g.N) * double(op.g.K), 0.0);
     const bool d_is_grad = op.g.D >= c->G && op.g.D < c->G + c->total_int;
     if (op.zero_first && !(d_is_grad && c->g_zero))
         B2_CUDA(cudaMemsetAsync(op.g.D, 0, sizeof(float) * size_t(op.g.ldd) * op.g.N, c->stream));
     if (op.tc) {
         // tensor maps span the whole training matrix; a batch start only moves the TMA coordinates
-        B2_CUDA(tc_plan_launch(op.plan, c->stream, wait, op.a_is_x ? x_start : 0));
+        B2_CUDA(tc_plan_launch(op.plan, c->stream, wait, op.a_is_x ? x_start : 0, out));
         ++c->tc_launches;
     } else {
         GemmDesc g = op.g;
@@ -678,7 +679,7 @@ int run_gemm(b2nn_ctx* c, const GemmOp& op, int64_t x_start, int kind, const TcW
 }
 
 // forwardPropagate (cublasNN.cpp:642-661) over rows [x_start, x_start+rows) of X; leaves z_{L-2} in ws.z_last.
-int forward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_desc* d, int gate_step = 0) {
+int forward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_desc* d, int gate_step = 0, const TcOutput* out = nullptr) {
     const int nw = int(sp.fwd.size()) - (sp.use_tail ? 1 : 0);      // the tail kernel owns the last layer
     const bool custom = d->act_kind == B2NN_ACT_CUSTOM;
     for (int j = 0; j < nw; ++j) {
@@ -686,7 +687,8 @@ int forward_pass(b2nn_ctx* c, StepPlan& sp, int64_t x_start, const b2nn_train_de
         TcWait wait{c->p2p_flags + (1 * P2P_MAX_LAYERS + j) * P2P_MAX_WORLD, c->nranks, gate_step};
         if (gate_step > 0 && sp.fwd_waits[j] == 1)
             B2_CUDA(p2p_gate_launch(wait.flags, wait.count, wait.value, c->stream));
-        int rc = run_gemm(c, sp.fwd[j], x_start, 0, (gate_step > 0 && sp.fwd_waits[j] == 2) ? &wait : nullptr);
+        int rc = run_gemm(c, sp.fwd[j], x_start, 0, (gate_step > 0 && sp.fwd_waits[j] == 2) ? &wait : nullptr,
+                          j == int(sp.fwd.size()) - 1 ? out : nullptr);      // the output layer rides in the last contraction's epilogue
         if (rc) return rc;
         if (custom && j < int(sp.fwd.size()) - 1) {
             // User activation: a host function that launches on the legacy default stream (cublasNN.cpp:648, 655).  The
@@ -998,10 +1000,37 @@ int train_step(b2nn_ctx* c, const b2nn_train_desc* d, int prec, const float* X, 
         c->w_lo_valid = false;
         return B2NN_OK;
     } else {
-    rc = forward_pass(c, sp, x_start, d, (any_fused && c->p2p_step > 1) ? c->p2p_step - 1 : 0);
+    // Output layer fused into the epilogue of the last forward contraction (north_star: "the softmax+NLL gradient fused into
+    // the epilogues") when that contraction is a tcgen05 launch with a single column tile of <= 16 units (configs C3, C4):
+    // with split-K the warp that adds the last partial sums of a 32-sample slice finishes the slice.
+    TcOutput fused_out{};
+    bool fuse_out = false;
+    {
+        const GemmOp& lastf = sp.fwd.back();
+        const int Kout = c->layers.back();
+        fuse_out = !custom_oc && !sp.use_tail && lastf.tc && !lastf.plan.swapped && lastf.plan.tiles_n == 1 && Kout <= 16 &&
+                   lastf.g.epi == EPI_STORE && !std::getenv("B2NN_NO_FUSED_OUTPUT");
+        if (fuse_out) {
+            const int need = lastf.plan.tiles_m * lastf.plan.ncta * 4;
+            if (need > c->out_counters_cap) {
+                B2_CUDA(cudaStreamSynchronize(c->stream));
+                cudaFree(c->out_counters); c->out_counters = nullptr; c->out_counters_cap = 0;
+                B2_CUDA(cudaMalloc(&c->out_counters, sizeof(int) * size_t(need)));
+                B2_CUDA(cudaMemset(c->out_counters, 0, sizeof(int) * size_t(need)));
+                c->out_counters_cap = need;
+            }
+            fused_out.y = Y + x_start; fused_out.ldy = ldy;
+            fused_out.delta = c->ws.delta[c->L.size() - 1]; fused_out.ldd = c->ws.ld;
+            fused_out.cost_sum = cost_slot; fused_out.counters = c->out_counters;
+            fused_out.out_kind = d->classify ? d->out_kind : B2NN_OUT_LINEAR;
+            fused_out.cost_kind = d->classify ? d->cost_kind : B2NN_COST_SQUARED;
+        }
+    }
+    rc = forward_pass(c, sp, x_start, d, (any_fused && c->p2p_step > 1) ? c->p2p_step - 1 : 0, fuse_out ? &fused_out : nullptr);
     if (rc) return rc;
     trace_mark(c, "fwd_done", -1, c->stream);
-    if (custom_oc) rc = output_custom(c, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
+    if (fuse_out) rc = B2NN_OK;
+    else if (custom_oc) rc = output_custom(c, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
     else if (sp.use_tail) rc = run_tail(c, sp, d, Y + x_start, ldy, rows, true, cost_slot, nullptr, nullptr, nullptr, nullptr, 0);
     else rc = output_and_delta(c, d, Y + x_start, ldy, rows, cost_slot);
     if (rc) return rc;
@@ -1339,7 +1368,7 @@ void b2nn_destroy(b2nn_ctx* c) {
     cudaFree(c->X); cudaFree(c->Y); cudaFree(c->Xs); cudaFree(c->Ys); cudaFree(c->Xsp); cudaFree(c->Ysp);
     cudaFree(c->d_acc);
     cudaFree(c->d_mean); cudaFree(c->d_std);
-    cudaFree(c->m3_partial);
+    cudaFree(c->m3_partial); cudaFree(c->out_counters);
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->pr_x[i]); cudaFree(c->pr_p[i]); cudaFree(c->pr_h[i]);
         if (c->pr_hx[i]) cudaFreeHost(c->pr_hx[i]);

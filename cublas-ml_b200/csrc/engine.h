@@ -82,7 +82,19 @@ struct TcPlan {
 bool tc_plan_build(TcPlan& plan, const GemmDesc& g, std::string& err);
 // Optional gate fused into the kernel: its TMA producer spins until flags[0 .. count) >= value before the first load.
 struct TcWait { const int* flags; int count; int value; };
-cudaError_t tc_plan_launch(const TcPlan& plan, cudaStream_t stream, const TcWait* wait = nullptr, int64_t a_shift = 0);
+// Output layer fused into the last forward contraction (N <= 16 output units, training): the epilogue warp that completes
+// a 32-sample slice — with split-K the LAST of the splits to add its partial sums, found through a self-resetting counter —
+// applies the output activation, writes delta = h - y and sums the cost (activations.cu:68-88, kernels.cu:46-51,
+// costfunctions.cu:14-26 in the epilogue of cublasNN.cpp:658-659's contraction).
+struct TcOutput {
+    const float* y; int64_t ldy;      // targets, laid out like D (unit-major)
+    float* delta; int64_t ldd;        // h - y
+    double* cost_sum;                 // += per-element cost in double (may be null)
+    int* counters;                    // one per 32-sample slice, zero between launches
+    int out_kind, cost_kind;
+};
+cudaError_t tc_plan_launch(const TcPlan& plan, cudaStream_t stream, const TcWait* wait = nullptr, int64_t a_shift = 0,
+                           const TcOutput* out = nullptr);
 bool tc_runtime_ok(std::string& err);      // driver entry point for cuTensorMapEncodeTiled available?
 // Persistent GEMM grids leave `n` SMs unoccupied so a concurrent NCCL kernel is never queued behind a whole GEMM.
 void tc_set_reserved_sms(int n);

@@ -26,6 +26,7 @@
 #include "epilogue.cuh"
 #include "ptx.cuh"
 #include "pdl.cuh"
+#include "../../include/b2nn.h"
 
 #include <cuda_bf16.h>
 
@@ -80,6 +81,7 @@ struct TcArgs {
     int scatter_bulk;               // scatter mode: tiles leave through bulk asynchronous stores staged in shared memory
     const int* wait_flags;          // data parallel over peer memory: the weights this contraction reads are complete once
     int wait_count, wait_value;     // wait_flags[0 .. wait_count) >= wait_value (one flag per owner rank, written by the owners)
+    TcOutput out;                   // fused output layer (out.counters != nullptr): see engine.h
 };
 
 // Work item -> output tile.  Tiles are walked in groups of `group_m` row-tiles: inside a group the row-tile index is
@@ -104,6 +106,54 @@ __device__ __forceinline__ void decode_tile(int rem, int tiles_m, int tiles_n, i
 // the tf32 rounding of the contraction they follow.  The fp32 FFMA path keeps expf / tanhf (epilogue.cuh).
 __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// Output layer of one 32-sample slice (lane = sample), called by the epilogue warp that completed the slice's z: output
+// activation (max-shifted softmax like output_layer_kernel), delta = h - y, cost summed in double.  Kept out of line: its
+// registers must not count against the 576-thread GEMM kernel's budget; it runs once per slice.
+__device__ __noinline__ void fused_output_slice(const float* __restrict__ y, int64_t ldy, float* __restrict__ delta, int64_t ldd,
+                                                double* cost_sum, int out_kind, int cost_kind, const float* __restrict__ Z,
+                                                int64_t ldz, int K, int m, bool m_ok, int lane) {
+    struct { const float* y; int64_t ldy; float* delta; int64_t ldd; double* cost_sum; int out_kind, cost_kind; } o{y, ldy, delta, ldd, cost_sum, out_kind, cost_kind};
+    double cost = 0.0;
+    if (m_ok) {
+        float zv[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) zv[k] = k < K ? __ldcg(Z + int64_t(k) * ldz + m) : -INFINITY;
+        float zmax = -INFINITY, total = 0.f;
+        if (o.out_kind == B2NN_OUT_SOFTMAX) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) zmax = fmaxf(zmax, zv[k]);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) if (k < K) { zv[k] = expf(zv[k] - zmax); total += zv[k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k < K) {
+                float h;
+                if (o.out_kind == B2NN_OUT_SOFTMAX) h = zv[k] / total;
+                else if (o.out_kind == B2NN_OUT_SIGMOID) h = 1.0f / (1.0f + expf(-zv[k]));
+                else h = zv[k];
+                const float yv = __ldg(o.y + int64_t(k) * o.ldy + m);
+                const float dv = h - yv;
+                o.delta[int64_t(k) * o.ldd + m] = dv;
+                if (o.cost_sum) {
+                    float cst = 0.f;
+                    if (o.cost_kind == B2NN_COST_SQUARED) cst = dv * dv;
+                    else {
+                        if (yv != 0.f) cst += -yv * logf(h);
+                        if (o.cost_kind == B2NN_COST_NEGLNMAX && yv != 1.f) cst += -(1.f - yv) * logf(1.f - h);
+                        cst = fabsf(cst);
+                    }
+                    cost += double(cst);
+                }
+            }
+        }
+    }
+    if (o.cost_sum) {
+        for (int s = 16; s > 0; s >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, s);
+        if (lane == 0 && cost != 0.0) atomicAdd(o.cost_sum, cost);
+    }
+}
 
 // Persistent, warp-specialised tcgen05 GEMM.  NCTA = 1: one CTA per 128 x BN tile.  NCTA = 2: a CTA pair (cluster of
 // two, cta_group::2) per 256 x BN tile — each CTA stages its own 128 rows of A and HALF of B, so the L2 -> shared
@@ -472,6 +522,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (NCTA == 2) mbar_arrive_remote(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
+
+            // ---- fused output layer: the warp whose partial sums complete this 32-sample slice finishes it ----
+            if (p.out.counters != nullptr && c_begin == 0) {
+                const int slice = (tile_m * NCTA + int(rank)) * 4 + q;
+                __threadfence();                                   // this warp's red.adds / stores of z are performed
+                int last = 0;
+                if (lane == 0) last = atomicAdd(p.out.counters + slice, 1) == p.splits - 1;
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    __threadfence();
+                    fused_output_slice(p.out.y, p.out.ldy, p.out.delta, p.out.ldd, p.out.cost_sum, p.out.out_kind, p.out.cost_kind, Dp, p.ldd,
+                                       p.N, m, m_ok, lane);
+                    if (lane == 0) p.out.counters[slice] = 0;      // ready for the next launch
+                }
+            }
         }
         if (p.scatter_bulk) bulk_wait_all();       // every queued store has been performed before the kernel retires
     }
@@ -743,7 +808,7 @@ bool tc_plan_build(TcPlan& plan, const GemmDesc& gu, std::string& err) {
     return true;
 }
 
-cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream, const TcWait* wait, int64_t a_shift) {
+cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream, const TcWait* wait, int64_t a_shift, const TcOutput* out) {
     if (!pl.valid) return cudaErrorInvalidValue;
     GemmDesc g = effective_desc(pl.g, pl.swapped);
     // a_shift: the caller's A operand (the training matrix) starts `a_shift` samples further on — only its TMA coordinates
@@ -758,6 +823,12 @@ cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream, const TcWait* 
     for (int i = 0; i < 8; ++i) a.scatter_base[i] = g.scatter_base[i];
     a.scatter_world = g.scatter_world; a.scatter_rank = g.scatter_rank; a.scatter_rows = g.scatter_rows;
     a.scatter_bulk = pl.scatter_bulk ? 1 : 0;
+    a.out = TcOutput{};
+    if (out) {
+        // one column tile, plain store / split-K epilogue, samples on the TMEM lanes
+        if (pl.swapped || pl.tiles_n != 1 || g.N > 16 || g.epi != EPI_STORE || g.d_trans) return cudaErrorInvalidValue;
+        a.out = *out;
+    }
     a.wait_flags = wait ? wait->flags : nullptr; a.wait_count = wait ? wait->count : 0; a.wait_value = wait ? wait->value : 0;
     a.n_rot = 0;
     if (g.scatter_world > 1 && !std::getenv("B2NN_TC_NO_ROT"))
