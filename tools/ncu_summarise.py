@@ -29,7 +29,7 @@ def main():
     idx = {h: i for i, h in enumerate(hdr)}
     names = {"gemm_tc_kernel<256, 1, 0": "fwd", "gemm_tc_kernel<16, 1, 0": "fwd_last", "gemm_tc_kernel<256, 0, 0": "wgrad",
              "gemm_tc_kernel<256, 1, 1": "bwd", "output_layer": "output", "skinny_bwd": "skinny_bwd (delta + gradient of the 10-unit layer)",
-             "momentum_update": "update", "mlp3_kernel": "mlp3 step", "mlp3_reduce_update": "mlp3 reduce+update"}
+             "momentum_update": "update (per layer, second stream)", "mlp3_kernel": "mlp3 step", "mlp3_reduce_update": "mlp3 reduce+update"}
     lines, total, per_launch = [], 0.0, {}
     for r in rows[2:]:
         k = r[idx["Kernel Name"]]
