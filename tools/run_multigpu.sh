@@ -2,6 +2,7 @@
 # One multi-GPU session (run under `gpurun --gpus 8`): the data-parallel parity tests at 2 / 4 / 8 ranks, then bench.py
 # at N = 8 and N = 4 — the evidence behind the scaling rows of BASELINE.md.  Logs land in gpurun_out/ (copied to profiles/).
 nvidia-smi -L | wc -l
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/r2_smoke.log
 timeout 600 python -m pytest tests/test_dp_gpu.py -m gpu -q -k "c4_mini or custom" > gpurun_out/r2_pytest_dp_8gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r2_pytest_dp_8gpu.log
 tail -3 gpurun_out/r2_pytest_dp_8gpu.log
