@@ -158,7 +158,8 @@ struct b2nn_ctx {
     // double-buffered staging of b2nn_train_host (streaming trainer)
     float* Xst[2] = {nullptr, nullptr}; float* Yst[2] = {nullptr, nullptr}; int64_t ldst = 0, capst = 0;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t st_copied[2] = {nullptr, nullptr}, st_consumed[2] = {nullptr, nullptr};
+    cudaStream_t loss_stream = nullptr;        // per-step loss read-back of b2nn_train_host (keeps the DMA off the compute stream)
+    cudaEvent_t st_copied[2] = {nullptr, nullptr}, st_consumed[2] = {nullptr, nullptr}, st_loss = nullptr;
     double* d_jsteps = nullptr; double* h_jsteps = nullptr; int64_t jsteps_cap = 0;
 
     // staging of b2nn_predict (kept between calls: small-batch inference is otherwise dominated by cudaMalloc/cudaFree)
@@ -1386,6 +1387,8 @@ void b2nn_destroy(b2nn_ctx* c) {
     cudaFree(c->d_jsteps);
     if (c->h_jsteps) cudaFreeHost(c->h_jsteps);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->loss_stream) cudaStreamDestroy(c->loss_stream);
+    if (c->st_loss) cudaEventDestroy(c->st_loss);
     if (c->h_acc) cudaFreeHost(c->h_acc);
     for (auto e : c->log_events) cudaEventDestroy(e);
     for (auto& r : c->prof) { if (r.own_e0) cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -1944,6 +1947,10 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
     const int64_t steps = int64_t(d->iters) * nb;
 
     if (!c->copy_stream) B2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->loss_stream) B2_CUDA(cudaStreamCreateWithFlags(&c->loss_stream, cudaStreamNonBlocking));
+    if (!c->st_loss) B2_CUDA(cudaEventCreateWithFlags(&c->st_loss, cudaEventDisableTiming));
+    // the 8-byte loss copies ride their own stream: a DMA between two steps on the compute stream costs a bubble per step
+    const bool loss_inline = std::getenv("B2NN_LOSS_D2H_INLINE") != nullptr;
     for (int i = 0; i < 2; ++i) {
         if (!c->st_copied[i]) B2_CUDA(cudaEventCreateWithFlags(&c->st_copied[i], cudaEventDisableTiming));
         if (!c->st_consumed[i]) B2_CUDA(cudaEventCreateWithFlags(&c->st_consumed[i], cudaEventDisableTiming));
@@ -2022,7 +2029,13 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
                         c->d_jsteps + s);
         if (rc) return rc;
         B2_CUDA(cudaEventRecord(c->st_consumed[buf], c->stream));
-        B2_CUDA(cudaMemcpyAsync(c->h_jsteps + s, c->d_jsteps + s, sizeof(double), cudaMemcpyDeviceToHost, c->stream));   // this step's loss
+        cudaStream_t ls = loss_inline ? c->stream : c->loss_stream;
+        if (!loss_inline) B2_CUDA(cudaStreamWaitEvent(ls, c->st_consumed[buf], 0));
+        B2_CUDA(cudaMemcpyAsync(c->h_jsteps + s, c->d_jsteps + s, sizeof(double), cudaMemcpyDeviceToHost, ls));   // this step's loss
+    }
+    if (!loss_inline) {          // the timed region (and the caller) ends after the last loss has landed
+        B2_CUDA(cudaEventRecord(c->st_loss, c->loss_stream));
+        B2_CUDA(cudaStreamWaitEvent(c->stream, c->st_loss, 0));
     }
     if (c->p2p && c->p2p_step > 0) {
         uint64_t mask = 0;       // gate only layers that went through the peer-memory exchange; other flags stay 0

@@ -65,6 +65,7 @@ struct TcArgs {
     int M, N;
     int tiles_m, tiles_n, splits;   // work item = (tile_m, tile_n, split); tile_m counts (128 * NCTA)-row tiles
     int group_m;                    // rasterisation group (see decode_tile)
+    int serp;                       // 1: odd groups walk the column tiles backwards (see decode_tile)
     int k_blocks;                   // K blocks per split
     int k_blocks_total;
     int a_mn0, a_k0, b_mn0, b_k0;
@@ -88,17 +89,20 @@ struct TcArgs {
 // fastest, then the column-tile index, so the ~148 tiles in flight at any time touch about group_m panels of A and
 // 148 / group_m panels of B.  group_m = 1 sweeps all column tiles of one row-tile first (B stays L2 resident when it is
 // the small operand, e.g. the weights in forward / backprop); large group_m approaches row-fastest order.
+// serp: odd groups walk the column tiles backwards, so the B panels one group ended on are the ones the next starts on.
 // n_rot (fused reduce-scatter): the column-tile index is rotated by (rank + 1) owners' worth of tiles, so at any moment
 // the ranks are storing to DIFFERENT owners (no incast on one GPU's NVLink ingress) and each rank's own tiles — plain
 // local stores — come last, where the epilogue of the final wave is no longer hidden behind MMAs.
-__device__ __forceinline__ void decode_tile(int rem, int tiles_m, int tiles_n, int group_m, int n_rot, int& tile_m, int& tile_n) {
+__device__ __forceinline__ void decode_tile(int rem, int tiles_m, int tiles_n, int group_m, int n_rot, int serp, int& tile_m, int& tile_n) {
     const int per_group = group_m * tiles_n;
     const int g = rem / per_group;
     const int first_m = g * group_m;
     const int gsize = min(group_m, tiles_m - first_m);
     const int in_g = rem - g * per_group;
     tile_m = first_m + in_g % gsize;
-    tile_n = in_g / gsize + n_rot;
+    int tn = in_g / gsize;
+    if (serp && (g & 1)) tn = tiles_n - 1 - tn;
+    tile_n = tn + n_rot;
     if (tile_n >= tiles_n) tile_n -= tiles_n;
 }
 
@@ -247,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t ph = 0;
         for (int w = worker; w < total_work; w += n_workers) {
             const int split = w / tiles_mn, rem = w - split * tiles_mn;
-            int tile_m, tile_n; decode_tile(rem, p.tiles_m, p.tiles_n, p.group_m, p.n_rot, tile_m, tile_n);
+            int tile_m, tile_n; decode_tile(rem, p.tiles_m, p.tiles_n, p.group_m, p.n_rot, p.serp, tile_m, tile_n);
             const int m0 = (tile_m * NCTA + int(rank)) * BM;          // this CTA's 128 rows of A
             const int n0 = tile_n * BN + int(rank) * B_ROWS;          // this CTA's share of B
             const int kb0 = split * p.k_blocks;
@@ -376,7 +380,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int t = 0;
         for (int w = worker; w < total_work; w += n_workers, ++t) {
             const int split = w / tiles_mn, rem = w - split * tiles_mn;
-            int tile_m, tile_n; decode_tile(rem, p.tiles_m, p.tiles_n, p.group_m, p.n_rot, tile_m, tile_n);
+            int tile_m, tile_n; decode_tile(rem, p.tiles_m, p.tiles_n, p.group_m, p.n_rot, p.serp, tile_m, tile_n);
             const int m = (tile_m * NCTA + int(rank)) * BM + q * 32 + lane;
             const int n0 = tile_n * BN;
             const bool m_ok = m < p.M;
@@ -836,12 +840,17 @@ cudaError_t tc_plan_launch(const TcPlan& pl, cudaStream_t stream, const TcWait* 
     a.M = g.M; a.N = g.N; a.d_trans = g.d_trans ? 1 : 0;
     a.tiles_m = pl.tiles_m; a.tiles_n = pl.tiles_n; a.splits = pl.splits;
     {
-        // measured on the 8192 x 4096 x 4096 contractions: 582 (row-fastest) -> 611 TFLOP/s with groups of 8-16 row-tiles
-        int gm = 16;
+        // Groups of 8 row-tiles walked serpentine (profiles/r2_tile_walk.md): against the round-1 walk (groups of 16, column
+        // tiles always ascending) the three 8192 x 4096 x 4096 contractions of config C3 read 11 % less DRAM and the
+        // sustained step is ~1 % shorter; row-fastest order (one group) costs 582 vs 611 TFLOP/s.
+        int gm = 8;
         if (const char* e = std::getenv("B2NN_TC_GROUP_M")) gm = std::atoi(e);
         if (gm < 1) gm = 1;
         if (gm > pl.tiles_m) gm = pl.tiles_m;
         a.group_m = gm;
+        a.serp = 1;
+        if (const char* e = std::getenv("B2NN_TC_SERP")) a.serp = std::atoi(e) ? 1 : 0;
+        if (a.n_rot) a.serp = 0;    // the reduce-scatter rotation fixes the column order (own tiles last)
     }
     a.k_blocks = pl.k_blocks; a.k_blocks_total = pl.k_blocks_total;
     a.a_mn0 = int(g.a_mn0); a.a_k0 = int(g.a_k0); a.b_mn0 = int(g.b_mn0); a.b_k0 = int(g.b_k0);
