@@ -60,7 +60,8 @@ def build(force: bool = False, verbose: bool = False) -> dict:
         list(ex.map(_run, jobs))
     lib = os.path.join(LIB, "libb2nn.so")
     if force or jobs or _newer(lib, objs):
-        _run([NVCC, "-shared", "-o", lib] + objs + ["-cudart", "static", "-L", os.path.join(CUDA, "lib64"), "-lcurand",
+        # the arch is named on the link line too: nvcc's device-link stub otherwise defaults to sm_52
+        _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-cudart", "static", "-L", os.path.join(CUDA, "lib64"), "-lcurand",
              "-ldl", "-Xlinker", f"-rpath={os.path.join(CUDA, 'lib64')}", "-ccbin", CXX])
     out = {"libb2nn": lib}
     facade_src = os.path.join(HOST, "cublasNN.cpp")

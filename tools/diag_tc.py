@@ -1,5 +1,5 @@
 """Bring-up diagnostic for the tcgen05 GEMM (not a test): error statistics per operand-major combination, CTA-pair
-mode and TMA box mode, then timings of the config-C3 contractions.  python tests/diag_tc.py [--perf-only]"""
+mode and TMA box mode, then timings of the config-C3 contractions.  python tools/diag_tc.py [--perf-only]"""
 import os
 import sys
 

@@ -1,4 +1,4 @@
-"""Run ONE config-C3 contraction a few times (for ncu).  python tests/prof_gemm.py <fwd0|fwd1|bwd1|bwd2|wgrad1|...> <single|pair> [reps]"""
+"""Run ONE config-C3 contraction a few times (for ncu).  python tools/prof_gemm.py <fwd0|fwd1|bwd1|bwd2|wgrad1|...> <single|pair> [reps]"""
 import os
 import sys
 
