@@ -339,7 +339,13 @@ int ensure_acc(b2nn_ctx* c, int slots) {
     return B2NN_OK;
 }
 
+static int ensure_workspace_impl(b2nn_ctx* c, int64_t rows, bool custom, bool want_lo);
 int ensure_workspace(b2nn_ctx* c, int64_t rows, bool custom, bool want_lo = false) {
+    const int rc = ensure_workspace_impl(c, rows, custom, want_lo);
+    if (rc) { c->ws.release(); c->plans.clear(); }     // a half-built workspace must not claim its capacity
+    return rc;
+}
+static int ensure_workspace_impl(b2nn_ctx* c, int64_t rows, bool custom, bool want_lo) {
     Workspace& w = c->ws;
     const int nl = int(c->layers.size());
     const bool need_z = custom && w.z.empty();
@@ -1341,7 +1347,7 @@ int b2nn_create(b2nn_ctx** out, int device) {
     if (rc) { set_error(why); return rc; }
     if (device < 0) cudaGetDevice(&device);
     B2_CUDA(cudaSetDevice(device));
-    std::unique_ptr<b2nn_ctx> c(new b2nn_ctx);
+    struct CtxGuard { b2nn_ctx* p; ~CtxGuard() { if (p) b2nn_destroy(p); } b2nn_ctx* operator->() const { return p; } } c{new b2nn_ctx};
     c->device = device;
     B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamDefault));          // blocking: orders with user ops on stream 0
     B2_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
@@ -1349,7 +1355,8 @@ int b2nn_create(b2nn_ctx** out, int device) {
         set_error("curandCreateGenerator failed"); return B2NN_ERR_CUDA;
     }
     curandSetStream(c->gen, c->stream);
-    *out = c.release();
+    *out = c.p;
+    c.p = nullptr;
     return B2NN_OK;
 }
 
@@ -1412,6 +1419,9 @@ int b2nn_set_layers(b2nn_ctx* c, const int* layers, int n_layers, int init_kind,
         set_error("bad init_kind"); return B2NN_ERR_ARG;
     }
     B2_CUDA(cudaSetDevice(c->device));
+    // Peer-memory exchange: peers hold IPC mappings of the arenas about to be freed.  Collective teardown (every rank
+    // calls set_layers): close what this rank imported, meet at a barrier, only then free what it exported.
+    if (int rc = p2p_teardown(c)) return rc;
     c->layers.assign(layers, layers + n_layers);
     c->L.assign(n_layers - 1, LayerInfo());
     c->total_ref = 0; c->total_int = 0;
@@ -1424,9 +1434,6 @@ int b2nn_set_layers(b2nn_ctx* c, const int* layers, int n_layers, int init_kind,
         c->total_ref += li.ref_size;
         c->total_int += li.ldw * li.out;      // multiple of 4 floats: every layer block starts 16-byte aligned
     }
-    // Peer-memory exchange: peers hold IPC mappings of the arenas about to be freed.  Collective teardown (every rank
-    // calls set_layers): close what this rank imported, meet at a barrier, only then free what it exported.
-    if (int rc = p2p_teardown(c)) return rc;
     release_staging(c);       // sized for the old input / output widths (their ones row sits at the old index n)
     cudaFree(c->W); cudaFree(c->V); cudaFree(c->G); cudaFree(c->W_lo);
     c->W = c->V = c->G = c->W_lo = nullptr; c->w_lo_valid = false;
@@ -1445,18 +1452,19 @@ int b2nn_set_layers(b2nn_ctx* c, const int* layers, int n_layers, int init_kind,
     c->g_zero = false;        // a fresh arena: the first step zeroes what it accumulates into
 
     // One uniform draw over the whole reference-layout arena, then the per-layer rescale (cublasNN.cpp:314-326).
-    float* ref = nullptr;
-    B2_CUDA(cudaMalloc(&ref, sizeof(float) * c->total_ref));
+    DevBuf refbuf;
+    B2_CUDA(cudaMalloc(&refbuf.p, sizeof(float) * c->total_ref));
+    float* const ref = refbuf.as<float>();
     const unsigned long long s = seed_is_clock ? (unsigned long long)clock() : (unsigned long long)seed;   // :27
     curandSetPseudoRandomGeneratorSeed(c->gen, s);
     curandSetGeneratorOffset(c->gen, 0ULL);
     if (curandGenerateUniform(c->gen, ref, size_t(c->total_ref)) != CURAND_STATUS_SUCCESS) {
-        cudaFree(ref); set_error("curandGenerateUniform failed"); return B2NN_ERR_CUDA;
+        set_error("curandGenerateUniform failed"); return B2NN_ERR_CUDA;
     }
     for (int j = 0; j < n_layers - 1; ++j) {
         const LayerInfo& li = c->L[j];
         if (init_kind == B2NN_INIT_CUSTOM) {
-            if (li.ref_size > INT32_MAX) { cudaFree(ref); set_error("custom init: layer too large for int count"); return B2NN_ERR_ARG; }
+            if (li.ref_size > INT32_MAX) { set_error("custom init: layer too large for int count"); return B2NN_ERR_ARG; }
             custom_init(ref + li.ref_off, li.in + 1, li.out, int(li.ref_size));       // legacy stream, ordered by the blocking engine stream
         } else {
             B2_CUDA(init_scale_launch(ref + li.ref_off, li.in + 1, li.out, li.ref_size, init_kind, c->stream));
@@ -1468,7 +1476,6 @@ int b2nn_set_layers(b2nn_ctx* c, const int* layers, int n_layers, int init_kind,
         B2_CUDA(theta_ref_to_internal_launch(ref + li.ref_off, c->W + li.w_off, li.in, li.out, li.ldw, c->stream));
     }
     B2_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(ref);
     return B2NN_OK;
 }
 
@@ -1564,11 +1571,26 @@ int b2nn_load_checkpoint(b2nn_ctx* c, const char* path) {
     get(&has_v, 4); get(&nn, 4); get(&nw, 8);
     int64_t expect = 0;
     for (int i = 0; ok && i + 1 < nl; ++i) {
-        if (layers[size_t(i)] < 1 || layers[size_t(i + 1)] < 1) ok = false;
+        if (layers[size_t(i)] < 1 || layers[size_t(i + 1)] < 1) { ok = false; break; }
         expect += (int64_t(layers[size_t(i)]) + 1) * layers[size_t(i + 1)];
+        if (expect > (int64_t(1) << 40)) ok = false;
     }
-    if (!ok || nw != expect || nn < 0 || (nn != 0 && nn != layers[0])) { set_error("load_checkpoint: inconsistent header"); return B2NN_ERR_ARG; }
-    std::vector<float> th(static_cast<size_t>(nw)), vel(has_v ? static_cast<size_t>(nw) : 0), mean(static_cast<size_t>(nn)), sd(static_cast<size_t>(nn));
+    if (!ok || nw != expect || (has_v != 0 && has_v != 1) || nn < 0 || (nn != 0 && nn != layers[0])) {
+        set_error("load_checkpoint: inconsistent header"); return B2NN_ERR_ARG;
+    }
+    // the header must agree with the file's length before anything is sized by it
+    const long body0 = std::ftell(f);
+    if (body0 < 0 || std::fseek(f, 0, SEEK_END) != 0) { set_error("load_checkpoint: cannot seek"); return B2NN_ERR_ARG; }
+    const long flen = std::ftell(f);
+    const int64_t need = int64_t(sizeof(float)) * (nw * (1 + has_v) + 2 * int64_t(nn)) + 8;
+    if (flen < 0 || int64_t(flen) - int64_t(body0) != need || std::fseek(f, body0, SEEK_SET) != 0) {
+        set_error("load_checkpoint: truncated file or checksum mismatch"); return B2NN_ERR_ARG;
+    }
+    std::vector<float> th, vel, mean, sd;
+    try {
+        th.resize(static_cast<size_t>(nw)); vel.resize(has_v ? static_cast<size_t>(nw) : 0);
+        mean.resize(static_cast<size_t>(nn)); sd.resize(static_cast<size_t>(nn));
+    } catch (const std::bad_alloc&) { set_error("load_checkpoint: out of host memory"); return B2NN_ERR_ALLOC; }
     get(th.data(), sizeof(float) * th.size()); get(vel.data(), sizeof(float) * vel.size());
     get(mean.data(), sizeof(float) * mean.size()); get(sd.data(), sizeof(float) * sd.size());
     const uint64_t sum = h;
@@ -1891,13 +1913,15 @@ int b2nn_train_step_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, 
     const int prec = effective_precision(c, resolve_precision(d->precision), rows);
     const int n = c->layers[0], K = c->layers.back();
     if (rows > c->caps) {
-        cudaFree(c->Xs); cudaFree(c->Ys); c->Xs = c->Ys = nullptr;
-        c->caps = rows; c->lds = round_up(rows, 32);
+        drop_lo(c, c->Xs);
+        cudaFree(c->Xs); cudaFree(c->Ys); c->Xs = c->Ys = nullptr; c->caps = 0;
+        c->lds = round_up(rows, 32);
         B2_CUDA(cudaMalloc(&c->Xs, sizeof(float) * c->lds * (n + 1)));
         B2_CUDA(cudaMalloc(&c->Ys, sizeof(float) * c->lds * K));
         B2_CUDA(cudaMemsetAsync(c->Xs, 0, sizeof(float) * c->lds * (n + 1), c->stream));
         B2_CUDA(cudaMemsetAsync(c->Ys, 0, sizeof(float) * c->lds * K, c->stream));
         B2_CUDA(fill_launch(c->Xs + int64_t(n) * c->lds, 1.0f, c->lds, c->stream));
+        c->caps = rows;           // only a fully built pair of buffers claims its capacity
     }
     rc = ensure_workspace(c, rows, d->act_kind == B2NN_ACT_CUSTOM);
     if (rc) return rc;
@@ -1956,19 +1980,24 @@ int b2nn_train_host(b2nn_ctx* c, const b2nn_train_desc* d, const float* x, const
         if (!c->st_consumed[i]) B2_CUDA(cudaEventCreateWithFlags(&c->st_consumed[i], cudaEventDisableTiming));
     }
     if (last_rows > c->capst) {
-        c->capst = last_rows; c->ldst = round_up(last_rows, 32);
         for (int i = 0; i < 2; ++i) {
+            drop_lo(c, c->Xst[i]);
             cudaFree(c->Xst[i]); cudaFree(c->Yst[i]); c->Xst[i] = c->Yst[i] = nullptr;
+        }
+        c->capst = 0;
+        c->ldst = round_up(last_rows, 32);
+        for (int i = 0; i < 2; ++i) {
             B2_CUDA(cudaMalloc(&c->Xst[i], sizeof(float) * c->ldst * n_plus_1));
             B2_CUDA(cudaMalloc(&c->Yst[i], sizeof(float) * c->ldst * k));
             B2_CUDA(cudaMemsetAsync(c->Xst[i], 0, sizeof(float) * c->ldst * n_plus_1, c->stream));
             B2_CUDA(cudaMemsetAsync(c->Yst[i], 0, sizeof(float) * c->ldst * k, c->stream));
             B2_CUDA(fill_launch(c->Xst[i] + int64_t(n) * c->ldst, 1.0f, c->ldst, c->stream));
         }
+        c->capst = last_rows;     // only fully built buffers claim their capacity
     }
     if (steps > c->jsteps_cap) {
         cudaFree(c->d_jsteps); if (c->h_jsteps) cudaFreeHost(c->h_jsteps);
-        c->d_jsteps = nullptr; c->h_jsteps = nullptr;
+        c->d_jsteps = nullptr; c->h_jsteps = nullptr; c->jsteps_cap = 0;
         B2_CUDA(cudaMalloc(&c->d_jsteps, sizeof(double) * steps));
         B2_CUDA(cudaMallocHost(&c->h_jsteps, sizeof(double) * steps));
         c->jsteps_cap = steps;
@@ -2346,6 +2375,7 @@ int b2nn_comm_unique_id(void* id128) {
 int b2nn_comm_init(b2nn_ctx* c, int rank, int nranks, const void* id128) {
     if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) { set_error("comm_init: bad arguments"); return B2NN_ERR_ARG; }
     if (nranks == 1) return B2NN_OK;
+    if (c->comm) { set_error("comm_init: this context already has a communicator"); return B2NN_ERR_ARG; }
     std::call_once(g_nccl_once, load_nccl);
     if (!g_nccl_err.empty()) { set_error(g_nccl_err); return B2NN_ERR_CUDA; }
     B2_CUDA(cudaSetDevice(c->device));
@@ -2407,6 +2437,13 @@ int b2nn_comm_p2p_open(b2nn_ctx* c, const void* blobs) {
     if (!blobs) { c->p2p = false; c->plans.clear(); return B2NN_OK; }      // switch back to the NCCL path
     if (!c->p2p_flags) { set_error("p2p_open: call b2nn_comm_p2p_export first"); return B2NN_ERR_ARG; }
     B2_CUDA(cudaSetDevice(c->device));
+    if (!c->p2p_opened.empty()) {       // opened before: an IPC handle maps once per process, close the old imports first
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->upd_stream) B2_CUDA(cudaStreamSynchronize(c->upd_stream));
+        for (void* p : c->p2p_opened) cudaIpcCloseMemHandle(p);
+        c->p2p_opened.clear();
+        c->p2p = false;
+    }
     const char* b = static_cast<const char*>(blobs);
     c->peers.world = c->nranks; c->peers.rank = c->rank;
     for (int r = 0; r < c->nranks; ++r) {

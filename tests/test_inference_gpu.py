@@ -211,6 +211,20 @@ def test_checkpoint_round_trip(b2nn, oracle, tmp_path):
     open(bad, "wb").write(bytes(blob))
     with pytest.raises(b2nn.B2nnError):
         b2nn.Net().load_checkpoint(bad)
+    # a truncated file, and a header that promises far more weights than the file holds (nothing may be sized by it)
+    good = open(path, "rb").read()
+    open(bad, "wb").write(good[:len(good) - 100])
+    with pytest.raises(b2nn.B2nnError):
+        b2nn.Net().load_checkpoint(bad)
+    nl = int(np.frombuffer(good[8:12], dtype=np.int32)[0])
+    lie = bytearray(good)
+    lie[12:16] = np.int32(1 << 30).tobytes()                    # first layer width
+    lie[12 + 4 * nl + 4:12 + 4 * nl + 8] = np.int32(0).tobytes()      # no normalisation statistics: the header stays consistent
+    off_nw = 12 + 4 * nl + 8
+    lie[off_nw:off_nw + 8] = np.int64(((1 << 30) + 1) * c.layers[1] + sum((a + 1) * b for a, b in zip(c.layers[1:-1], c.layers[2:]))).tobytes()
+    open(bad, "wb").write(bytes(lie))
+    with pytest.raises(b2nn.B2nnError):
+        b2nn.Net().load_checkpoint(bad)
     net.close(); other.close()
 
 
