@@ -107,7 +107,8 @@ typedef struct b2nn_train_result {
 int  b2nn_create(b2nn_ctx** out, int device);
 void b2nn_destroy(b2nn_ctx* ctx);
 const char* b2nn_last_error(void);
-/* 1 when a usable sm_100 device is present.  Never throws; no side effects beyond CUDA runtime init. */
+/* 1 when a usable sm_100 device is present.  Never throws; no side effects beyond CUDA runtime init.  (The reference
+ * checks nothing: its constructor creates handles on whatever device 0 is, cublasNN.cpp:12-30.) */
 int  b2nn_device_ok(void);
 const char* b2nn_version(void);
 
@@ -138,7 +139,8 @@ int b2nn_set_train_data(b2nn_ctx* ctx, const float* x, const float* y, int64_t m
  * for b2nn_evaluate_raw / b2nn_predict_raw; mean_out / std_out (optional, n floats) receive them. */
 int b2nn_set_train_data_raw(b2nn_ctx* ctx, const float* x_raw, const float* y, int64_t m, int n, int k, int normalise,
                             float* mean_out, float* std_out);
-/* Install / read the statistics directly (n = 0 clears them). */
+/* Install / read the statistics directly (n = 0 clears them): the reference keeps them as host members filled by
+ * mean / stddev (cublasNN.cpp:214-268) and reuses them for the validation and prediction sets (cublasNN.cpp:191-197). */
 int b2nn_set_normalisation(b2nn_ctx* ctx, const float* mean, const float* stddev, int n);
 int b2nn_get_normalisation(b2nn_ctx* ctx, float* mean, float* stddev, int n);
 
@@ -147,11 +149,13 @@ int b2nn_get_normalisation(b2nn_ctx* ctx, float* mean, float* stddev, int n);
 int b2nn_train(b2nn_ctx* ctx, const b2nn_train_desc* desc, b2nn_log_cb log, void* log_user,
                b2nn_train_result* result);
 
-/* One mini-batch step from HOST buffers (the end-to-end path: H2D of the batch, forward, backward, update, J back).
+/* One iteration of the reference's batch loop (cublasNN.cpp:597-629 / 540-568) from HOST buffers (the end-to-end
+ * path: H2D of the batch, forward, backward, update, J back).
  * x: rows x n_plus_1, y: rows x k column-major (ld = rows).  Velocity persists across calls until
  * b2nn_reset_velocity.  global_rows: batch rows summed over all data-parallel ranks (0 => rows). */
 int b2nn_train_step_host(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x, const float* y, int64_t rows,
                          int64_t global_rows, float* J_out);
+/* velocity = 0, what every train* call of the reference starts with (cublasNN.cpp:533-534, 590-591). */
 int b2nn_reset_velocity(b2nn_ctx* ctx);
 
 /* Streaming trainer for a HOST-resident training set (it never has to fit on the device): same loop as b2nn_train,
@@ -179,12 +183,14 @@ int b2nn_evaluate_raw(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x
                       int y_is_labels, int normalise, double* cost_out, double* errors_out);
 int b2nn_predict_raw(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x_raw, int64_t rows, int normalise, float* out,
                      float* probs);
-/* Same forward with x ALREADY on the device (config 5's data-resident inference sweep). */
+/* Same forward (forwardPropagate + the output activation, cublasNN.cpp:642-661, 937-960) with x ALREADY on the device
+ * (config 5's data-resident inference sweep). */
 int b2nn_predict_device(b2nn_ctx* ctx, const b2nn_train_desc* desc, const float* x_dev, int64_t rows, int64_t ld,
                         float* out_dev);
 
 /* ---- built-in recognition ----------------------------------------------------------------------------------- */
-/* Maps the address of a built-in op (tanhGPU, softmaxGPU, ...) to its B2NN_* enum, or -1 for user code.
+/* The reference passes its ops as function pointers (cublasNN.h:42-69; activations.h, costfunctions.h,
+ * randinitweights.h).  Maps the address of a built-in op (tanhGPU, softmaxGPU, ...) to its B2NN_* enum, or -1 for user code.
  * family: 0 hidden activation, 1 its derivative, 2 output activation, 3 cost, 4 init. */
 int b2nn_builtin_kind(const void* fn, int family);
 
@@ -204,16 +210,19 @@ int b2nn_comm_p2p_export(b2nn_ctx* ctx, void* blob192);
 int b2nn_comm_p2p_open(b2nn_ctx* ctx, const void* blobs_world_x_192);   /* NULL: back to the NCCL path */
 
 /* ---- introspection ------------------------------------------------------------------------------------------ */
-/* Raw GEMM entry used by the kernel unit tests and the roofline benchmark: D(m,n) = sum_k A(m,k) B(n,k), D stored
+/* Raw GEMM entry (what the reference's cublasSgemm call sites compute, cublasNN.cpp:645-684) used by the kernel unit
+ * tests and the roofline benchmark: D(m,n) = sum_k A(m,k) B(n,k), D stored
  * at D[n*ldd + m].  a_major / b_major: 0 = K contiguous (A[m*lda+k]), 1 = M/N contiguous (A[k*lda+m]).
  * epi: 0 store, 1 sigmoid, 2 tanh, 3 multiply by sigmoid'(aux), 4 multiply by tanh'(aux) with aux = activation values
  * laid out like D.  All pointers are device pointers.  backend: 0 fp32 FFMA, 1 tcgen05 tf32, 3 tcgen05 tf32 where
  * the caller guarantees 32 floats of readable slack after every row of an M/N-contiguous operand (one TMA box per
  * tile instead of one per 32-float atom); 5 / 7 = the same two with the fp32-grade 3xTF32 arithmetic (operand low
- * parts are split into temporaries inside the call). */
+ * parts are split into temporaries inside the call); 9 / 11 = the same two on bf16 copies of the operands (kind::f16,
+ * fp32 accumulation). */
 int b2nn_gemm(b2nn_ctx* ctx, int backend, const float* A, int64_t lda, int a_major, const float* B, int64_t ldb,
               int b_major, float* D, int64_t ldd, int M, int N, int K, int epi, const float* aux, int64_t ldaux);
-/* Momentum update kernel alone: v = mu*v + alpha*g ; theta = theta + v over count elements (device pointers). */
+/* Momentum update kernel alone (the reference's two cublasSgeam per layer, cublasNN.cpp:558-566, 619-627):
+ * v = mu*v + alpha*g ; theta = theta + v over count elements (device pointers). */
 int b2nn_momentum_update(b2nn_ctx* ctx, float* theta, float* vel, const float* grad, int64_t count, float mu,
                          float alpha);
 void* b2nn_stream(b2nn_ctx* ctx);   /* cudaStream_t the engine launches on */
