@@ -80,13 +80,16 @@ struct cublasNN::Impl {
     bool x_norm = false, xv_norm = false, xp_norm = false;                  // normalise*Data was called
     b2nn_train_result last{};
 
+    // No usable sm_100 device: there is no CPU path and nothing after this point can work.  The reference would print
+    // "cudaMalloc Failed" and carry on with null pointers (cublasNN.cpp:309, 366); here the failure is an exception, so an
+    // unmodified main.cpp stops with a message and a non-zero status instead of reporting results it never computed.
     bool ensure_ctx() {
         if (ctx) return true;
-        if (ctx_failed) return false;
-        if (b2nn_create(&ctx, -1) != B2NN_OK) {
+        if (ctx_failed || b2nn_create(&ctx, -1) != B2NN_OK) {
             ctx_failed = true;
-            std::cout << "b2nn: " << b2nn_last_error() << std::endl;
-            return false;
+            const std::string why = std::string("b2nn: ") + b2nn_last_error();
+            std::cerr << why << std::endl;
+            throw std::runtime_error(why);
         }
         return true;
     }

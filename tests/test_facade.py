@@ -47,6 +47,25 @@ def _write_csv(path, a, fmt):
     np.savetxt(path, a, delimiter=",", fmt=fmt)
 
 
+def test_facade_program_fails_loudly_without_a_gpu(tmp_path, b2nn):
+    """No sm_100 device: a program written against class cublasNN must stop with a message and a non-zero status — never
+    run to the end on a CPU path or print results it did not compute."""
+    if b2nn.lib().b2nn_device_ok():
+        pytest.skip("a usable GPU is present")
+    if not os.path.exists(os.path.join(LIB, "libcublasNN_b200.so")):
+        pytest.skip("facade not built")
+    rng = np.random.default_rng(0)
+    _write_csv(tmp_path / "trainX.csv", rng.integers(0, 255, size=(40, 784)), "%d")
+    _write_csv(tmp_path / "trainY.csv", rng.integers(0, 10, size=(40, 1)), "%d")
+    exe = tmp_path / "mnist_example"
+    _build(os.path.join(ROOT, "examples", "mnist_example.cpp"), str(exe))
+    r = subprocess.run([str(exe), str(tmp_path / "trainX.csv"), str(tmp_path / "trainY.csv"), "2", "5", "42"],
+                       capture_output=True, text=True, cwd=tmp_path, timeout=120)
+    assert r.returncode != 0, r.stdout[-1000:]
+    assert "b2nn: no" in r.stderr, r.stderr[-1000:]
+    assert "Final Cost" not in r.stdout and "errors" not in r.stdout, r.stdout[-1000:]
+
+
 @pytest.mark.gpu
 def test_bikeshare_example_matches_oracle(tmp_path, oracle):
     """Config C2 end to end through the class API (CSV -> normalise -> train -> validate -> predict), fp32 mode,
